@@ -1,0 +1,129 @@
+// common.cuh — shared plumbing for the sm_100a kernels behind include/ppo_b200.h.
+//
+// Error convention: the reference checks nothing in release and sync+exit(1)s in
+// debug (include/cuda_helper.h:4-19).  Here every CUDA/NCCL return is checked and a failure prints
+// file:line and aborts.  There is deliberately NO CPU fallback anywhere in this directory.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "ppo_b200.h"
+
+#define B200_FATAL(...)                                                         \
+    do {                                                                        \
+        fprintf(stderr, "ppo_b200 fatal (%s:%d): ", __FILE__, __LINE__);         \
+        fprintf(stderr, __VA_ARGS__);                                           \
+        fprintf(stderr, "\n*** FAILED - ABORTING\n");                           \
+        abort();                                                                \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                        \
+    do {                                                                        \
+        cudaError_t err__ = (expr);                                             \
+        if (err__ != cudaSuccess) B200_FATAL("%s -> %s", #expr, cudaGetErrorString(err__)); \
+    } while (0)
+
+namespace b200 {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- runtime state (runtime.cu) ---------------------------------------------------------------
+cudaStream_t stream();            // the stream every kernel of this library is launched on
+void ensure_device();             // aborts when no CUDA device is usable
+extern unsigned long long g_launches;
+int num_sms();
+
+// Grow-only device scratch, keyed by slot, so hot paths never cudaMalloc (the reference mallocs per
+// minibatch, src/loss.cu:51, src/ppo.cu:150).
+enum ScratchSlot { kScratchGae = 0, kScratchGaeV, kScratchGaeVNext, kScratchLoss, kScratchStage,
+                   kScratchStage2, kScratchStage3, kScratchPartials, kScratchMisc, kScratchSlots };
+void* scratch(ScratchSlot slot, size_t bytes);
+void* scratch_zeroed_once(ScratchSlot slot, size_t bytes);  // zero-filled when (re)allocated only
+
+template <typename T>
+T* dmalloc(size_t count) {
+    ensure_device();
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 4));
+    return static_cast<T*>(p);
+}
+template <typename T>
+T* hmalloc_pinned(size_t count) {
+    ensure_device();
+    void* p = nullptr;
+    CUDA_CHECK(cudaHostAlloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 4, cudaHostAllocPortable | cudaHostAllocMapped));
+    return static_cast<T*>(p);
+}
+
+#define B200_LAUNCH(kernel, grid, block, smem, ...)                              \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), ::b200::stream()>>>(__VA_ARGS__);      \
+        ++::b200::g_launches;                                                    \
+        CUDA_CHECK(cudaGetLastError());                                          \
+    } while (0)
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// streaming 128-bit loads/stores that do not allocate in L1 (data touched once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+enum Act { kActNone = 0, kActRelu = 1, kActTanh = 2 };
+inline int act_code(const char* name) {
+    if (name && strcmp(name, "relu") == 0) return kActRelu;
+    if (name && strcmp(name, "tanh") == 0) return kActTanh;
+    return kActNone;  // src/activation_function.cu:49-55: anything else is the identity
+}
+__device__ __forceinline__ float act_apply(float x, int act) {
+    if (act == kActRelu) return x > 0.f ? x : 0.f;
+    if (act == kActTanh) return tanhf(x);
+    return x;
+}
+// derivative expressed through the POST-activation value y (src/activation_function.cu:11-15)
+__device__ __forceinline__ float act_grad(float y, float g, int act) {
+    if (act == kActRelu) return y > 0.f ? g : 0.f;
+    if (act == kActTanh) return g * (1.f - y * y);
+    return g;
+}
+
+}  // namespace b200

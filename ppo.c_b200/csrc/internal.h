@@ -1,0 +1,135 @@
+// internal.h — C++ interfaces between the translation units of libppo_b200.so (not exported).
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+// Stage host arrays through device scratch, run `fn` on device pointers, copy outputs back.
+struct HostStage {
+    struct Item { void* host; size_t bytes; bool in, out; void* dev; };
+    std::vector<Item> items;
+    void* add(const void* host, size_t bytes, bool in, bool out) {
+        items.push_back({const_cast<void*>(host), bytes, in, out, nullptr});
+        return nullptr;
+    }
+    void upload() {
+        size_t total = 0;
+        for (auto& it : items) total += (it.bytes + 255) & ~size_t(255);
+        char* base = static_cast<char*>(scratch(kScratchStage, total));
+        size_t off = 0;
+        for (auto& it : items) {
+            it.dev = base + off;
+            off += (it.bytes + 255) & ~size_t(255);
+            if (it.in) CUDA_CHECK(cudaMemcpyAsync(it.dev, it.host, it.bytes, cudaMemcpyHostToDevice, stream()));
+        }
+    }
+    void download() {
+        for (auto& it : items)
+            if (it.out) CUDA_CHECK(cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, stream()));
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+    }
+    template <typename T> T* dev(int i) { return static_cast<T*>(items[i].dev); }
+};
+
+
+// ---- gae.cu -----------------------------------------------------------------------------------
+struct GaeWork {
+    double* stats_d;   // device {mean, M2, n}
+    float* stats_f;    // device {mean, std}
+    float4* wstats;
+    int nchunks;
+};
+GaeWork gae_scan(const float* reward, const float* v, const float* v_next, const bool* terminated,
+                 const bool* truncated, int n, float gamma, float lambda, float* advantage,
+                 float* adv_target);
+void gae_merge_ranks(const double* triples_dev, int world, float* stats_f);
+void gae_normalize(float* advantage, int n, const float* stats_f);
+
+// ---- adam.cu ----------------------------------------------------------------------------------
+// w,g,m,v flat device vectors.  If partials != nullptr the gradient is first formed as the
+// fixed-order sum over `splits` slabs of length `stride` (deterministic split-K reduction) and
+// written to g.
+void adam_flat(float* w, float* g, float* m, float* v, int n, float lr, float beta1, float beta2,
+               int time_step, const float* partials, int splits, size_t stride);
+void reduce_partials(float* g, const float* partials, int splits, size_t stride, int n);
+
+// ---- gemm.cu ----------------------------------------------------------------------------------
+// y[m][l] = act(x[m][n] . W[l][n]^T + b[l])            (reference mat_mul.cu:132-163 + activation)
+void linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act);
+// gx[m][n] = (g[m][l] . W[l][n]) * act'(xin)  where xin[m][n] is the POST-activation input of this
+// layer produced with activation `act_prev` (kActNone: no mask).      (mat_mul.cu:175-188 + K8)
+void linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev);
+// partial dW / db slabs: for split s, rows [s*rows_per_split, ...): gW_part[s][l][n] = g^T . x,
+// gb_part[s][l] = column sums of g.  Slab s of layer tensor lives at part + s*stride.  (mat_mul.cu:195-208, K9)
+void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int splits, const float* g,
+                            const float* x, int m, int n, int l);
+int choose_splits(int m, size_t param_count);
+void activation_inplace(float* x, long long count, int act);
+void activation_grad_inplace(const float* y, float* grad, long long count, int act);
+
+// ---- nn.cu ------------------------------------------------------------------------------------
+struct NetDev {               // device-side view of one NeuralNetwork (side table keyed by pointer)
+    int num_layers = 0;       // reference convention: number of sizes (weight layers = num_layers-1)
+    std::vector<int> sizes;
+    std::vector<int> acts;
+    float* params = nullptr;  // flat arena W0,b0,W1,b1,...
+    float* grads = nullptr;
+    size_t param_count = 0;
+    std::vector<size_t> w_off, b_off;
+    // activation cache: layer inputs; act[0] is either owned copy or borrowed pointer
+    std::vector<float*> a;    // a[i] : [cap][sizes[i]]
+    std::vector<float*> gx;   // gradient wrt a[i]
+    int cap_fwd = 0, cap_bwd = 0;
+    bool a0_borrowed = false;
+    float* a0_owned = nullptr;
+    int a0_cap = 0;
+    float* partials = nullptr;   // [splits][param_count]
+    size_t partials_cap = 0;     // floats
+    int last_splits = 1;
+    int last_m = 0;
+};
+NetDev* net_dev(NeuralNetwork* nn);
+// forward without copying the input (training path); output = a.back()
+void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input);
+// backward from grad wrt output (device, [m][out]); leaves split-K slabs in nd->partials
+void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m);
+void net_reduce_grads(NeuralNetwork* nn);   // partials -> nd->grads (fixed order)
+
+// ---- policy.cu --------------------------------------------------------------------------------
+void launch_log_prob(const float* mu, const float* log_std, const float* action, float* out, int m, int A);
+// fused value head: grad[i] = 2 (y-t)/m_total ; loss_slot += sum (t-y)^2 / m_total
+void launch_value_head(const float* y, const float* target, float* grad, int m, int m_total, float* loss_slot);
+// fused policy head (src/policy.cu:91-111 + src/ppo.cu:82-107): log-prob, clipped surrogate,
+// grad_mu[m][A], grad_log_std[A] (+ entropy grad), loss
+void launch_policy_head(const float* mu, const float* log_std, const float* action, const float* logp_old,
+                        const float* adv, int m, int A, int m_total, float epsilon, float ent_coeff,
+                        float* logp_out, float* grad_mu, float* grad_log_std, float* loss_slot);
+
+// ---- buffer.cu --------------------------------------------------------------------------------
+void launch_gather(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* state,
+                   const float* action, const float* logprob, const float* advantage, const float* adv_target,
+                   float* states, float* actions, float* logprobs, float* advantages, float* adv_targets);
+void host_shuffle(int* idx, int limit);   // the reference's rand() swap chain, trajectory_buffer.cu:132-141
+
+// ---- env.cu -----------------------------------------------------------------------------------
+struct DeviceEnv;
+DeviceEnv* as_device_env(Env* env);
+int device_env_count(DeviceEnv* e);
+// fused rollout: T steps for every env; writes the env-major buffer (index = env*T + t)
+void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buffer, int T,
+                    const float* obs_mean, const float* obs_inv_std, float* return_stats /* dev: sum, episodes */);
+void launch_sample_action(GaussianPolicy* policy, const float* state_hostmapped, float* action_hostmapped,
+                          float* logprob_hostmapped, const int* rand_draws, int n_draws);
+
+// ---- dist.cu ----------------------------------------------------------------------------------
+bool dist_active();
+int dist_rank();
+int dist_world();
+int dist_shard_mode();
+void dist_allreduce_sum(float* buf, size_t count);
+void dist_allgather_doubles(const double* send, double* recv, int count_per_rank);
+
+}  // namespace b200

@@ -1,0 +1,340 @@
+// nn.cu — the NeuralNetwork object behind include/neural_network.h.
+//
+// Mirrors create/forward/backward/save/load of reference src/neural_network.cu, with a different
+// memory design: all parameters of a net live in ONE device arena (W0,b0,W1,b1,...), gradients in a
+// second one, `layers[i].d_*` are slices of them.  Activation buffers grow monotonically (the
+// reference frees and reallocates them whenever the batch size changes, src/neural_network.cu:76-89).
+#include <unordered_map>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200 {
+
+static std::unordered_map<NeuralNetwork*, NetDev*> g_nets;
+
+NetDev* net_dev(NeuralNetwork* nn) {
+    auto it = g_nets.find(nn);
+    if (it == g_nets.end()) B200_FATAL("NeuralNetwork %p was not created by this library", (void*)nn);
+    return it->second;
+}
+
+static void attach_device(NeuralNetwork* nn) {
+    ensure_device();
+    NetDev* nd = new NetDev();
+    const int L = nn->num_layers - 1;
+    nd->num_layers = nn->num_layers;
+    size_t off = 0;
+    for (int i = 0; i < L; i++) {
+        nd->sizes.push_back(nn->layers[i].input_size);
+        nd->acts.push_back(act_code(nn->activation_functions[i]));
+        nd->w_off.push_back(off);
+        off += (size_t)nn->layers[i].input_size * nn->layers[i].output_size;
+        nd->b_off.push_back(off);
+        off += nn->layers[i].output_size;
+    }
+    nd->sizes.push_back(nn->output_size);
+    nd->param_count = off;
+    nd->params = dmalloc<float>(off);
+    nd->grads = dmalloc<float>(off);
+    CUDA_CHECK(cudaMemsetAsync(nd->grads, 0, off * sizeof(float), stream()));
+    nd->a.assign(nn->num_layers, nullptr);
+    nd->gx.assign(nn->num_layers, nullptr);
+    for (int i = 0; i < L; i++) {
+        nn->layers[i].d_weights = nd->params + nd->w_off[i];
+        nn->layers[i].d_biases = nd->params + nd->b_off[i];
+        nn->layers[i].d_grad_weights = nd->grads + nd->w_off[i];
+        nn->layers[i].d_grad_biases = nd->grads + nd->b_off[i];
+        nn->layers[i].d_activation_function = build_activation_function_cuda(nn->activation_functions[i]);
+        nn->layers[i].d_input = nullptr;
+        nn->layers[i].d_grad_x = nullptr;
+    }
+    nn->layers[L].d_input = nullptr;
+    nn->layers[L].d_grad_x = nullptr;
+    nn->d_output = nullptr;
+    nn->cache_m_forward = 0;
+    nn->cache_m_backward = 0;
+    nn->cublas_handle = nullptr;
+    g_nets[nn] = nd;
+}
+
+static void ensure_fwd_capacity(NeuralNetwork* nn, NetDev* nd, int m) {
+    if (m <= nd->cap_fwd) return;
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    const int cap = m + m / 8;
+    for (int i = 1; i < nn->num_layers; i++) {
+        if (nd->a[i]) CUDA_CHECK(cudaFree(nd->a[i]));
+        nd->a[i] = dmalloc<float>((size_t)cap * nd->sizes[i]);
+        nn->layers[i].d_input = nd->a[i];
+    }
+    nd->cap_fwd = cap;
+}
+
+static void ensure_bwd_capacity(NeuralNetwork* nn, NetDev* nd, int m) {
+    if (m <= nd->cap_bwd) return;
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    const int cap = m + m / 8;
+    for (int i = 1; i < nn->num_layers; i++) {   // gradient wrt layer-0 input is never formed
+        if (nd->gx[i]) CUDA_CHECK(cudaFree(nd->gx[i]));
+        nd->gx[i] = dmalloc<float>((size_t)cap * nd->sizes[i]);
+        nn->layers[i].d_grad_x = nd->gx[i];
+    }
+    nd->cap_bwd = cap;
+}
+
+void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input) {
+    NetDev* nd = net_dev(nn);
+    ensure_fwd_capacity(nn, nd, m);
+    const int L = nn->num_layers - 1;
+    if (borrow_input) {
+        nd->a[0] = const_cast<float*>(input);
+        nd->a0_borrowed = true;
+    } else {   // the reference keeps a private copy of the input (src/neural_network.cu:81)
+        if (m > nd->a0_cap) {
+            CUDA_CHECK(cudaStreamSynchronize(stream()));
+            if (nd->a0_owned) CUDA_CHECK(cudaFree(nd->a0_owned));
+            nd->a0_cap = m + m / 8;
+            nd->a0_owned = dmalloc<float>((size_t)nd->a0_cap * nd->sizes[0]);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(nd->a0_owned, input, (size_t)m * nd->sizes[0] * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
+        nd->a[0] = nd->a0_owned;
+        nd->a0_borrowed = false;
+    }
+    nn->layers[0].d_input = nd->a[0];
+    for (int i = 0; i < L; i++)
+        linear_forward(nd->a[i + 1], nd->a[i], nd->params + nd->w_off[i], nd->params + nd->b_off[i], m,
+                       nd->sizes[i], nd->sizes[i + 1], nd->acts[i]);
+    nn->cache_m_forward = m;
+    nd->last_m = m;
+    nn->d_output = nd->a[L];
+}
+
+void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
+    NetDev* nd = net_dev(nn);
+    if (m != nd->last_m) B200_FATAL("backward with m=%d after forward with m=%d", m, nd->last_m);
+    ensure_bwd_capacity(nn, nd, m);
+    const int L = nn->num_layers - 1;
+    const int splits = choose_splits(m, nd->param_count);
+    const size_t need = (size_t)splits * nd->param_count;
+    if (need > nd->partials_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
+        nd->partials = dmalloc<float>(need);
+        nd->partials_cap = need;
+    }
+    nd->last_splits = splits;
+    // gradient wrt the output, with the output activation's derivative (src/neural_network.cu:199-201)
+    const float* g = grad_out;
+    if (nd->acts[L - 1] != kActNone) {
+        CUDA_CHECK(cudaMemcpyAsync(nd->gx[L], grad_out, (size_t)m * nd->sizes[L] * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
+        activation_grad_inplace(nd->a[L], nd->gx[L], (long long)m * nd->sizes[L], nd->acts[L - 1]);
+        g = nd->gx[L];
+    }
+    for (int i = L - 1; i >= 0; i--) {
+        const int n = nd->sizes[i], l = nd->sizes[i + 1];
+        linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->param_count, splits, g,
+                               nd->a[i], m, n, l);
+        if (i > 0) {  // dX of layer 0 is unused by every caller (the reference computes it anyway)
+            linear_backward_input(nd->gx[i], g, nd->params + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
+            g = nd->gx[i];
+        }
+    }
+    nn->cache_m_backward = m;
+}
+
+void net_reduce_grads(NeuralNetwork* nn) {
+    NetDev* nd = net_dev(nn);
+    reduce_partials(nd->grads, nd->partials, nd->last_splits, nd->param_count, (int)nd->param_count);
+}
+
+static NeuralNetwork* alloc_host_net(int num_layers) {
+    NeuralNetwork* nn = (NeuralNetwork*)malloc(sizeof(NeuralNetwork));
+    nn->num_layers = num_layers;
+    nn->layers = (Layer*)calloc(num_layers, sizeof(Layer));   // one extra slot, as the reference
+    nn->activation_functions = (char**)malloc((num_layers - 1) * sizeof(char*));
+    nn->output = nullptr;
+    nn->d_output = nullptr;
+    return nn;
+}
+
+static void alloc_host_layer(NeuralNetwork* nn, int i, int in, int out) {
+    Layer& L = nn->layers[i];
+    L.input_size = in;
+    L.output_size = out;
+    L.weights = (float*)malloc((size_t)in * out * sizeof(float));
+    L.biases = (float*)malloc((size_t)out * sizeof(float));
+    L.grad_weights = (float*)calloc((size_t)in * out, sizeof(float));
+    L.grad_biases = (float*)calloc(out, sizeof(float));
+    L.activation_function = build_activation_function(nn->activation_functions[i]);
+    L.input = nullptr;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+// src/neural_network.cu:6-72.  The initialiser consumes glibc rand() in the reference's order
+// (per layer: all W then all b) and in its float arithmetic, so a seeded srand() reproduces the
+// reference's initial weights bit for bit (host-side integer->float setup, not a compute path).
+NeuralNetwork* create_neural_network(int* layer_sizes, char** activation_functions, int num_layers) {
+    NeuralNetwork* nn = alloc_host_net(num_layers);
+    for (int i = 0; i < num_layers - 1; i++) nn->activation_functions[i] = strdup(activation_functions[i]);
+    for (int i = 0; i < num_layers - 1; i++) {
+        alloc_host_layer(nn, i, layer_sizes[i], layer_sizes[i + 1]);
+        const float gain = i == num_layers - 2 ? 1 : sqrtf(2.0);
+        const float std = gain * sqrtf(2.0 / (layer_sizes[i] + layer_sizes[i + 1]));
+        for (int j = 0; j < layer_sizes[i] * layer_sizes[i + 1]; j++)
+            nn->layers[i].weights[j] = (2 * (float)rand() / RAND_MAX - 1) * sqrtf(3.0) * std;
+        for (int j = 0; j < layer_sizes[i + 1]; j++)
+            nn->layers[i].biases[j] = (2 * (float)rand() / RAND_MAX - 1) * (1. / sqrtf(layer_sizes[i]));
+    }
+    nn->layers[num_layers - 1].input_size = layer_sizes[num_layers - 1];
+    nn->output_size = nn->layers[num_layers - 2].output_size;
+    attach_device(nn);
+    nn_write_weights_to_device(nn);
+    return nn;
+}
+
+void free_neural_network(NeuralNetwork* nn) {
+    if (!nn) return;
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    auto it = g_nets.find(nn);
+    if (it != g_nets.end()) {
+        NetDev* nd = it->second;
+        CUDA_CHECK(cudaFree(nd->params));
+        CUDA_CHECK(cudaFree(nd->grads));
+        for (int i = 1; i < nn->num_layers; i++) {
+            if (nd->a[i]) CUDA_CHECK(cudaFree(nd->a[i]));
+            if (nd->gx[i]) CUDA_CHECK(cudaFree(nd->gx[i]));
+        }
+        if (nd->a0_owned) CUDA_CHECK(cudaFree(nd->a0_owned));
+        if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
+        delete nd;
+        g_nets.erase(it);
+    }
+    for (int i = 0; i < nn->num_layers - 1; i++) {
+        free(nn->layers[i].weights);
+        free(nn->layers[i].biases);
+        free(nn->layers[i].grad_weights);
+        free(nn->layers[i].grad_biases);
+        free(nn->layers[i].input);
+        free(nn->layers[i].activation_function);
+        free(nn->layers[i].d_activation_function);
+        free(nn->activation_functions[i]);
+    }
+    free(nn->activation_functions);
+    free(nn->layers);
+    free(nn->output);
+    free(nn);
+}
+
+void nn_write_weights_to_device(NeuralNetwork* nn) {   // src/neural_network.cu:233-239
+    NetDev* nd = net_dev(nn);
+    for (int i = 0; i < nn->num_layers - 1; i++) {
+        const Layer& L = nn->layers[i];
+        CUDA_CHECK(cudaMemcpyAsync(nd->params + nd->w_off[i], L.weights, (size_t)L.input_size * L.output_size * sizeof(float), cudaMemcpyHostToDevice, stream()));
+        CUDA_CHECK(cudaMemcpyAsync(nd->params + nd->b_off[i], L.biases, (size_t)L.output_size * sizeof(float), cudaMemcpyHostToDevice, stream()));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+void nn_write_weights_to_host(NeuralNetwork* nn) {     // src/neural_network.cu:241-247
+    NetDev* nd = net_dev(nn);
+    for (int i = 0; i < nn->num_layers - 1; i++) {
+        const Layer& L = nn->layers[i];
+        CUDA_CHECK(cudaMemcpyAsync(L.weights, nd->params + nd->w_off[i], (size_t)L.input_size * L.output_size * sizeof(float), cudaMemcpyDeviceToHost, stream()));
+        CUDA_CHECK(cudaMemcpyAsync(L.biases, nd->params + nd->b_off[i], (size_t)L.output_size * sizeof(float), cudaMemcpyDeviceToHost, stream()));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+void forward_propagation_cuda(NeuralNetwork* nn, float* input, int m) {   // src/neural_network.cu:74-105
+    net_forward(nn, input, m, /*borrow_input=*/false);
+}
+
+void backward_propagation_cuda(NeuralNetwork* nn, float* grad_in, int m) { // src/neural_network.cu:121-161
+    net_backward_partials(nn, grad_in, m);
+    net_reduce_grads(nn);
+}
+
+// Host-pointer twins (src/neural_network.cu:163-231): device weights are refreshed from the host
+// arrays (the host twins of the reference read layers[i].weights), input is staged, nn->output and
+// the host gradient arrays are filled on return.
+void forward_propagation(NeuralNetwork* nn, float* input, int m) {
+    NetDev* nd = net_dev(nn);
+    nn_write_weights_to_device(nn);
+    float* d_in = static_cast<float*>(scratch(kScratchStage2, (size_t)m * nd->sizes[0] * sizeof(float)));
+    CUDA_CHECK(cudaMemcpyAsync(d_in, input, (size_t)m * nd->sizes[0] * sizeof(float), cudaMemcpyHostToDevice, stream()));
+    net_forward(nn, d_in, m, false);
+    free(nn->output);
+    nn->output = (float*)malloc((size_t)m * nn->output_size * sizeof(float));
+    CUDA_CHECK(cudaMemcpyAsync(nn->output, nn->d_output, (size_t)m * nn->output_size * sizeof(float), cudaMemcpyDeviceToHost, stream()));
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+void backward_propagation(NeuralNetwork* nn, float* grad_in, int m) {
+    NetDev* nd = net_dev(nn);
+    float* d_g = static_cast<float*>(scratch(kScratchStage2, (size_t)m * nn->output_size * sizeof(float)));
+    CUDA_CHECK(cudaMemcpyAsync(d_g, grad_in, (size_t)m * nn->output_size * sizeof(float), cudaMemcpyHostToDevice, stream()));
+    net_backward_partials(nn, d_g, m);
+    net_reduce_grads(nn);
+    for (int i = 0; i < nn->num_layers - 1; i++) {
+        const Layer& L = nn->layers[i];
+        CUDA_CHECK(cudaMemcpyAsync(L.grad_weights, nd->grads + nd->w_off[i], (size_t)L.input_size * L.output_size * sizeof(float), cudaMemcpyDeviceToHost, stream()));
+        CUDA_CHECK(cudaMemcpyAsync(L.grad_biases, nd->grads + nd->b_off[i], (size_t)L.output_size * sizeof(float), cudaMemcpyDeviceToHost, stream()));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+// Checkpoint block, byte format of src/neural_network.cu:284-300 (host arrays are written, like the
+// reference: callers sync device->host first, src/ppo.cu:536-538).
+void save_neural_network(NeuralNetwork* nn, FILE* file) {
+    fwrite(&nn->num_layers, sizeof(int), 1, file);
+    fwrite(&nn->output_size, sizeof(int), 1, file);
+    for (int i = 0; i < nn->num_layers - 1; i++) {
+        int length = (int)strlen(nn->activation_functions[i]) + 1;
+        fwrite(&length, sizeof(int), 1, file);
+        fwrite(nn->activation_functions[i], sizeof(char), length, file);
+    }
+    for (int i = 0; i < nn->num_layers - 1; i++) {
+        const Layer& L = nn->layers[i];
+        fwrite(&L.input_size, sizeof(int), 1, file);
+        fwrite(&L.output_size, sizeof(int), 1, file);
+        fwrite(L.weights, sizeof(float), (size_t)L.input_size * L.output_size, file);
+        fwrite(L.biases, sizeof(float), L.output_size, file);
+    }
+}
+
+static void must_read(void* dst, size_t size, size_t count, FILE* file) {
+    if (fread(dst, size, count, file) != count) B200_FATAL("checkpoint truncated");
+}
+
+NeuralNetwork* load_neural_network(FILE* file) {       // src/neural_network.cu:303-358
+    int num_layers, output_size;
+    must_read(&num_layers, sizeof(int), 1, file);
+    must_read(&output_size, sizeof(int), 1, file);
+    NeuralNetwork* nn = alloc_host_net(num_layers);
+    nn->output_size = output_size;
+    for (int i = 0; i < num_layers - 1; i++) {
+        int length;
+        must_read(&length, sizeof(int), 1, file);
+        nn->activation_functions[i] = (char*)malloc(length);
+        must_read(nn->activation_functions[i], 1, length, file);
+    }
+    for (int i = 0; i < num_layers - 1; i++) {
+        int in, out;
+        must_read(&in, sizeof(int), 1, file);
+        must_read(&out, sizeof(int), 1, file);
+        alloc_host_layer(nn, i, in, out);
+        must_read(nn->layers[i].weights, sizeof(float), (size_t)in * out, file);
+        must_read(nn->layers[i].biases, sizeof(float), out, file);
+    }
+    nn->layers[num_layers - 1].input_size = output_size;
+    attach_device(nn);
+    nn_write_weights_to_device(nn);
+    return nn;
+}
+
+}  // extern "C"

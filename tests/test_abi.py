@@ -1,0 +1,89 @@
+"""CPU-only checks of the drop-in boundary: the product library loads without a GPU, exports every
+symbol include/ppo_b200.h declares, keeps the reference's struct layouts, and the reference's own
+caller (src/main.c) compiles and links against it unmodified."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import b200
+import cabi
+
+ROOT = cabi.ROOT
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "ppo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set()
+    for m in re.finditer(r"^[A-Za-z_][\w \*]*?\b(\w+)\s*\([^;{]*\)\s*;", src, flags=re.M):
+        name = m.group(1)
+        if "(*" in m.group(0).split(name)[0]:
+            continue
+        names.add(name)
+    return names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    b200.package().build()
+    lib = b200.lib()      # binds the reference API + extension API (raises on a missing symbol)
+    names = declared_functions()
+    assert len(names) > 90
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    for n in cabi.REFERENCE_API:
+        assert n in names, n
+    assert b"sm_100a" in lib.ppo_b200_version()
+
+
+def test_struct_layouts_match_reference_abi():
+    """sizeof/offsetof of the public structs, as compiled from include/ppo_b200.h by gcc, must equal
+    the ctypes mirror of the REFERENCE headers (tests/cabi.py)."""
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "ppo.h"
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("Layer %zu\nNeuralNetwork %zu\nGaussianPolicy %zu\nTrajectoryBuffer %zu\nAdam %zu\nEnv %zu\nPPO %zu\n",
+         sizeof(Layer), sizeof(NeuralNetwork), sizeof(GaussianPolicy), sizeof(TrajectoryBuffer), sizeof(Adam), sizeof(Env), sizeof(PPO));
+  P(Layer, d_grad_x); P(Layer, input_size); P(NeuralNetwork, d_output); P(NeuralNetwork, cublas_handle);
+  P(GaussianPolicy, d_input_action); P(TrajectoryBuffer, random_idx); P(TrajectoryBuffer, full);
+  P(TrajectoryBuffer, truncated); P(Adam, time_step); P(Env, gamma); P(PPO, use_cuda); P(PPO, lambda);
+  return 0; }
+'''
+    tmp = os.path.join(ROOT, "build", "abi_probe")
+    os.makedirs(tmp, exist_ok=True)
+    open(os.path.join(tmp, "probe.c"), "w").write(prog)
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(tmp, "probe.c"), "-o", os.path.join(tmp, "probe")])
+    out = dict(line.rsplit(" ", 1) for line in subprocess.check_output([os.path.join(tmp, "probe")], text=True).splitlines())
+    sizes = {"Layer": cabi.Layer, "NeuralNetwork": cabi.NeuralNetwork, "GaussianPolicy": cabi.GaussianPolicy,
+             "TrajectoryBuffer": cabi.TrajectoryBuffer, "Adam": cabi.Adam, "Env": cabi.Env, "PPO": cabi.PPO}
+    for name, t in sizes.items():
+        assert int(out[name]) == C.sizeof(t), name
+    for key, (t, f) in {"Layer.d_grad_x": (cabi.Layer, "d_grad_x"), "Layer.input_size": (cabi.Layer, "input_size"),
+                        "NeuralNetwork.d_output": (cabi.NeuralNetwork, "d_output"),
+                        "NeuralNetwork.cublas_handle": (cabi.NeuralNetwork, "cublas_handle"),
+                        "GaussianPolicy.d_input_action": (cabi.GaussianPolicy, "d_input_action"),
+                        "TrajectoryBuffer.random_idx": (cabi.TrajectoryBuffer, "random_idx"),
+                        "TrajectoryBuffer.full": (cabi.TrajectoryBuffer, "full"),
+                        "TrajectoryBuffer.truncated": (cabi.TrajectoryBuffer, "truncated"),
+                        "Adam.time_step": (cabi.Adam, "time_step"), "Env.gamma": (cabi.Env, "gamma"),
+                        "PPO.use_cuda": (cabi.PPO, "use_cuda"), "PPO.lambda": (cabi.PPO, "lambda_")}.items():
+        assert int(out[key]) == getattr(t, f).offset, key
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/main.c"), reason="reference not mounted")
+def test_reference_main_compiles_and_links_unmodified():
+    """The reference's own caller, src/main.c, compiled where it lies against OUR headers and linked
+    against OUR library (it is not run here: it needs a GPU)."""
+    b200.package().build()
+    out = os.path.join(ROOT, "build", "abi_probe", "ref_main")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(["gcc", "-std=gnu11", "-Wno-implicit-function-declaration", "-Wno-discarded-qualifiers",
+                           "-I", os.path.join(ROOT, "include"), "/root/reference/src/main.c", "-o", out,
+                           "-L", os.path.join(ROOT, "ppo.c_b200"), "-lppo_b200", "-lm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "ppo.c_b200")])
+    assert os.path.exists(out)
