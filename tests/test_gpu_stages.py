@@ -384,8 +384,9 @@ def test_policy_stage_vs_reference_golden(L, golden, pre):
     assert nerr(gl, g[pre + "grad_logprob"]) < TOL and ge.value == -ec
     dgmu, dgls = b200.dev_empty((m, A)), b200.dev_empty(A)
     L.log_prob_backwards_cuda(pol, dgl.fp(), dgmu.fp(), dgls.fp(), m)
-    mu_o, cache = oracle.mlp_forward(g[pre + "params"], sizes, RELU3, g[pre + "state"])
-    gmu_o, gls_o = oracle.log_prob_backwards(mu_o, g[pre + "log_std"], g[pre + "action"], g[pre + "grad_logprob"], ref_index=False)
+    # stage-level: the oracle gets exactly the inputs the kernel got (the device mu and grad_logprob)
+    mu_dev = b200.d2h(L, pol.contents.mu.contents.d_output, (m, A))
+    gmu_o, gls_o = oracle.log_prob_backwards(mu_dev, g[pre + "log_std"], g[pre + "action"], gl, ref_index=False)
     assert nerr(dgmu.numpy(), gmu_o) < TOL and nerr(dgls.numpy(), gls_o) < TOL
     if A == 1:
         assert nerr(dgmu.numpy(), g["pol_grad_mu"]) < TOL and nerr(dgls.numpy(), g["pol_grad_log_std"]) < TOL
