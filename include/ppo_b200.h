@@ -354,6 +354,10 @@ void  ppo_b200_memset(void* dst, int value, size_t bytes);
 void  ppo_b200_sync(void);
 unsigned long long ppo_b200_launch_count(void); /* kernels launched by this library so far */
 const char* ppo_b200_version(void);
+/* Per-kernel timing without a profiler: between begin and end every launch of the library is
+ * bracketed by a CUDA-event pair on the launching stream.  end() writes "name count total_ms" lines. */
+void ppo_b200_profile_begin(void);
+int  ppo_b200_profile_end(char* out, int out_bytes);
 
 /* ---- stage-level kernels on plain DEVICE arrays ------------------------------------------------ */
 /* GAE + returns (src/ppo.cu:338-353) as one segmented reverse scan; optional normalisation
@@ -389,8 +393,10 @@ void ppo_b200_sync_host(PPO* ppo);       /* device buffer + weights -> host mirr
 /* Whole iterations, device-resident, no host mirrors (bench `value`): rollout + update, n_iters times. */
 void ppo_b200_train_iterations(PPO* ppo, Env* env, int n_iters, int batch_size, int n_epochs_policy,
                                int n_epochs_value);
-/* permutation source: 0 = reference glibc rand() chain on the host (bit-exact indices, default),
- *                     1 = device counter-based permutation (no host work, no H2D). */
+/* permutation source: 0 = reference glibc rand() chain on the host (bit-exact indices),
+ *                     1 = device counter-based permutation (no host work, no H2D),
+ *                    -1 = auto (default): 0 for host envs / host-filled buffers (the reference-
+ *                         compatible path), 1 after a device rollout (whose noise is Philox anyway). */
 void ppo_b200_set_permutation_mode(PPO* ppo, int mode, unsigned long long seed);
 /* Running observation normalisation (new; Welford merge of include/welford_var.h:33-40): 0 = off. */
 void ppo_b200_set_obs_norm(PPO* ppo, int enabled);

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -62,11 +63,18 @@ T* hmalloc_pinned(size_t count) {
     return static_cast<T*>(p);
 }
 
+// Every kernel launch of the library goes through this macro: launch counter (bench.py's
+// gpu_launches) and, when ppo_b200_profile_begin() is active, a CUDA-event pair per launch on the
+// launching stream so per-kernel durations can be reported without a profiler attached.
+void profile_mark(const char* name, bool begin);
+extern bool g_profiling;
 #define B200_LAUNCH(kernel, grid, block, smem, ...)                              \
     do {                                                                         \
+        if (::b200::g_profiling) ::b200::profile_mark(#kernel, true);            \
         kernel<<<(grid), (block), (smem), ::b200::stream()>>>(__VA_ARGS__);      \
         ++::b200::g_launches;                                                    \
         CUDA_CHECK(cudaGetLastError());                                          \
+        if (::b200::g_profiling) ::b200::profile_mark(#kernel, false);           \
     } while (0)
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -28,7 +28,8 @@ struct Trainer {
     int* d_perm[2] = {nullptr, nullptr};
     cudaEvent_t perm_evt[2] = {nullptr, nullptr};
     int perm_cap = 0, perm_slot = 0;
-    int perm_mode = 0;
+    int perm_mode = -1;          // -1 auto: device generator after a device rollout, reference rand() chain otherwise
+    bool last_rollout_on_device = false;
     unsigned long long perm_seed = 0, perm_epoch = 0;
     float* d_scalars = nullptr;   // [0] value-loss sum, [1] policy-loss sum, [2..3] return stats, [4..] dist triples
     int n_v_steps = 0, n_p_steps = 0;
@@ -88,7 +89,8 @@ static const int* next_permutation(Trainer* t, int n) {
     ensure_perm(t, n);
     const int s = t->perm_slot;
     t->perm_slot ^= 1;
-    if (t->perm_mode == 1) {
+    const bool on_device = t->perm_mode == 1 || (t->perm_mode < 0 && t->last_rollout_on_device);
+    if (on_device) {
         ppo_b200_permutation(t->d_perm[s], n, t->perm_seed, t->perm_epoch++);
     } else {
         CUDA_CHECK(cudaEventSynchronize(t->perm_evt[s]));   // the upload that last used this pinned slot
@@ -342,6 +344,7 @@ void ppo_b200_update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_
 }
 
 void ppo_b200_update(PPO* ppo, float gamma, int batch_size, int n_epochs_policy, int n_epochs_value) {
+    trainer(ppo)->last_rollout_on_device = false;
     ppo_b200_buffer_upload(ppo);
     update_device(ppo, gamma, batch_size, n_epochs_policy, n_epochs_value);
     ppo_b200_sync_host(ppo);
@@ -351,6 +354,7 @@ void ppo_b200_train_iterations(PPO* ppo, Env* env, int n_iters, int batch_size, 
     Trainer* t = trainer(ppo);
     DeviceEnv* e = as_device_env(env);
     for (int i = 0; i < n_iters; i++) {
+        t->last_rollout_on_device = e != nullptr;
         if (e) {
             collect_device(ppo->buffer, e, ppo->policy, ppo->buffer->capacity, t->d_scalars + 2);
         } else {

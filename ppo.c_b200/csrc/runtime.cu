@@ -1,7 +1,32 @@
 // runtime.cu — device/stream plumbing exported through include/ppo_b200.h ("runtime plumbing").
+#include <map>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b200 {
+
+// ---- event-pair profiling of every launch (see B200_LAUNCH) ------------------------------------
+bool g_profiling = false;
+struct ProfRec { const char* name; cudaEvent_t beg, end; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t pool_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+}
+void profile_mark(const char* name, bool begin) {
+    if (begin) {
+        ProfRec r{name, pool_event(), pool_event()};
+        CUDA_CHECK(cudaEventRecord(r.beg, stream()));
+        g_prof.push_back(r);
+    } else {
+        CUDA_CHECK(cudaEventRecord(g_prof.back().end, stream()));
+    }
+}
 
 unsigned long long g_launches = 0;
 static cudaStream_t g_stream = nullptr;
@@ -92,6 +117,45 @@ void ppo_b200_memset(void* dst, int value, size_t bytes) {
 }
 void ppo_b200_sync(void) { CUDA_CHECK(cudaStreamSynchronize(stream())); }
 unsigned long long ppo_b200_launch_count(void) { return g_launches; }
+void ppo_b200_profile_begin(void) {
+    for (auto& r : g_prof) { g_event_pool.push_back(r.beg); g_event_pool.push_back(r.end); }
+    g_prof.clear();
+    g_profiling = true;
+}
+
+// Stops profiling and writes one line per kernel: "name count total_ms\n".  Returns bytes written.
+int ppo_b200_profile_end(char* out, int out_bytes) {
+    g_profiling = false;
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, r.beg, r.end));
+        std::string name(r.name);
+        const size_t lt = name.find('<');          // strip template arguments' namespace noise
+        (void)lt;
+        auto& a = agg[name];
+        a.first += 1;
+        a.second += ms;
+        g_event_pool.push_back(r.beg);
+        g_event_pool.push_back(r.end);
+    }
+    g_prof.clear();
+    std::string s;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        s += line;
+    }
+    if (out && out_bytes > 0) {
+        const int n = (int)std::min<size_t>(s.size(), (size_t)out_bytes - 1);
+        memcpy(out, s.data(), n);
+        out[n] = 0;
+        return n;
+    }
+    return 0;
+}
+
 const char* ppo_b200_version(void) { return "ppo.c_b200 0.1 (sm_100a)"; }
 void openblas_set_num_threads(int n) { (void)n; }
 
