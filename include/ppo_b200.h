@@ -398,6 +398,9 @@ void ppo_b200_train_iterations(PPO* ppo, Env* env, int n_iters, int batch_size, 
  *                    -1 = auto (default): 0 for host envs / host-filled buffers (the reference-
  *                         compatible path), 1 after a device rollout (whose noise is Philox anyway). */
 void ppo_b200_set_permutation_mode(PPO* ppo, int mode, unsigned long long seed);
+/* kernel path of the update/GAE-forward: -1 default (fused small-net kernels when every layer width
+ * is <= 128, else layer-wise; env PPO_B200_FUSED=0 disables), 0 = force layer-wise, 1 = force fused. */
+void ppo_b200_set_kernel_path(int path);
 /* Running observation normalisation (new; Welford merge of include/welford_var.h:33-40): 0 = off. */
 void ppo_b200_set_obs_norm(PPO* ppo, int enabled);
 /* mean undiscounted return per episode of the last device rollout (eval_ppo's "R", src/ppo.cu:581) */

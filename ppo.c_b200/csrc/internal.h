@@ -98,6 +98,13 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
 void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m);
 void net_reduce_grads(NeuralNetwork* nn);   // partials -> nd->grads (fixed order)
 
+// ---- fused_mlp.cu -----------------------------------------------------------------------------
+bool fused_supported(NeuralNetwork* nn);
+void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out);
+bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
+                            const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
+                            float epsilon, float ent_coeff, float* loss_slot, bool apply_adam);
+
 // ---- policy.cu --------------------------------------------------------------------------------
 void launch_log_prob(const float* mu, const float* log_std, const float* action, float* out, int m, int A);
 // fused value head: grad[i] = 2 (y-t)/m_total ; loss_slot += sum (t-y)^2 / m_total

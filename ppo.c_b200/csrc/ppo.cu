@@ -101,13 +101,31 @@ static const int* next_permutation(Trainer* t, int n) {
     return t->d_perm[s];
 }
 
+// PPO_B200_FUSED=0 forces the generic layer-wise kernels (A/B testing, parity tests of both paths).
+static int g_force_path_decl_dummy = 0;
+static bool use_fused_env() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("PPO_B200_FUSED"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
+static int g_force_path = -1;   // tests: -1 env default, 0 layer-wise, 1 fused
+static bool use_fused() { (void)g_force_path_decl_dummy; return g_force_path < 0 ? use_fused_env() : g_force_path == 1; }
+
 // compute_gae on device arrays (src/ppo.cu:261-323): two V forwards, scan, global stats, normalise.
 static void gae_device(NeuralNetwork* V, TrajectoryBuffer* b, Trainer* t, int limit, float gamma, float lambda) {
     float* v_next = static_cast<float*>(scratch(kScratchGaeVNext, (size_t)limit * sizeof(float)));
-    net_forward(V, b->d_next_state_p, limit, true);
-    CUDA_CHECK(cudaMemcpyAsync(v_next, V->d_output, (size_t)limit * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
-    net_forward(V, b->d_state_p, limit, true);
-    const float* v = V->d_output;
+    const float* v;
+    if (use_fused() && fused_supported(V)) {   // one launch per pass, activations stay in shared memory
+        float* vbuf = static_cast<float*>(scratch(kScratchGaeV, (size_t)limit * sizeof(float)));
+        fused_forward(V, b->d_next_state_p, limit, v_next);
+        fused_forward(V, b->d_state_p, limit, vbuf);
+        v = vbuf;
+    } else {
+        net_forward(V, b->d_next_state_p, limit, true);
+        CUDA_CHECK(cudaMemcpyAsync(v_next, V->d_output, (size_t)limit * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
+        net_forward(V, b->d_state_p, limit, true);
+        v = V->d_output;
+    }
     GaeWork w = gae_scan(b->d_reward_p, v, v_next, b->d_terminated_p, b->d_truncated_p, limit, gamma, lambda,
                          b->d_advantage_p, b->d_adv_target_p);
     if (dist_active() && dist_shard_mode() == 1 && t) {
@@ -144,6 +162,8 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     const int num_batches = limit / batch_size;   // src/ppo.cu:387-388 (ceilf of an integer quotient)
     NetDev* ndV = net_dev(ppo->V);
     NetDev* ndP = net_dev(pol->mu);
+    const bool fusedV = use_fused() && fused_supported(ppo->V);
+    const bool fusedP = use_fused() && fused_supported(pol->mu);
     CUDA_CHECK(cudaMemsetAsync(t->d_scalars, 0, 2 * sizeof(float), stream()));
     t->n_v_steps = n_epochs_value * num_batches;
     t->n_p_steps = n_epochs_policy * num_batches;
@@ -152,6 +172,11 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     for (int j = 0; j < n_epochs_value; j++) {
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
+            if (fusedV && G == 1) {
+                fused_minibatch_update(ppo->V, nullptr, ppo->adam_V, nullptr, ppo->lr_V, perm, k * batch_size + row0, limit,
+                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, true);
+                continue;
+            }
             launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
                           b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
             net_forward(ppo->V, t->states, mb_local, true);
@@ -174,6 +199,12 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     for (int j = 0; j < n_epochs_policy; j++) {
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
+            if (fusedP && G == 1) {
+                fused_minibatch_update(pol->mu, pol, ppo->adam_policy, ppo->adam_entropy, ppo->lr_policy, perm,
+                                       k * batch_size + row0, limit, mb_local, mb_total, b, ppo->epsilon, ppo->ent_coeff,
+                                       t->d_scalars + 1, true);
+                continue;
+            }
             launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
                           b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
             net_forward(pol->mu, t->states, mb_local, true);
@@ -444,6 +475,8 @@ void ppo_b200_set_permutation_mode(PPO* ppo, int mode, unsigned long long seed) 
     t->perm_seed = seed;
     t->perm_epoch = 0;
 }
+
+void ppo_b200_set_kernel_path(int path) { g_force_path = path; }
 
 void ppo_b200_set_obs_norm(PPO* ppo, int enabled) { trainer(ppo)->obs_norm = enabled != 0; }
 
