@@ -235,6 +235,7 @@ void adam_update_cuda(Adam* adam, float lr) {
     if (it == g_adam_meta.end()) B200_FATAL("adam_update_cuda: Adam %p was not created by create_adam*_cuda", (void*)adam);
     AdamMeta& meta = it->second;
     adam->time_step += 1;
+    for (float* w : meta.w) net_mark_params_written(w);
     if (meta.contiguous) {
         adam_flat(meta.w[0], meta.g[0], adam->m, adam->v, adam->size, lr, adam->beta1, adam->beta2,
                   adam->time_step, nullptr, 0, 0);

@@ -5,10 +5,11 @@
 //   fused_update_kernel   gather rows by permutation index -> forward through ALL layers -> fused loss
 //                         head (MSE, or Gaussian log-prob + PPO-clip surrogate) -> backward through
 //                         all layers -> this CTA's partial gradient slab.  Weights are staged ONCE per
-//                         CTA in shared memory (transposed, k-major), activations never leave shared
-//                         memory, nothing but the slab is written to HBM.
+//                         CTA in shared memory, activations never leave shared memory, nothing but
+//                         the slab is written to HBM.
 //   fused_reduce_adam_kernel  fixed-order sum of the slabs + Adam on the flat parameter vector (+ the
-//                         log_std vector for the policy) + loss accumulation.
+//                         log_std vector for the policy) + loss accumulation; also refreshes the
+//                         pre-transposed weight image the next fused_update_kernel will stage.
 // versus ~14 launches through the layer-wise kernels of gemm.cu/policy.cu/adam.cu (which remain the
 // generic path for wider nets).  The reference does this with ~25 launches, 1-3 blocking D2H reads
 // and 1-2 cudaMallocs per minibatch (src/ppo.cu:495-532).
@@ -16,11 +17,15 @@
 // Shared-memory layouts (TM = rows per CTA, TMP = TM + 4 so that TMP % 32 == 4):
 //   activations / gradients  At[feature][TMP]   feature-major: a thread reads 4 consecutive ROWS with
 //                            one conflict-free LDS.128
-//   weights                  Wt[in][out_pad]    k-major transpose of the reference's W[out][in]
+//   weights                  Wt[in][out_pad]    k-major transpose of the reference's W[out][in]; the whole
+//                            "image" [Wt_0|Wt_1|..|biases] is kept pre-transposed in global memory by the
+//                            Adam kernel and lands in shared memory with ONE TMA bulk copy
+//                            (cp.async.bulk + mbarrier complete_tx) that overlaps the row gather
 // Thread mappings (256 threads):
-//   forward / dX : thread = (row lane tr, column group tc): rows {4tr..4tr+3, TM/2+4tr..+3} x 4 columns
-//   dW           : thread = (tj, tk) in 16x16, owns j = tj+16*jj, k = tk+16*kk (interleaved so the 16
+//   forward / dX : thread = (row lane tr, column group tc): RT rows x 4 columns
+//   dW (+db)     : thread = (tj, tk) in 16x16, owns j = tj+16*jj, k = tk+16*kk (interleaved so the 16
 //                  lanes of a half-warp read 16 consecutive feature rows: stride TMP -> conflict-free)
+// Tile configs: <TM=64,RT=4> two CTAs per SM (widths <= 64), <TM=64,RT=8> one CTA per SM (widths <= 128).
 // All arithmetic is fp32 FFMA (tolerance 1e-5).
 #include "common.cuh"
 #include "internal.h"
@@ -36,9 +41,10 @@ struct FusedNet {
     int sizes[kFusedMaxLayers + 1];
     int acts[kFusedMaxLayers];
     int w_off[kFusedMaxLayers], b_off[kFusedMaxLayers];   // offsets in the flat parameter vector
-    int wt_off[kFusedMaxLayers];        // offsets of Wt[in][out_pad] in shared memory (floats)
-    int a_off[kFusedMaxLayers + 1];     // offsets of At buffers in shared memory (floats)
-    int bs_off[kFusedMaxLayers];        // offsets of the layer biases inside the shared bias region
+    int wt_off[kFusedMaxLayers];        // offsets of Wt[in][out_pad] inside the weight image (floats)
+    int bs_off[kFusedMaxLayers];        // offsets of the layer biases inside the weight image (floats)
+    int img_floats;                     // image size (multiple of 32 floats = 128 B; TMA bulk needs 16 B)
+    int a_off[kFusedMaxLayers + 1];     // offsets of At buffers in shared memory (floats, after the image)
     int P;
     int max_width_pad;
 };
@@ -47,7 +53,7 @@ enum FusedMode { kFusedForward = 0, kFusedValue = 1, kFusedPolicy = 2 };
 
 struct FusedArgs {
     FusedNet net;
-    const float* params;
+    const float* image;        // pre-transposed weight image in global memory
     const int* idx;            // permutation (may be null: row = offset + r)
     int offset, limit, m, m_total, mode;
     const float* state;        // [*][S]
@@ -61,107 +67,144 @@ struct FusedArgs {
     float* partials;           // [gridDim.x][slab]  slab = P + A + 1 (grads | grad_log_std | loss term)
     int slab;
     int smem_g_off;            // offset of the two gradient buffers
-    int smem_b_off;            // biases
-    int smem_red_off;
+    int smem_red_off;          // 64 floats of reduction scratch, TM ints of source rows, 1 mbarrier
 };
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 
-template <int TM>
+// ---- TMA bulk copy + mbarrier (SASS: UBLKCP + SYNCS) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// rows owned by a thread: RT=4 -> {4tr..4tr+3}; RT=8 -> {4tr..4tr+3, TM/2+4tr..TM/2+4tr+3}
+template <int TM, int RT>
+__device__ __forceinline__ void load_rows(const float* base, float (&a)[RT]) {
+    const float4 a0 = *reinterpret_cast<const float4*>(base);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+    if (RT == 8) {
+        const float4 a1 = *reinterpret_cast<const float4*>(base + TM / 2);
+        a[RT - 4] = a1.x; a[RT - 3] = a1.y; a[RT - 2] = a1.z; a[RT - 1] = a1.w;
+    }
+}
+template <int TM, int RT>
+__device__ __forceinline__ void store_rows(float* base, const float (&a)[RT]) {
+    *reinterpret_cast<float4*>(base) = make_float4(a[0], a[1], a[2], a[3]);
+    if (RT == 8) *reinterpret_cast<float4*>(base + TM / 2) = make_float4(a[RT - 4], a[RT - 3], a[RT - 2], a[RT - 1]);
+}
+
+template <int TM, int RT>
 __device__ __forceinline__ void fused_forward_layer(const float* __restrict__ Xt, const float* __restrict__ Wt,
                                                     const float* __restrict__ bias, float* __restrict__ Yt,
                                                     int n_in, int n_out, int act) {
-    constexpr int TMP = TM + 4, RL = TM / 8;
+    constexpr int TMP = TM + 4, RL = TM / RT;
     const int tr = threadIdx.x % RL, tc = threadIdx.x / RL;
     const int out_pad = pad4(n_out);
     if (4 * tc >= out_pad) return;
-    float acc[8][4];
+    float acc[RT][4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const float b = (4 * tc + c < n_out) ? bias[4 * tc + c] : 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; r++) acc[r][c] = b;
+        for (int r = 0; r < RT; r++) acc[r][c] = b;
     }
     const float* xp = Xt + 4 * tr;
     const float* wp = Wt + 4 * tc;
 #pragma unroll 4
     for (int k = 0; k < n_in; k++) {
-        const float4 a0 = *reinterpret_cast<const float4*>(xp + k * TMP);
-        const float4 a1 = *reinterpret_cast<const float4*>(xp + k * TMP + TM / 2);
+        float a[RT];
+        load_rows<TM, RT>(xp + k * TMP, a);
         const float4 w = *reinterpret_cast<const float4*>(wp + k * out_pad);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int r = 0; r < RT; r++)
 #pragma unroll
             for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        float* yp = Yt + (4 * tc + c) * TMP + 4 * tr;
-        *reinterpret_cast<float4*>(yp) = make_float4(act_apply(acc[0][c], act), act_apply(acc[1][c], act),
-                                                     act_apply(acc[2][c], act), act_apply(acc[3][c], act));
-        *reinterpret_cast<float4*>(yp + TM / 2) = make_float4(act_apply(acc[4][c], act), act_apply(acc[5][c], act),
-                                                              act_apply(acc[6][c], act), act_apply(acc[7][c], act));
+        float o[RT];
+#pragma unroll
+        for (int r = 0; r < RT; r++) o[r] = act_apply(acc[r][c], act);
+        store_rows<TM, RT>(Yt + (4 * tc + c) * TMP + 4 * tr, o);
     }
 }
 
 // GXt[k][r] = (sum_j Gt[j][r] * W[j][k]) * act'(Ht[k][r])   (Wt is [k][out_pad])
-template <int TM>
+template <int TM, int RT>
 __device__ __forceinline__ void fused_backward_input(const float* __restrict__ Gt, const float* __restrict__ Wt,
                                                      const float* __restrict__ Ht, float* __restrict__ GXt,
                                                      int n_in, int n_out, int act_prev) {
-    constexpr int TMP = TM + 4, RL = TM / 8;
+    constexpr int TMP = TM + 4, RL = TM / RT;
     const int tr = threadIdx.x % RL, tc = threadIdx.x / RL;
     const int out_pad = pad4(n_out);
     if (4 * tc >= pad4(n_in)) return;
-    float acc[8][4];
+    float acc[RT][4];
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+    for (int r = 0; r < RT; r++)
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
     const float* gp = Gt + 4 * tr;
-    const float* wp = Wt + (4 * tc) * out_pad;
-    bool kok[4];
+    // rows of Wt owned by this thread; out-of-range columns alias row 0 and are discarded below
+    const float* wp[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) kok[c] = 4 * tc + c < n_in;
+    for (int c = 0; c < 4; c++) wp[c] = Wt + (size_t)((4 * tc + c < n_in) ? 4 * tc + c : 0) * out_pad;
 #pragma unroll 4
     for (int j = 0; j < n_out; j++) {
-        const float4 g0 = *reinterpret_cast<const float4*>(gp + j * TMP);
-        const float4 g1 = *reinterpret_cast<const float4*>(gp + j * TMP + TM / 2);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float g[RT];
+        load_rows<TM, RT>(gp + j * TMP, g);
         float wv[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) wv[c] = kok[c] ? wp[c * out_pad + j] : 0.f;
+        for (int c = 0; c < 4; c++) wv[c] = wp[c][j];
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int r = 0; r < RT; r++)
 #pragma unroll
             for (int c = 0; c < 4; c++) acc[r][c] = fmaf(g[r], wv[c], acc[r][c]);
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        if (!kok[c]) continue;
-        const float* hp = Ht + (4 * tc + c) * TMP + 4 * tr;
-        float* op = GXt + (4 * tc + c) * TMP + 4 * tr;
-        const float4 h0 = *reinterpret_cast<const float4*>(hp), h1 = *reinterpret_cast<const float4*>(hp + TM / 2);
-        *reinterpret_cast<float4*>(op) = make_float4(act_grad(h0.x, acc[0][c], act_prev), act_grad(h0.y, acc[1][c], act_prev),
-                                                     act_grad(h0.z, acc[2][c], act_prev), act_grad(h0.w, acc[3][c], act_prev));
-        *reinterpret_cast<float4*>(op + TM / 2) = make_float4(act_grad(h1.x, acc[4][c], act_prev), act_grad(h1.y, acc[5][c], act_prev),
-                                                              act_grad(h1.z, acc[6][c], act_prev), act_grad(h1.w, acc[7][c], act_prev));
+        if (4 * tc + c >= n_in) continue;
+        float h[RT], o[RT];
+        load_rows<TM, RT>(Ht + (4 * tc + c) * TMP + 4 * tr, h);
+#pragma unroll
+        for (int r = 0; r < RT; r++) o[r] = act_grad(h[r], acc[r][c], act_prev);
+        store_rows<TM, RT>(GXt + (4 * tc + c) * TMP + 4 * tr, o);
     }
 }
 
-// gW[j][k] = sum_r Gt[j][r] * Xt[k][r]  -> global slab (row-major [out][in], the reference layout)
+// gW[j][k] = sum_r Gt[j][r] * Xt[k][r]  and  gb[j] = sum_r Gt[j][r]  -> global slab
+// (row-major [out][in], the reference layout; src/mat_mul.cu:195-208 + src/neural_network.cu:108-118)
 template <int TM, int JJ, int KK>
 __device__ __forceinline__ void fused_backward_weights(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                       float* __restrict__ gW, int n_in, int n_out) {
+                                                       float* __restrict__ gW, float* __restrict__ gb, int n_in, int n_out) {
     constexpr int TMP = TM + 4;
     const int tk = threadIdx.x & 15, tj = threadIdx.x >> 4;
-    float acc[JJ][KK];
+    float acc[JJ][KK], bsum[JJ];
 #pragma unroll
-    for (int a = 0; a < JJ; a++)
+    for (int a = 0; a < JJ; a++) {
+        bsum[a] = 0.f;
 #pragma unroll
         for (int b = 0; b < KK; b++) acc[a][b] = 0.f;
+    }
     // clamp out-of-range rows to a valid one (results discarded) so loads stay in bounds
     int jrow[JJ], krow[KK];
 #pragma unroll
@@ -176,7 +219,8 @@ __device__ __forceinline__ void fused_backward_weights(const float* __restrict__
 #pragma unroll
         for (int b = 0; b < KK; b++) x[b] = *reinterpret_cast<const float4*>(Xt + krow[b] + r);
 #pragma unroll
-        for (int a = 0; a < JJ; a++)
+        for (int a = 0; a < JJ; a++) {
+            if (tk == 0) bsum[a] += (g[a].x + g[a].y) + (g[a].z + g[a].w);
 #pragma unroll
             for (int b = 0; b < KK; b++) {
                 acc[a][b] = fmaf(g[a].x, x[b].x, acc[a][b]);
@@ -184,11 +228,13 @@ __device__ __forceinline__ void fused_backward_weights(const float* __restrict__
                 acc[a][b] = fmaf(g[a].z, x[b].z, acc[a][b]);
                 acc[a][b] = fmaf(g[a].w, x[b].w, acc[a][b]);
             }
+        }
     }
 #pragma unroll
     for (int a = 0; a < JJ; a++) {
         const int j = tj + 16 * a;
         if (j >= n_out) continue;
+        if (tk == 0) gb[j] = bsum[a];
 #pragma unroll
         for (int b = 0; b < KK; b++) {
             const int k = tk + 16 * b;
@@ -198,26 +244,13 @@ __device__ __forceinline__ void fused_backward_weights(const float* __restrict__
 }
 
 template <int TM>
-__device__ __forceinline__ void fused_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out) {
+__device__ __forceinline__ void fused_weights_dispatch(const float* Gt, const float* Xt, float* gW, float* gb, int n_in, int n_out) {
     const int jj = (n_out + 15) / 16, kk = (n_in + 15) / 16;
-#define B200_DW(J, K) fused_backward_weights<TM, J, K>(Gt, Xt, gW, n_in, n_out)
-    if (jj <= 1) { if (kk <= 1) B200_DW(1, 1); else if (kk <= 4) B200_DW(1, 4); else B200_DW(1, 8); }
-    else if (jj <= 4) { if (kk <= 1) B200_DW(4, 1); else if (kk <= 2) B200_DW(4, 2); else if (kk <= 4) B200_DW(4, 4); else B200_DW(4, 8); }
-    else { if (kk <= 1) B200_DW(8, 1); else if (kk <= 2) B200_DW(8, 2); else if (kk <= 4) B200_DW(8, 4); else B200_DW(8, 8); }
+#define B200_DW(J, K) fused_backward_weights<TM, J, K>(Gt, Xt, gW, gb, n_in, n_out)
+    if (jj <= 1) { if (kk <= 2) B200_DW(1, 2); else if (kk <= 4) B200_DW(1, 4); else B200_DW(1, 8); }
+    else if (jj <= 4) { if (kk <= 2) B200_DW(4, 2); else if (kk <= 4) B200_DW(4, 4); else B200_DW(4, 8); }
+    else { if (kk <= 2) B200_DW(8, 2); else if (kk <= 4) B200_DW(8, 4); else B200_DW(8, 8); }
 #undef B200_DW
-}
-
-// gb[j] = sum_r Gt[j][r] : one warp per feature row
-template <int TM>
-__device__ __forceinline__ void fused_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out) {
-    constexpr int TMP = TM + 4;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < n_out; j += kFusedThreads / 32) {
-        float s = 0.f;
-        for (int r = lane; r < TM; r += 32) s += Gt[j * TMP + r];
-        s = warp_sum(s);
-        if (lane == 0) gb[j] = s;
-    }
 }
 
 __device__ __forceinline__ float fused_log_prob(const float* mu, const float* log_std, const float* action, int A) {
@@ -229,53 +262,66 @@ __device__ __forceinline__ float fused_log_prob(const float* mu, const float* lo
     return logprob;
 }
 
-template <int TM>
-__global__ void __launch_bounds__(kFusedThreads, 1) fused_update_kernel(const FusedArgs p) {
+template <int TM, int RT>
+__global__ void __launch_bounds__(kFusedThreads, (TM == 64 && RT == 4) ? 2 : 1) fused_update_kernel(const FusedArgs p) {
     constexpr int TMP = TM + 4;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const FusedNet& net = p.net;
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * TM;
     const int S = net.sizes[0], OUT = net.sizes[net.L];
-    float* bias_s = smem + p.smem_b_off;
-    float* red = smem + p.smem_red_off;           // 64 floats
-    int* src_rows = reinterpret_cast<int*>(red + 64);   // TM ints
+    float* img = smem;                                   // [Wt_0 | Wt_1 | ... | biases]
+    float* act0 = smem + net.img_floats;                 // activation buffers
+    float* red = smem + p.smem_red_off;                  // 64 floats
+    int* src_rows = reinterpret_cast<int*>(red + 64);    // TM ints
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64 + TM);
 
-    // ---- stage weights (transposed) + biases; resolve the source rows of this tile
-    for (int l = 0; l < net.L; l++) {
-        const int n_in = net.sizes[l], n_out = net.sizes[l + 1], out_pad = pad4(n_out);
-        float* Wt = smem + net.wt_off[l];
-        const float* W = p.params + net.w_off[l];
-        for (int e = tid; e < n_in * out_pad; e += kFusedThreads) {
-            const int j = e / n_in, k = e - j * n_in;    // coalesced along k in global memory
-            Wt[k * out_pad + j] = (j < n_out) ? W[(size_t)j * n_in + k] : 0.f;
-        }
-        for (int j = tid; j < n_out; j += kFusedThreads) bias_s[net.bs_off[l] + j] = p.params[net.b_off[l] + j];
+    // ---- one elected thread launches the TMA bulk copy of the weight image; everybody else gathers
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+        tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
     }
+    // per-row head inputs are fetched now so their latency hides behind the forward pass
+    float h_target = 0.f, h_adv = 0.f, h_lp_old = 0.f, h_act[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) h_act[j] = 0.f;
+    int my_src = -1;
     if (tid < TM) {
         const int r = row0 + tid;
-        int src = -1;
-        if (r < p.m) src = p.idx ? p.idx[(p.offset + r) % p.limit] : p.offset + r;
-        src_rows[tid] = src;
+        if (r < p.m) my_src = p.idx ? p.idx[(p.offset + r) % p.limit] : p.offset + r;
+        src_rows[tid] = my_src;
     }
     __syncthreads();
-    // ---- gather the input tile: Xt[k][r] = state[src][k]
-    {
-        float* Xt = smem + net.a_off[0];
+    {   // gather the input tile: Xt[k][r] = state[src][k]
+        float* Xt = act0 + net.a_off[0];
         for (int e = tid; e < TM * S; e += kFusedThreads) {
             const int r = e / S, k = e - r * S;
             const int src = src_rows[r];
             Xt[k * TMP + r] = src >= 0 ? p.state[(size_t)src * S + k] : 0.f;
         }
     }
+    if (my_src >= 0) {
+        if (p.mode == kFusedValue) {
+            h_target = p.adv_target[my_src];
+        } else if (p.mode == kFusedPolicy) {
+            h_adv = p.advantage[my_src];
+            h_lp_old = p.logprob[my_src];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < OUT) h_act[j] = p.action[(size_t)my_src * OUT + j];
+        }
+    }
+    mbar_wait(mbar, 0);
     __syncthreads();
     // ---- forward
     for (int l = 0; l < net.L; l++) {
-        fused_forward_layer<TM>(smem + net.a_off[l], smem + net.wt_off[l], bias_s + net.bs_off[l],
-                                smem + net.a_off[l + 1], net.sizes[l], net.sizes[l + 1], net.acts[l]);
+        fused_forward_layer<TM, RT>(act0 + net.a_off[l], img + net.wt_off[l], img + net.bs_off[l], act0 + net.a_off[l + 1],
+                                    net.sizes[l], net.sizes[l + 1], net.acts[l]);
         __syncthreads();
     }
-    const float* Yt = smem + net.a_off[net.L];
+    const float* Yt = act0 + net.a_off[net.L];
     if (p.mode == kFusedForward) {
         for (int e = tid; e < TM * OUT; e += kFusedThreads) {
             const int r = e / OUT, j = e - r * OUT;
@@ -293,35 +339,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_update_kernel(const Fu
 #pragma unroll
         for (int j = 0; j < 8; j++) gls[j] = 0.f;
         if (tid < TM) {
-            const int src = src_rows[tid];
             float gout[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) gout[j] = 0.f;
-            if (src >= 0) {
+            if (my_src >= 0) {
                 if (p.mode == kFusedValue) {            // src/loss.cu:5-23
-                    const float y = Yt[tid], t = p.adv_target[src];
-                    gout[0] = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(y, t)), (float)p.m_total);
-                    const float d = __fsub_rn(t, y);
+                    const float y = Yt[tid];
+                    gout[0] = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(y, h_target)), (float)p.m_total);
+                    const float d = __fsub_rn(h_target, y);
                     loss_term = __fmul_rn(d, d);
                 } else {                                // src/policy.cu:67-111 + src/ppo.cu:89-98
-                    float mu[8], act[8];
+                    float mu[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        if (j < OUT) { mu[j] = Yt[j * TMP + tid]; act[j] = p.action[(size_t)src * OUT + j]; }
-                    const float lp = fused_log_prob(mu, p.log_std, act, OUT);
-                    const float adv = p.advantage[src];
-                    const float ratio = expf(__fsub_rn(lp, p.logprob[src]));
-                    const bool adv_pos = adv > 0.f;
+                    for (int j = 0; j < 8; j++) mu[j] = (j < OUT) ? Yt[j * TMP + tid] : 0.f;
+                    const float lp = fused_log_prob(mu, p.log_std, h_act, OUT);
+                    const float ratio = expf(__fsub_rn(lp, h_lp_old));
+                    const bool adv_pos = h_adv > 0.f;
                     const bool hi = ratio > 1.f + p.epsilon, lo = ratio < 1.f - p.epsilon;
                     const float sel = adv_pos ? (hi ? 1.f + p.epsilon : ratio) : (lo ? 1.f - p.epsilon : ratio);
-                    loss_term = __fmul_rn(adv, sel);
+                    loss_term = __fmul_rn(h_adv, sel);
                     const int keep = adv_pos ? !hi : !lo;
-                    const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), adv), ratio), (float)p.m_total);
+                    const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)p.m_total);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         if (j < OUT) {
                             const float e2 = expf(-2.f * p.log_std[j]);
-                            const float diff = __fsub_rn(act[j], mu[j]);
+                            const float diff = __fsub_rn(h_act[j], mu[j]);
                             gout[j] = __fmul_rn(__fmul_rn(diff, e2), g);
                             gls[j] = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), g);
                         }
@@ -353,17 +396,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_update_kernel(const Fu
             slab[net.P + tid] = t;
         }
     }
-    __syncthreads();
     // ---- backward
     float* G = Ga;
     float* Gn = Gb;
     for (int l = net.L - 1; l >= 0; l--) {
         const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
-        const float* Xt = smem + net.a_off[l];
-        fused_weights_dispatch<TM>(G, Xt, slab + net.w_off[l], n_in, n_out);
-        fused_bias_grad<TM>(G, slab + net.b_off[l], n_out);
+        const float* Xt = act0 + net.a_off[l];
+        fused_weights_dispatch<TM>(G, Xt, slab + net.w_off[l], slab + net.b_off[l], n_in, n_out);
         if (l > 0) {
-            fused_backward_input<TM>(G, smem + net.wt_off[l], Xt, Gn, n_in, n_out, net.acts[l - 1]);
+            fused_backward_input<TM, RT>(G, img + net.wt_off[l], Xt, Gn, n_in, n_out, net.acts[l - 1]);
             __syncthreads();
             float* tmp = G; G = Gn; Gn = tmp;
         }
@@ -383,15 +424,33 @@ struct ReduceAdamArgs {
     int mode, m_total;
     float ent_coeff;
     const float* log_std;
+    FusedNet layout;         // to refresh the transposed weight image
+    float* image;
+    int apply;               // 0: only write the reduced slab to `reduced` (data-parallel path)
+    float* reduced;
 };
 
-__device__ __forceinline__ void adam_apply(const AdamSeg& s, int i, float g) {
+__device__ __forceinline__ float adam_apply(const AdamSeg& s, int i, float g) {
     float m = s.m[i], v = s.v[i], w = s.w[i];
     m = __fadd_rn(__fmul_rn(s.beta1, m), __fmul_rn(s.omb1, g));
     v = __fadd_rn(__fmul_rn(s.beta2, v), __fmul_rn(s.omb2, __fmul_rn(g, g)));
     const float denom = (float)((double)__fsqrt_rn(__fdiv_rn(v, s.bc2)) + 1e-8);
     w = __fsub_rn(w, __fdiv_rn(__fmul_rn(s.step_size, m), denom));
     s.m[i] = m; s.v[i] = v; s.w[i] = w; s.g[i] = g;
+    return w;
+}
+
+// position of flat parameter e inside the transposed image
+__host__ __device__ inline int image_index(const FusedNet& n, int e) {
+    for (int l = 0; l < n.L; l++) {
+        const int n_in = n.sizes[l], n_out = n.sizes[l + 1];
+        if (e < n.b_off[l]) {
+            const int q = e - n.w_off[l], j = q / n_in, k = q - j * n_in;
+            return n.wt_off[l] + k * pad4(n_out) + j;
+        }
+        if (e < n.b_off[l] + n_out) return n.bs_off[l] + (e - n.b_off[l]);
+    }
+    return -1;
 }
 
 // One CTA per 32 consecutive slab entries; 8 warps split the slabs, fixed-order combine.
@@ -404,8 +463,16 @@ __global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const ReduceAdam
     if (e < total) {
         const int per = (p.nparts + 7) / 8;
         const int b0 = warp * per, b1 = min(p.nparts, b0 + per);
-#pragma unroll 8
-        for (int b = b0; b < b1; b++) s += p.partials[(size_t)b * p.slab + e];
+        const float* src = p.partials + e;
+        int b = b0;
+        for (; b + 8 <= b1; b += 8) {       // 8 independent loads in flight, added in slab order
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = src[(size_t)(b + u) * p.slab];
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += t[u];
+        }
+        for (; b < b1; b++) s += src[(size_t)b * p.slab];
     }
     red[warp][lane] = s;
     __syncthreads();
@@ -413,8 +480,11 @@ __global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const ReduceAdam
     float g = red[0][lane];
 #pragma unroll
     for (int w = 1; w < 8; w++) g += red[w][lane];
+    if (!p.apply) { p.reduced[e] = g; return; }
     if (e < p.P) {
-        adam_apply(p.net, e, g);
+        const float w = adam_apply(p.net, e, g);
+        const int ii = image_index(p.layout, e);
+        if (ii >= 0) p.image[ii] = w;
     } else if (e < p.P + p.A) {
         if (p.mode == kFusedPolicy) adam_apply(p.ls, e - p.P, g + (-p.ent_coeff));   // src/ppo.cu:436-438
     } else {
@@ -428,19 +498,28 @@ __global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const ReduceAdam
     }
 }
 
-// ---- host side ------------------------------------------------------------------------------------
-struct FusedPlan { bool ok; int tm; size_t smem_bytes; FusedNet net; int g_off, b_off, red_off; };
+// (re)build the image from the flat parameters (after host uploads / non-fused updates).  The image was
+// zero-filled at allocation, padding slots are never written, so only parameter slots are refreshed.
+__global__ void __launch_bounds__(256) build_image_kernel(const float* __restrict__ params, float* __restrict__ image, FusedNet n) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n.P; e += gridDim.x * blockDim.x) {
+        const int ii = image_index(n, e);
+        if (ii >= 0) image[ii] = params[e];
+    }
+}
 
-static FusedPlan make_plan(NetDev* nd, int tm) {
+// ---- host side ------------------------------------------------------------------------------------
+struct FusedPlan { bool ok; int tm, rt; size_t smem_bytes; FusedNet net; int g_off, red_off; };
+
+static FusedPlan make_plan(NetDev* nd, int tm, int rt) {
     FusedPlan pl{};
     pl.ok = false;
     const int L = nd->num_layers - 1;
     if (L < 1 || L > kFusedMaxLayers) return pl;
     const int tmp = tm + 4;
-    const int cg = kFusedThreads / (tm / 8);        // column groups of 4
+    const int cg = kFusedThreads / (tm / rt);        // column groups of 4
     FusedNet& n = pl.net;
     n.L = L;
-    int off = 0, maxw = 4, boff = 0;
+    int off = 0, maxw = 4;
     for (int l = 0; l <= L; l++) n.sizes[l] = nd->sizes[l];
     for (int l = 0; l < L; l++) {
         n.acts[l] = nd->acts[l];
@@ -451,56 +530,74 @@ static FusedPlan make_plan(NetDev* nd, int tm) {
         if (n.sizes[l] > 128) return pl;
         n.wt_off[l] = off;
         off += n.sizes[l] * pad4(n.sizes[l + 1]);
-        n.bs_off[l] = boff;
-        boff += pad4(n.sizes[l + 1]);
     }
-    if (n.sizes[L] > 8) return pl;                  // loss heads keep <= 8 outputs in registers
+    for (int l = 0; l < L; l++) { n.bs_off[l] = off; off += pad4(n.sizes[l + 1]); }
+    n.img_floats = (off + 31) & ~31;                 // 128-byte multiple
+    if (n.sizes[L] > 8) return pl;                   // loss heads keep <= 8 outputs in registers
     n.P = (int)nd->param_count;
+    off = 0;
     for (int l = 0; l <= L; l++) {
         n.a_off[l] = off;
         off += pad4(n.sizes[l]) * tmp;
         if (l > 0) maxw = std::max(maxw, pad4(n.sizes[l]));
     }
     n.max_width_pad = maxw;
+    off += n.img_floats;
     pl.g_off = off;
     off += 2 * maxw * tmp;
-    pl.b_off = off;
-    off += boff;
     pl.red_off = off;
-    off += 64 + tm;
+    off += 64 + tm + 4;
     pl.smem_bytes = (size_t)off * sizeof(float);
     pl.tm = tm;
-    pl.ok = pl.smem_bytes <= 220 * 1024;
+    pl.rt = rt;
+    const size_t limit = (tm == 64 && rt == 4) ? 110 * 1024 : 220 * 1024;   // two CTAs per SM in the <64,4> config
+    pl.ok = pl.smem_bytes <= limit;
     return pl;
 }
 
 static FusedPlan choose_plan(NetDev* nd) {
-    FusedPlan p = make_plan(nd, 128);
+    FusedPlan p = make_plan(nd, 64, 4);
     if (p.ok) return p;
-    return make_plan(nd, 64);
+    return make_plan(nd, 64, 8);
 }
 
 bool fused_supported(NeuralNetwork* nn) { return choose_plan(net_dev(nn)).ok; }
 
-static void launch_fused(const FusedPlan& pl, FusedArgs& a) {
+static float* ensure_image(NetDev* nd, const FusedPlan& pl) {
+    if (!nd->image || nd->image_floats != pl.net.img_floats) {
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (nd->image) CUDA_CHECK(cudaFree(nd->image));
+        nd->image = dmalloc<float>(pl.net.img_floats);
+        CUDA_CHECK(cudaMemsetAsync(nd->image, 0, (size_t)pl.net.img_floats * sizeof(float), stream()));
+        nd->image_floats = pl.net.img_floats;
+        nd->image_dirty = true;
+    }
+    if (nd->image_dirty) {
+        B200_LAUNCH(build_image_kernel, std::max(1, std::min(64, div_up(pl.net.P, 256))), 256, 0, nd->params, nd->image, pl.net);
+        nd->image_dirty = false;
+    }
+    return nd->image;
+}
+
+static void launch_fused(NetDev* nd, const FusedPlan& pl, FusedArgs& a) {
     a.net = pl.net;
+    a.image = ensure_image(nd, pl);
     a.smem_g_off = pl.g_off;
-    a.smem_b_off = pl.b_off;
     a.smem_red_off = pl.red_off;
     const int blocks = div_up(a.m, pl.tm);
     static size_t configured[2] = {0, 0};
-    if (pl.tm == 128) {
+    if (pl.rt == 4) {
         if (pl.smem_bytes > configured[0]) {
-            CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+            CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
             configured[0] = pl.smem_bytes;
         }
-        B200_LAUNCH(fused_update_kernel<128>, blocks, kFusedThreads, pl.smem_bytes, a);
+        B200_LAUNCH((fused_update_kernel<64, 4>), blocks, kFusedThreads, pl.smem_bytes, a);
     } else {
         if (pl.smem_bytes > configured[1]) {
-            CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+            CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
             configured[1] = pl.smem_bytes;
         }
-        B200_LAUNCH(fused_update_kernel<64>, blocks, kFusedThreads, pl.smem_bytes, a);
+        B200_LAUNCH((fused_update_kernel<64, 8>), blocks, kFusedThreads, pl.smem_bytes, a);
     }
 }
 
@@ -509,10 +606,9 @@ void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out) {
     const FusedPlan pl = choose_plan(nd);
     if (!pl.ok) B200_FATAL("fused_forward on an unsupported net");
     FusedArgs a{};
-    a.params = nd->params;
     a.idx = nullptr; a.offset = 0; a.limit = m; a.m = m; a.m_total = m; a.mode = kFusedForward;
     a.state = x; a.y_out = y_out;
-    launch_fused(pl, a);
+    launch_fused(nd, pl, a);
 }
 
 static AdamSeg make_seg(float* w, float* g, Adam* adam, float lr) {
@@ -527,10 +623,12 @@ static AdamSeg make_seg(float* w, float* g, Adam* adam, float lr) {
 }
 
 // One fused minibatch update.  policy == nullptr: value net (MSE on adv_target); else the policy.
+// reduced_out != nullptr (data-parallel path): no Adam; the reduced slab [grads | grad_log_std | loss
+// term] is written there and the caller all-reduces and applies the optimiser.
 // Returns false when the net is outside the fused kernel's limits (caller uses the layer-wise path).
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
-                            float epsilon, float ent_coeff, float* loss_slot, bool apply_adam) {
+                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out) {
     NetDev* nd = net_dev(nn);
     const FusedPlan pl = choose_plan(nd);
     if (!pl.ok) return false;
@@ -545,7 +643,6 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
         nd->partials_cap = need;
     }
     FusedArgs a{};
-    a.params = nd->params;
     a.idx = perm; a.offset = offset; a.limit = limit; a.m = m; a.m_total = m_total;
     a.mode = policy ? kFusedPolicy : kFusedValue;
     a.state = b->d_state_p; a.action = b->d_action_p; a.logprob = b->d_logprob_p;
@@ -553,19 +650,25 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
     a.log_std = policy ? policy->d_log_std : nullptr;
     a.epsilon = epsilon; a.ent_coeff = ent_coeff;
     a.partials = nd->partials; a.slab = slab;
-    launch_fused(pl, a);
+    launch_fused(nd, pl, a);
     nd->last_splits = blocks;
 
     ReduceAdamArgs r{};
     r.partials = nd->partials; r.nparts = blocks; r.slab = slab; r.P = (int)nd->param_count; r.A = A;
     r.mode = a.mode; r.m_total = m_total; r.ent_coeff = ent_coeff; r.loss_slot = loss_slot;
     r.log_std = a.log_std;
-    if (!apply_adam) return true;      // data-parallel callers reduce + all-reduce + update themselves
-    adam_net->time_step += 1;
-    r.net = make_seg(nd->params, nd->grads, adam_net, lr);
-    if (policy) {
-        adam_ls->time_step += 1;
-        r.ls = make_seg(policy->d_log_std, policy->d_log_std_grad, adam_ls, lr);
+    r.layout = pl.net; r.image = nd->image;
+    r.apply = reduced_out ? 0 : 1;
+    r.reduced = reduced_out;
+    if (!reduced_out) {
+        adam_net->time_step += 1;
+        r.net = make_seg(nd->params, nd->grads, adam_net, lr);
+        if (policy) {
+            adam_ls->time_step += 1;
+            r.ls = make_seg(policy->d_log_std, policy->d_log_std_grad, adam_ls, lr);
+        }
+    } else {
+        nd->image_dirty = true;     // the caller updates the parameters with the generic Adam kernel
     }
     B200_LAUNCH(fused_reduce_adam_kernel, div_up(slab, 32), 256, 0, r);
     return true;

@@ -90,8 +90,12 @@ struct NetDev {               // device-side view of one NeuralNetwork (side tab
     size_t partials_cap = 0;     // floats
     int last_splits = 1;
     int last_m = 0;
+    float* image = nullptr;      // pre-transposed weight image staged by the fused kernels (fused_mlp.cu)
+    int image_floats = 0;
+    bool image_dirty = true;     // set by every writer of `params` other than fused_reduce_adam_kernel
 };
 NetDev* net_dev(NeuralNetwork* nn);
+void net_mark_params_written(const float* params_ptr);
 // forward without copying the input (training path); output = a.back()
 void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input);
 // backward from grad wrt output (device, [m][out]); leaves split-K slabs in nd->partials
@@ -103,7 +107,7 @@ bool fused_supported(NeuralNetwork* nn);
 void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out);
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
-                            float epsilon, float ent_coeff, float* loss_slot, bool apply_adam);
+                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out);
 
 // ---- policy.cu --------------------------------------------------------------------------------
 void launch_log_prob(const float* mu, const float* log_std, const float* action, float* out, int m, int A);

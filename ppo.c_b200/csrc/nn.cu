@@ -19,6 +19,12 @@ NetDev* net_dev(NeuralNetwork* nn) {
     return it->second;
 }
 
+// Any writer of a parameter arena other than the fused Adam kernel must invalidate the staged image.
+void net_mark_params_written(const float* params_ptr) {
+    for (auto& kv : g_nets)
+        if (params_ptr >= kv.second->params && params_ptr < kv.second->params + kv.second->param_count) kv.second->image_dirty = true;
+}
+
 static void attach_device(NeuralNetwork* nn) {
     ensure_device();
     NetDev* nd = new NetDev();
@@ -211,6 +217,7 @@ void free_neural_network(NeuralNetwork* nn) {
         }
         if (nd->a0_owned) CUDA_CHECK(cudaFree(nd->a0_owned));
         if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
+        if (nd->image) CUDA_CHECK(cudaFree(nd->image));
         delete nd;
         g_nets.erase(it);
     }
@@ -232,6 +239,7 @@ void free_neural_network(NeuralNetwork* nn) {
 
 void nn_write_weights_to_device(NeuralNetwork* nn) {   // src/neural_network.cu:233-239
     NetDev* nd = net_dev(nn);
+    nd->image_dirty = true;
     for (int i = 0; i < nn->num_layers - 1; i++) {
         const Layer& L = nn->layers[i];
         CUDA_CHECK(cudaMemcpyAsync(nd->params + nd->w_off[i], L.weights, (size_t)L.input_size * L.output_size * sizeof(float), cudaMemcpyHostToDevice, stream()));

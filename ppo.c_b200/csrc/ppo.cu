@@ -172,11 +172,19 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     for (int j = 0; j < n_epochs_value; j++) {
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
-            if (fusedV && G == 1) {
+            if (fusedV) {
+                float* red = G > 1 ? static_cast<float*>(scratch(kScratchMisc, (ndV->param_count + 2) * sizeof(float))) : nullptr;
                 fused_minibatch_update(ppo->V, nullptr, ppo->adam_V, nullptr, ppo->lr_V, perm, k * batch_size + row0, limit,
-                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, true);
+                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, red);
+                if (G > 1) {   // slab-reduce -> NCCL all-reduce -> Adam
+                    dist_allreduce_sum(red, ndV->param_count + 2);
+                    ppo->adam_V->time_step += 1;
+                    adam_flat(ndV->params, red, ppo->adam_V->m, ppo->adam_V->v, (int)ndV->param_count, ppo->lr_V,
+                              ppo->adam_V->beta1, ppo->adam_V->beta2, ppo->adam_V->time_step, nullptr, 0, 0);
+                }
                 continue;
             }
+            ndV->image_dirty = true;
             launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
                           b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
             net_forward(ppo->V, t->states, mb_local, true);
@@ -199,12 +207,24 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     for (int j = 0; j < n_epochs_policy; j++) {
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
-            if (fusedP && G == 1) {
+            if (fusedP) {
+                float* red = G > 1 ? static_cast<float*>(scratch(kScratchMisc, (ndP->param_count + A + 1) * sizeof(float))) : nullptr;
                 fused_minibatch_update(pol->mu, pol, ppo->adam_policy, ppo->adam_entropy, ppo->lr_policy, perm,
                                        k * batch_size + row0, limit, mb_local, mb_total, b, ppo->epsilon, ppo->ent_coeff,
-                                       t->d_scalars + 1, true);
+                                       t->d_scalars + 1, red);
+                if (G > 1) {
+                    if (ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
+                    dist_allreduce_sum(red, ndP->param_count + A + 1);
+                    ppo->adam_entropy->time_step += 1;
+                    ppo->adam_policy->time_step += 1;
+                    adam_flat(pol->d_log_std, red + ndP->param_count, ppo->adam_entropy->m, ppo->adam_entropy->v, A, ppo->lr_policy,
+                              ppo->adam_entropy->beta1, ppo->adam_entropy->beta2, ppo->adam_entropy->time_step, nullptr, 0, 0);
+                    adam_flat(ndP->params, red, ppo->adam_policy->m, ppo->adam_policy->v, (int)ndP->param_count, ppo->lr_policy,
+                              ppo->adam_policy->beta1, ppo->adam_policy->beta2, ppo->adam_policy->time_step, nullptr, 0, 0);
+                }
                 continue;
             }
+            ndP->image_dirty = true;
             launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
                           b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
             net_forward(pol->mu, t->states, mb_local, true);
