@@ -401,6 +401,14 @@ void ppo_b200_set_permutation_mode(PPO* ppo, int mode, unsigned long long seed);
 /* kernel path of the update/GAE-forward: -1 default (fused small-net kernels when every layer width
  * is <= 128, else layer-wise; env PPO_B200_FUSED=0 disables), 0 = force layer-wise, 1 = force fused. */
 void ppo_b200_set_kernel_path(int path);
+/* matmul precision of dense layers whose in/out widths are >= 64 and batch >= 128:
+ * 0 = fp32 FFMA (default; 1e-5 tolerance), 1 = TF32 tcgen05 tensor cores with fp32 accumulation
+ * (wide-MLP configs; tolerance ~1e-3, stated separately).  Env PPO_B200_TF32=1 sets the default. */
+void ppo_b200_set_matmul_precision(int mode);
+/* raw tensor-core layer kernels (tests/bench): mode 0 forward (aux = bias), 1 backward-input
+ * (aux = post-activation input), 2 backward-weights (out = `splits` slabs of l*n floats). */
+void ppo_b200_tc_linear(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l,
+                        int act, int splits);
 /* Running observation normalisation (new; Welford merge of include/welford_var.h:33-40): 0 = off. */
 void ppo_b200_set_obs_norm(PPO* ppo, int enabled);
 /* mean undiscounted return per episode of the last device rollout (eval_ppo's "R", src/ppo.cu:581) */

@@ -197,8 +197,18 @@ int choose_splits(int m, size_t param_count) {
     return (int)std::min(s, cap);
 }
 
+static int g_matmul_precision = -1;
+int matmul_precision() {
+    if (g_matmul_precision < 0) { const char* e = getenv("PPO_B200_TF32"); g_matmul_precision = (e && e[0] == '1') ? 1 : 0; }
+    return g_matmul_precision;
+}
+static bool use_tc(int m, int n, int l, const void* a, const void* b, int lda, int ldb) {
+    return matmul_precision() == 1 && m >= 128 && n >= 64 && l >= 64 && tc_shape_ok(a, b, lda, ldb);
+}
+
 void linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act) {
     if (m <= 0) return;
+    if (use_tc(m, n, l, x, W, n, n) && (l % 4) == 0) { tc_linear_forward(y, x, W, b, m, n, l, act); return; }
     if (l <= 8) {
         const int blocks = std::min(div_up(m, 8), num_sms() * 8);
         B200_LAUNCH(linear_forward_skinny_kernel, blocks, 256, 0, y, x, W, b, m, n, l, act);
@@ -213,6 +223,7 @@ void linear_forward(float* y, const float* x, const float* W, const float* b, in
 
 void linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev) {
     if (m <= 0) return;
+    if (use_tc(m, n, l, g, W, l, n)) { tc_linear_backward_input(gx, g, W, xin, m, n, l, act_prev); return; }
     GemmArgs a{};
     a.A = g; a.B = W; a.C = gx; a.M = m; a.N = n; a.K = l; a.lda = l; a.ldb = n; a.ldc = n;
     a.xin = xin; a.act = act_prev;
@@ -224,7 +235,13 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
                             const float* x, int m, int n, int l) {
     if (m <= 0) return;
     int rows = div_up(m, splits);
-    rows = div_up(rows, kBK) * kBK;
+    rows = div_up(rows, 32) * 32;          // multiple of both tile depths (16 FFMA, 32 TF32)
+    if (use_tc(m, n, l, g, x, l, n) && ((stride * 4) % 16) == 0 && ((uintptr_t)gW_part & 15) == 0) {
+        tc_linear_backward_weights(gW_part, stride, splits, g, x, m, n, l);
+        dim3 grid2(div_up(l, 32), splits, 1);
+        B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+        return;
+    }
     GemmArgs a{};
     a.A = g; a.B = x; a.C = gW_part; a.M = l; a.N = n; a.K = m; a.lda = l; a.ldb = n; a.ldc = n;
     a.k_per_split = rows; a.c_split_stride = stride;
@@ -250,6 +267,8 @@ void activation_grad_inplace(const float* y, float* grad, long long count, int a
 using namespace b200;
 
 extern "C" {
+
+void ppo_b200_set_matmul_precision(int mode) { g_matmul_precision = mode ? 1 : 0; }
 
 // include/mat_mul.h:19-20 (device pointers; handle ignored)
 void mat_mul_cuda(cublasHandle_t handle, float* out, float* x, float* weight, float* bias, int m, int n, int l) {

@@ -70,6 +70,14 @@ int choose_splits(int m, size_t param_count);
 void activation_inplace(float* x, long long count, int act);
 void activation_grad_inplace(const float* y, float* grad, long long count, int act);
 
+// ---- tc_gemm.cu (tcgen05 TF32 tensor-core path for wide layers) --------------------------------
+bool tc_shape_ok(const void* a, const void* b, int lda_cols, int ldb_cols);
+void tc_linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act);
+void tc_linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev);
+void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l);
+void tc_round_copy(const float* src, float* dst, size_t n);   // RNA-rounded TF32 shadow of a weight arena
+int matmul_precision();   // 0 fp32 FFMA (default), 1 TF32 tcgen05 for layers with n, l >= 64
+
 // ---- nn.cu ------------------------------------------------------------------------------------
 struct NetDev {               // device-side view of one NeuralNetwork (side table keyed by pointer)
     int num_layers = 0;       // reference convention: number of sizes (weight layers = num_layers-1)
@@ -90,6 +98,7 @@ struct NetDev {               // device-side view of one NeuralNetwork (side tab
     size_t partials_cap = 0;     // floats
     int last_splits = 1;
     int last_m = 0;
+    float* params_tf32 = nullptr;   // RNA-rounded shadow of `params` read by the tensor-core layers
     float* image = nullptr;      // pre-transposed weight image staged by the fused kernels (fused_mlp.cu)
     int image_floats = 0;
     bool image_dirty = true;     // set by every writer of `params` other than fused_reduce_adam_kernel

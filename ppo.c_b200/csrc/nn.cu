@@ -107,8 +107,16 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
         nd->a0_borrowed = false;
     }
     nn->layers[0].d_input = nd->a[0];
+    // TF32 mode: the tensor-core layers read an RNA-rounded shadow of the weights (refreshed per forward,
+    // i.e. once per optimiser step; backward re-uses it).  Biases stay fp32 (added in the epilogue).
+    const float* wsrc = nd->params;
+    if (matmul_precision() == 1) {
+        if (!nd->params_tf32) nd->params_tf32 = dmalloc<float>(nd->param_count);
+        tc_round_copy(nd->params, nd->params_tf32, nd->param_count);
+        wsrc = nd->params_tf32;
+    }
     for (int i = 0; i < L; i++)
-        linear_forward(nd->a[i + 1], nd->a[i], nd->params + nd->w_off[i], nd->params + nd->b_off[i], m,
+        linear_forward(nd->a[i + 1], nd->a[i], wsrc + nd->w_off[i], nd->params + nd->b_off[i], m,
                        nd->sizes[i], nd->sizes[i + 1], nd->acts[i]);
     nn->cache_m_forward = m;
     nd->last_m = m;
@@ -141,7 +149,8 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->param_count, splits, g,
                                nd->a[i], m, n, l);
         if (i > 0) {  // dX of layer 0 is unused by every caller (the reference computes it anyway)
-            linear_backward_input(nd->gx[i], g, nd->params + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
+            const float* wsrc = (matmul_precision() == 1 && nd->params_tf32) ? nd->params_tf32 : nd->params;
+            linear_backward_input(nd->gx[i], g, wsrc + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
             g = nd->gx[i];
         }
     }
@@ -218,6 +227,7 @@ void free_neural_network(NeuralNetwork* nn) {
         if (nd->a0_owned) CUDA_CHECK(cudaFree(nd->a0_owned));
         if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
         if (nd->image) CUDA_CHECK(cudaFree(nd->image));
+        if (nd->params_tf32) CUDA_CHECK(cudaFree(nd->params_tf32));
         delete nd;
         g_nets.erase(it);
     }

@@ -1,0 +1,354 @@
+// tc_gemm.cu — tcgen05 (5th-gen tensor core) GEMMs for the wide-MLP configs (SURVEY.md §8 rows a9/a10,
+// BASELINE config 4: 3x1024 nets, minibatch 65536).
+//
+// The reference runs these layers as cublasSgemm FP32 (src/mat_mul.cu:149-208).  Here one warp-specialised
+// kernel template covers the three contractions of a dense layer directly on the row-major fp32 arrays
+// the rest of the library uses — no transposed copies, no dtype conversion passes:
+//
+//   forward   y  = act(x . W^T + b)      A = x  [m][in]   K-major     B = W [out][in]  K-major
+//   dX        gx = (g . W) * act'(h)     A = g  [m][out]  K-major     B = W [out][in]  MN-major (k = out)
+//   dW        gW = g^T . x  (split-K)    A = g  [m][out]  MN-major    B = x [m][in]    MN-major (k = batch)
+//
+// Operands are fed as TF32 (tcgen05.mma kind::tf32 reads the fp32 words and uses the top 19 bits),
+// accumulation is fp32 in TMEM.  Tolerance for this path is stated separately from the fp32 kernels
+// (north-star): ~1e-3 norm-wise on layer outputs / gradients, measured in tests/test_gpu_tc.py.
+//
+// Kernel anatomy (Blackwell guide "canonical GEMM"): 192 threads =
+//   warp 0  TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage shared-memory ring,
+//                          mbarrier expect_tx / complete_tx
+//   warp 1  MMA issuer     one elected lane issues tcgen05.mma (M=128, N=BN, K=8) from shared-memory
+//                          descriptors; tcgen05.commit releases ring slots and publishes the accumulator
+//   warps 2-5 epilogue     tcgen05.ld 32x32b.x32 TMEM -> registers, fused bias+activation /
+//                          activation-derivative mask, 128-byte row stores
+// One 128 x BN output tile per CTA, fp32 accumulator = BN TMEM columns.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200 {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBKBytes = 128;            // one 128B swizzle row per k-block
+constexpr int kTcBK = kTcBKBytes / 4;      // 32 tf32 elements
+constexpr int kTcUmmaK = 8;                // tf32: 32 bytes
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 192;
+
+enum TcEpilogue { kTcFwd = 0, kTcDx = 1, kTcDw = 2 };
+
+struct TcArgs {
+    float* C;
+    int M, N, K;            // GEMM extents (output M x N, reduction K)
+    int ldc;
+    const float* bias;      // kTcFwd
+    const float* xin;       // kTcDx: post-activation input of the layer [M][N]
+    int act;
+    int k_per_split;        // kTcDw: reduction rows per blockIdx.z
+    size_t c_split_stride;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout SWIZZLE_128B (2) <<61
+// K-major operands use SWIZZLE_128B (16-byte chunks, 8-row atoms).  MN-major TF32 operands must use
+// SWIZZLE_128B_BASE32B (layout type 1: 32-byte chunks, 4-row atoms; cutlass sm100_common.inl: "for mn-major
+// tf32 operands, SW128_32B is the only available smem layout"), fed by TMA's SWIZZLE_128B_ATOM_32B mode.
+__device__ __forceinline__ uint64_t tc_make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+// Round-to-nearest fp32 -> tf32 (kept in an fp32 word).  kind::tf32 TRUNCATES its operands; truncation is
+// biased (every product shrinks), and the bias compounds through the layers.  Outputs that feed the next
+// tensor-core GEMM are therefore stored already RNA-rounded, so the next MMA reads exact TF32 values.
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = round_tf32(src[i]);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+    constexpr uint32_t A_BYTES = kTcBM * kTcBKBytes;           // 16 KB per stage
+    constexpr uint32_t B_BYTES = BN * kTcBKBytes;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTcStages * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + kTcStages;
+    uint64_t* tmem_full_bar = empty_bar + kTcStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
+    int kbeg = 0, kend = p.K;
+    if (EPI == kTcDw) { kbeg = blockIdx.z * p.k_per_split; kend = min(p.K, kbeg + p.k_per_split); }
+    const int num_kb = max(0, (kend - kbeg + kTcBK - 1) / kTcBK);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
+        for (int s = 0; s < kTcStages; s++) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], 1); }
+        tc_mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation is warp-wide; BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % kTcStages;
+                const uint32_t phase = (kb / kTcStages) & 1;
+                tc_mbar_wait(&empty_bar[s], phase ^ 1);
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                tc_mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                const int k0 = kbeg + kb * kTcBK;
+                if (!A_MN) {
+                    tc_tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                         // box {32 k, 128 rows}
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kTcBM / 32; i++)                                        // box {32 mn, 32 k-rows}
+                        tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + 32 * i, k0, &full_bar[s]);
+                }
+                if (!B_MN) {
+                    tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BN / 32; i++)
+                        tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * i, k0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % kTcStages;
+                const uint32_t phase = (kb / kTcStages) & 1;
+                tc_mbar_wait(&full_bar[s], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = s_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < kTcBK / kTcUmmaK; k++) {
+                    // K-major: 8 rows x 128 B swizzle atoms, 1024 B apart; a k-step is 32 B inside the row.
+                    // MN-major: 32-element (128 B) MN chunks kTcBK*128 B apart (LBO), 4 k-rows = 512 B atoms (SBO);
+                    //           a k-step (8 k-rows) spans two atoms = 1024 B.
+                    const uint64_t da = A_MN ? tc_make_desc(sa + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sa + k * 32, 16, 1024, 2);
+                    const uint64_t db = B_MN ? tc_make_desc(sb + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sb + k * 32, 16, 1024, 2);
+                    tc_umma_tf32(tmem_base, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
+            }
+            tc_umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        tc_mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* Crow = p.C + (EPI == kTcDw ? (size_t)blockIdx.z * p.c_split_stride : 0) + (size_t)row * p.ldc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            if (num_kb > 0) {
+                tc_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) r[j] = 0u;
+            }
+            if (row < p.M) {
+                const int nb = n0 + c0;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                if (EPI == kTcFwd) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (nb + j < p.N) v[j] = round_tf32(act_apply(v[j] + __ldg(p.bias + nb + j), p.act));
+                } else if (EPI == kTcDx) {
+                    if (p.act != kActNone) {
+                        const float* hrow = p.xin + (size_t)row * p.N + nb;
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
+                }
+                if (nb + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(Crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (nb + j < p.N) Crow[nb + j] = v[j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---- host: tensor maps --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) B200_FATAL("cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Row-major fp32 matrix [rows][cols]; box = {box_cols (innermost, 128 B), box_rows}, 128B swizzle.
+static CUtensorMap make_map(const float* base, int rows, int cols, int box_cols, int box_rows, bool mn_major = false) {
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) B200_FATAL("cuTensorMapEncodeTiled failed (%d) for %dx%d box %dx%d", (int)r, rows, cols, box_rows, box_cols);
+    return m;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
+    const size_t smem = (size_t)kTcStages * (kTcBM + BN) * kTcBKBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI>), grid, kTcThreads, smem, ta, tb, a);
+}
+
+// Shapes the tensor path accepts: TMA needs 16-byte row pitches and aligned bases.
+bool tc_shape_ok(const void* a, const void* b, int lda_cols, int ldb_cols) {
+    return ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && (lda_cols % 4) == 0 && (ldb_cols % 4) == 0;
+}
+
+void tc_round_copy(const float* src, float* dst, size_t n) {
+    if (n == 0) return;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)num_sms() * 8);
+    B200_LAUNCH(round_tf32_kernel, blocks, 256, 0, src, dst, n);
+}
+
+constexpr int kTcBN = 256;
+
+void tc_linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act) {
+    TcArgs a{};
+    a.C = y; a.M = m; a.N = l; a.K = n; a.ldc = l; a.bias = b; a.act = act;
+    const CUtensorMap ta = make_map(x, m, n, kTcBK, kTcBM);        // A K-major
+    const CUtensorMap tb = make_map(W, l, n, kTcBK, kTcBN);        // B K-major
+    launch_tc<kTcBN, false, false, kTcFwd>(ta, tb, a, dim3(div_up(l, kTcBN), div_up(m, kTcBM), 1));
+}
+
+void tc_linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev) {
+    TcArgs a{};
+    a.C = gx; a.M = m; a.N = n; a.K = l; a.ldc = n; a.xin = xin; a.act = act_prev;
+    const CUtensorMap ta = make_map(g, m, l, kTcBK, kTcBM);        // A K-major (k = out)
+    const CUtensorMap tb = make_map(W, l, n, 32, kTcBK, true);     // B MN-major: W[k=out][n=in], box {32 n, 32 k}
+    launch_tc<kTcBN, false, true, kTcDx>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(m, kTcBM), 1));
+}
+
+void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l) {
+    TcArgs a{};
+    int rows = div_up(m, splits);
+    rows = div_up(rows, kTcBK) * kTcBK;
+    a.C = gW_part; a.M = l; a.N = n; a.K = m; a.ldc = n; a.k_per_split = rows; a.c_split_stride = stride;
+    const CUtensorMap ta = make_map(g, m, l, 32, kTcBK, true);     // A MN-major: g[k=batch][m'=out]
+    const CUtensorMap tb = make_map(x, m, n, 32, kTcBK, true);     // B MN-major: x[k=batch][n=in]
+    launch_tc<kTcBN, true, true, kTcDw>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// Test / bench entry point: mode 0 forward, 1 backward-input, 2 backward-weights (one slab per split).
+extern "C" void ppo_b200_tc_linear(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l,
+                                   int act, int splits) {
+    if (mode == 0) tc_linear_forward(out, a, b, aux, m, n, l, act);
+    else if (mode == 1) tc_linear_backward_input(out, a, b, aux, m, n, l, act);
+    else tc_linear_backward_weights(out, (size_t)n * l, splits, a, b, m, n, l);
+}
