@@ -14,8 +14,11 @@
 //     (4 tiles x 32 lanes x float4; all global loads/stores are 128-bit, coalesced, L1-bypassing);
 //   * inside a tile: 4-element serial recurrence per lane + 5-step warp-shuffle suffix scan;
 //   * across chunks: decoupled look-back.  Chunks are claimed in DESCENDING order through an
-//     atomic ticket, each publishes (C_total, A_first) then its inclusive A_first with
-//     st.release; a successor chunk is therefore always resident or finished -> no deadlock.
+//     atomic ticket; each publishes ONE self-contained 64-bit word {epoch, state, A_first} — first its
+//     aggregate (state says whether the chunk contains a done, i.e. whether C_total is 0 or
+//     (gamma*lambda)^512), later its inclusive value.  Because flag and payload share one naturally
+//     atomic word no fence is needed (an ncu pass showed st.release membars costing 27% of the stall
+//     samples); a successor chunk is always resident or finished -> no deadlock.
 //     A chunk whose last element is done (every env stream of a TxN buffer) never looks back.
 // Algorithmic HBM traffic: 12 B (r,v,v') + 2 B (flags) read + 8 B written = 22 B/element; the
 // optional normalisation is a second 8 B/element pass -> 30 B/element.
@@ -29,185 +32,268 @@
 namespace b200 {
 
 constexpr int kGaeWarps = 8;
-constexpr int kGaeTiles = 4;
 constexpr int kGaeTile = 128;                         // 32 lanes x 4
-constexpr int kGaeChunk = kGaeTile * kGaeTiles;       // 512 elements per warp
-constexpr int kGaeBlockElems = kGaeChunk * kGaeWarps; // 4096 elements per CTA
 
-struct GaeDesc {                 // each word = (epoch << 32) | float bits
-    unsigned long long aggA;     // A_first with zero carry-in
-    unsigned long long aggC;     // product of c over the chunk
-    unsigned long long inc;      // A_first including everything behind the chunk
-    unsigned long long pad;
-};
+// One descriptor word per chunk: [63:34] epoch, [33:32] state, [31:0] float bits of A_first.
+enum { kGaeAggDone = 1u, kGaeAggOpen = 2u, kGaeInclusive = 3u };
+typedef unsigned long long GaeDesc;
 
-__device__ __forceinline__ unsigned long long pack(unsigned epoch, float x) {
-    return ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(x);
+__device__ __forceinline__ unsigned long long pack(unsigned epoch, unsigned state, float x) {
+    return ((unsigned long long)epoch << 34) | ((unsigned long long)state << 32) | (unsigned long long)__float_as_uint(x);
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    return r;
 }
 
-__global__ void __launch_bounds__(kGaeWarps * 32)
+template <int kGaeTiles>
+struct GaeRaw {                      // one chunk as it comes out of HBM: 14 registers per tile and lane
+    float4 r[kGaeTiles], v[kGaeTiles], vn[kGaeTiles];
+    uint32_t ft[kGaeTiles], fr[kGaeTiles];     // 4 terminated / truncated bytes each
+};
+
+template <int kGaeTiles, bool HINT>
+__device__ __forceinline__ void gae_load_chunk(GaeRaw<kGaeTiles>& raw, long long base, int lane, int n, int vec_ok,
+                                               const float* __restrict__ reward, const float* __restrict__ v,
+                                               const float* __restrict__ v_next, const unsigned char* __restrict__ terminated,
+                                               const unsigned char* __restrict__ truncated) {
+#pragma unroll
+    for (int t = 0; t < kGaeTiles; t++) {
+        const long long i0 = base + t * kGaeTile + lane * 4;
+        if (vec_ok && i0 + 3 < n) {
+            if (HINT) {
+                raw.r[t] = ld_stream4(reward + i0);
+                raw.v[t] = ld_stream4(v + i0);
+                raw.vn[t] = ld_stream4(v_next + i0);
+                raw.ft[t] = ld_stream_u32(terminated + i0);
+                raw.fr[t] = ld_stream_u32(truncated + i0);
+            } else {
+                raw.r[t] = __ldg(reinterpret_cast<const float4*>(reward + i0));
+                raw.v[t] = __ldg(reinterpret_cast<const float4*>(v + i0));
+                raw.vn[t] = __ldg(reinterpret_cast<const float4*>(v_next + i0));
+                raw.ft[t] = __ldg(reinterpret_cast<const uint32_t*>(terminated + i0));
+                raw.fr[t] = __ldg(reinterpret_cast<const uint32_t*>(truncated + i0));
+            }
+        } else {   // ragged tail / unaligned buffers: padding behaves as a terminated, zero-delta step
+            float rr[4], vv[4], nn[4];
+            uint32_t ft = 0, fr = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const bool ok = i0 + e < n;
+                rr[e] = ok ? reward[i0 + e] : 0.f;
+                vv[e] = ok ? v[i0 + e] : 0.f;
+                nn[e] = ok ? v_next[i0 + e] : 0.f;
+                ft |= (uint32_t)(ok ? (terminated[i0 + e] != 0) : 1) << (8 * e);
+                fr |= (uint32_t)(ok ? (truncated[i0 + e] != 0) : 1) << (8 * e);
+            }
+            raw.r[t] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+            raw.v[t] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            raw.vn[t] = make_float4(nn[0], nn[1], nn[2], nn[3]);
+            raw.ft[t] = ft;
+            raw.fr[t] = fr;
+        }
+    }
+}
+
+// Persistent kernel: global warp g handles chunks nchunks-1-(i*W+g), i = 0,1,...  (descending order, so a
+// chunk's successor is handled in the same or an earlier iteration by a resident warp -> the look-back
+// cannot deadlock as long as the whole grid is co-resident, which the host guarantees through the
+// occupancy API).  While a chunk is being scanned the NEXT chunk's 20 loads per lane are already in
+// flight (register double buffering), so every warp keeps HBM requests outstanding all the time.
+template <int kGaeTiles, bool HINT, int MINB>
+__global__ void __launch_bounds__(kGaeWarps * 32, MINB)
 gae_scan_kernel(const float* __restrict__ reward, const float* __restrict__ v,
                 const float* __restrict__ v_next, const unsigned char* __restrict__ terminated,
                 const unsigned char* __restrict__ truncated, int n, float gamma, float gl,
                 float* __restrict__ adv_out, float* __restrict__ target_out, GaeDesc* desc,
-                int* ticket, unsigned epoch, float4* __restrict__ wstats, int vec_ok) {
-    __shared__ int s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int cb = (int)gridDim.x - 1 - s_ticket;      // descending chunk order
+                unsigned epoch, float4* __restrict__ wstats, int vec_ok) {
+    constexpr int kGaeChunk = kGaeTile * kGaeTiles;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = (n + kGaeChunk - 1) / kGaeChunk;
-    const int wc = cb * kGaeWarps + warp;
-    if (wc >= nchunks) return;
-    const long long base = (long long)wc * kGaeChunk;
+    const int W = gridDim.x * kGaeWarps;
+    const int g = blockIdx.x * kGaeWarps + warp;
+    int wc = nchunks - 1 - g;
+    if (wc < 0) return;
+    float cfull = gl;
+#pragma unroll
+    for (int q = 1; q < kGaeChunk; q <<= 1) cfull *= cfull;     // gl^chunk: C_total of a chunk without a done step
 
-    float dl[kGaeTiles][4], cc[kGaeTiles][4], vv[kGaeTiles][4];
+    GaeRaw<kGaeTiles> cur;
+    gae_load_chunk<kGaeTiles, HINT>(cur, (long long)wc * kGaeChunk, lane, n, vec_ok, reward, v, v_next, terminated, truncated);
+    for (; wc >= 0; wc -= W) {
+        const long long base = (long long)wc * kGaeChunk;
+        GaeRaw<kGaeTiles> nxt;
+        const bool has_next = wc - W >= 0;
+        if (has_next) gae_load_chunk<kGaeTiles, HINT>(nxt, (long long)(wc - W) * kGaeChunk, lane, n, vec_ok, reward, v, v_next, terminated, truncated);
+
+        float dl[kGaeTiles][4], cc[kGaeTiles][4];
 #pragma unroll
-    for (int t = 0; t < kGaeTiles; t++) {
-        const long long i0 = base + t * kGaeTile + lane * 4;
-        float r4[4], n4[4];
-        unsigned char te[4], tr[4];
-        if (vec_ok && i0 + 3 < n) {
-            const float4 a = ld_stream4(reward + i0), b = ld_stream4(v + i0), c = ld_stream4(v_next + i0);
-            const uint32_t ft = ld_stream_u32(terminated + i0), fr = ld_stream_u32(truncated + i0);
-            r4[0] = a.x; r4[1] = a.y; r4[2] = a.z; r4[3] = a.w;
-            vv[t][0] = b.x; vv[t][1] = b.y; vv[t][2] = b.z; vv[t][3] = b.w;
-            n4[0] = c.x; n4[1] = c.y; n4[2] = c.z; n4[3] = c.w;
-#pragma unroll
-            for (int e = 0; e < 4; e++) { te[e] = (ft >> (8 * e)) & 0xff; tr[e] = (fr >> (8 * e)) & 0xff; }
-        } else {
+        for (int t = 0; t < kGaeTiles; t++) {
+            const float r4[4] = {cur.r[t].x, cur.r[t].y, cur.r[t].z, cur.r[t].w};
+            const float v4[4] = {cur.v[t].x, cur.v[t].y, cur.v[t].z, cur.v[t].w};
+            const float n4[4] = {cur.vn[t].x, cur.vn[t].y, cur.vn[t].z, cur.vn[t].w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const bool ok = i0 + e < n;
-                r4[e] = ok ? reward[i0 + e] : 0.f;
-                vv[t][e] = ok ? v[i0 + e] : 0.f;
-                n4[e] = ok ? v_next[i0 + e] : 0.f;
-                te[e] = ok ? terminated[i0 + e] : 1;   // padding behaves as a terminated, zero-delta step
-                tr[e] = ok ? truncated[i0 + e] : 1;
+                const bool te = (cur.ft[t] >> (8 * e)) & 0xff, tr = (cur.fr[t] >> (8 * e)) & 0xff;
+                dl[t][e] = r4[e] + gamma * n4[e] * (te ? 0.f : 1.f) - v4[e];
+                cc[t][e] = (te || tr) ? 0.f : gl;
             }
         }
+        // ---- local scan (zero carry-in): loc = advantage, cend = product of c from element to chunk end
+        float loc[kGaeTiles][4], cend[kGaeTiles][4];
+        float X = 0.f, Cx = 1.f;   // head of the already-scanned suffix (tiles behind this one)
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const float nt = te[e] ? 0.f : 1.f;
-            dl[t][e] = r4[e] + gamma * n4[e] * nt - vv[t][e];
-            cc[t][e] = (te[e] || tr[e]) ? 0.f : gl;
+        for (int t = kGaeTiles - 1; t >= 0; t--) {
+            float A = 0.f, C = 1.f;
+#pragma unroll
+            for (int e = 3; e >= 0; e--) { A = dl[t][e] + cc[t][e] * A; C = cc[t][e] * C; }
+            float Ai = A, Ci = C;  // inclusive suffix over lanes lane..31
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float Ao = __shfl_down_sync(kFull, Ai, off), Co = __shfl_down_sync(kFull, Ci, off);
+                if (lane + off < 32) { Ai = Ai + Ci * Ao; Ci = Ci * Co; }
+            }
+            const float An = __shfl_down_sync(kFull, Ai, 1), Cn = __shfl_down_sync(kFull, Ci, 1);
+            float a = (lane == 31) ? X : An + Cn * X;
+            float ce = (lane == 31) ? Cx : Cn * Cx;
+#pragma unroll
+            for (int e = 3; e >= 0; e--) {
+                a = dl[t][e] + cc[t][e] * a;
+                ce = cc[t][e] * ce;
+                loc[t][e] = a;
+                cend[t][e] = ce;
+            }
+            X = __shfl_sync(kFull, loc[t][0], 0);
+            Cx = __shfl_sync(kFull, cend[t][0], 0);
         }
-    }
-
-    // ---- local scan (zero carry-in): loc = advantage, cend = product of c from element to chunk end
-    float loc[kGaeTiles][4], cend[kGaeTiles][4];
-    float X = 0.f, Cx = 1.f;   // head of the already-scanned suffix (tiles behind this one)
-#pragma unroll
-    for (int t = kGaeTiles - 1; t >= 0; t--) {
-        float A = 0.f, C = 1.f;
-#pragma unroll
-        for (int e = 3; e >= 0; e--) { A = dl[t][e] + cc[t][e] * A; C = cc[t][e] * C; }
-        float Ai = A, Ci = C;  // inclusive suffix over lanes lane..31
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const float Ao = __shfl_down_sync(kFull, Ai, off), Co = __shfl_down_sync(kFull, Ci, off);
-            if (lane + off < 32) { Ai = Ai + Ci * Ao; Ci = Ci * Co; }
-        }
-        const float An = __shfl_down_sync(kFull, Ai, 1), Cn = __shfl_down_sync(kFull, Ci, 1);
-        float a = (lane == 31) ? X : An + Cn * X;
-        float ce = (lane == 31) ? Cx : Cn * Cx;
-#pragma unroll
-        for (int e = 3; e >= 0; e--) {
-            a = dl[t][e] + cc[t][e] * a;
-            ce = cc[t][e] * ce;
-            loc[t][e] = a;
-            cend[t][e] = ce;
-        }
-        X = __shfl_sync(kFull, loc[t][0], 0);
-        Cx = __shfl_sync(kFull, cend[t][0], 0);
-    }
-
-    // ---- publish the chunk aggregate, then resolve the carry-in by looking at later chunks
-    if (lane == 0) {
-        st_release_u64(&desc[wc].aggA, pack(epoch, X));
-        st_release_u64(&desc[wc].aggC, pack(epoch, Cx));
-    }
-    const float c_last = __shfl_sync(kFull, cend[kGaeTiles - 1][3], 31);
-    float carry = 0.f;
-    if (c_last != 0.f && wc + 1 < nchunks) {   // warp-uniform
-        if (lane == 0) {
-            float mult = 1.f;
-            int j = wc + 1;
-            while (j < nchunks) {
-                const unsigned long long inc = ld_acquire_u64(&desc[j].inc);
-                if ((unsigned)(inc >> 32) == epoch) { carry += mult * __uint_as_float((unsigned)inc); break; }
-                const unsigned long long a = ld_acquire_u64(&desc[j].aggA);
-                const unsigned long long c = ld_acquire_u64(&desc[j].aggC);
-                if ((unsigned)(a >> 32) == epoch && (unsigned)(c >> 32) == epoch) {
-                    carry += mult * __uint_as_float((unsigned)a);
-                    mult *= __uint_as_float((unsigned)c);
+        // ---- publish the chunk aggregate, then resolve the carry-in by looking at later chunks.
+        // Cx is exactly 0 when the chunk holds a done step, else (gamma*lambda)^512 up to rounding.
+        if (lane == 0) st_relaxed_u64(&desc[wc], pack(epoch, Cx == 0.f ? kGaeAggDone : kGaeAggOpen, X));
+        const float c_last = __shfl_sync(kFull, cend[kGaeTiles - 1][3], 31);
+        float carry = 0.f;
+        if (c_last != 0.f && wc + 1 < nchunks) {   // warp-uniform
+            if (lane == 0) {
+                float mult = 1.f;
+                int j = wc + 1;
+                while (j < nchunks) {
+                    const unsigned long long w = ld_relaxed_u64(&desc[j]);
+                    if ((unsigned)(w >> 34) != epoch) { __nanosleep(20); continue; }
+                    const unsigned state = (unsigned)(w >> 32) & 3u;
+                    carry += mult * __uint_as_float((unsigned)w);
+                    if (state != kGaeAggOpen) break;            // inclusive value, or the chunk cuts the chain
+                    mult *= cfull;
                     if (mult == 0.f) break;
                     j++;
-                } else {
-                    __nanosleep(40);
                 }
             }
+            carry = __shfl_sync(kFull, carry, 0);
         }
-        carry = __shfl_sync(kFull, carry, 0);
-    }
-    if (lane == 0) st_release_u64(&desc[wc].inc, pack(epoch, X + Cx * carry));
+        if (lane == 0 && Cx != 0.f) st_relaxed_u64(&desc[wc], pack(epoch, kGaeInclusive, X + Cx * carry));
 
-    // ---- final values, stores, Welford partial
-    float sum = 0.f;
-    int cnt = 0;
+        // ---- final values, stores, Welford partial
+        float sum = 0.f;
+        int cnt = 0;
 #pragma unroll
-    for (int t = 0; t < kGaeTiles; t++) {
-        const long long i0 = base + t * kGaeTile + lane * 4;
-        float a4[4], t4[4];
+        for (int t = 0; t < kGaeTiles; t++) {
+            const long long i0 = base + t * kGaeTile + lane * 4;
+            const float v4[4] = {cur.v[t].x, cur.v[t].y, cur.v[t].z, cur.v[t].w};
+            float a4[4], t4[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            a4[e] = loc[t][e] + cend[t][e] * carry;
-            t4[e] = vv[t][e] + a4[e];
-            loc[t][e] = a4[e];
-            if (i0 + e < n) { sum += a4[e]; cnt++; }
+            for (int e = 0; e < 4; e++) {
+                a4[e] = loc[t][e] + cend[t][e] * carry;
+                t4[e] = v4[e] + a4[e];
+                loc[t][e] = a4[e];
+                if (i0 + e < n) { sum += a4[e]; cnt++; }
+            }
+            if (vec_ok && i0 + 3 < n) {
+                if (HINT) {
+                    st_stream4(adv_out + i0, make_float4(a4[0], a4[1], a4[2], a4[3]));
+                    st_stream4(target_out + i0, make_float4(t4[0], t4[1], t4[2], t4[3]));
+                } else {
+                    *reinterpret_cast<float4*>(adv_out + i0) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                    *reinterpret_cast<float4*>(target_out + i0) = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (i0 + e < n) { adv_out[i0 + e] = a4[e]; target_out[i0 + e] = t4[e]; }
+            }
         }
-        if (vec_ok && i0 + 3 < n) {
-            st_stream4(adv_out + i0, make_float4(a4[0], a4[1], a4[2], a4[3]));
-            st_stream4(target_out + i0, make_float4(t4[0], t4[1], t4[2], t4[3]));
-        } else {
+        sum = warp_sum(sum);
+        int total = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+        const float mean = sum / (float)total;
+        float m2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < kGaeTiles; t++) {
+            const long long i0 = base + t * kGaeTile + lane * 4;
 #pragma unroll
             for (int e = 0; e < 4; e++)
-                if (i0 + e < n) { adv_out[i0 + e] = a4[e]; target_out[i0 + e] = t4[e]; }
+                if (i0 + e < n) { const float d = loc[t][e] - mean; m2 += d * d; }
         }
+        m2 = warp_sum(m2);
+        if (lane == 0) wstats[wc] = make_float4(mean, m2, (float)total, 0.f);
+        if (has_next) cur = nxt;
     }
-    sum = warp_sum(sum);
-    int total = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
-    const float mean = sum / (float)total;
-    float m2 = 0.f;
-#pragma unroll
-    for (int t = 0; t < kGaeTiles; t++) {
-        const long long i0 = base + t * kGaeTile + lane * 4;
-#pragma unroll
-        for (int e = 0; e < 4; e++)
-            if (i0 + e < n) { const float d = loc[t][e] - mean; m2 += d * d; }
-    }
-    m2 = warp_sum(m2);
-    if (lane == 0) wstats[wc] = make_float4(mean, m2, (float)total, 0.f);
 }
 
-// Fixed-order float64 combine of the chunk triples (welford_var.h:58-66 merge).  One CTA.
+// Fixed-order float64 combine of the chunk triples (welford_var.h:58-66 merge), two levels:
+// level 1: every CTA folds 4096 chunk triples into one double triple; level 2: one CTA folds those.
 // out_d = {mean, M2, n} (float64, for the cross-rank merge), out_f = {mean, std} (float32).
-__global__ void __launch_bounds__(1024)
-gae_stats_kernel(const float4* __restrict__ wstats, int nchunks, double* out_d, float* out_f) {
-    __shared__ double s_mean[1024], s_m2[1024], s_n[1024];
+constexpr int kStatsPerBlock = 4096;
+
+__global__ void __launch_bounds__(256)
+gae_stats_partial_kernel(const float4* __restrict__ wstats, int nchunks, double* __restrict__ part /* [blocks][3] */) {
+    __shared__ double s_mean[256], s_m2[256], s_n[256];
     const int tid = threadIdx.x;
-    // contiguous slab per thread -> fixed combine order regardless of scheduling
-    const int per = (nchunks + 1023) / 1024;
+    const int base = blockIdx.x * kStatsPerBlock + tid * (kStatsPerBlock / 256);
     double mean = 0.0, m2 = 0.0, cnt = 0.0;
-    for (int i = tid * per; i < min(nchunks, (tid + 1) * per); i++) {
+#pragma unroll 4
+    for (int i = base; i < min(nchunks, base + kStatsPerBlock / 256); i++) {
         const float4 w = wstats[i];
         const double nb = w.z;
         if (nb > 0.0) {
             const double delta = (double)w.x - mean, nn = cnt + nb;
             mean += delta * nb / nn;
             m2 += (double)w.y + delta * delta * cnt * nb / nn;
+            cnt = nn;
+        }
+    }
+    s_mean[tid] = mean; s_m2[tid] = m2; s_n[tid] = cnt;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) {
+            const double na = s_n[tid], nb = s_n[tid + s];
+            if (nb > 0.0) {
+                const double delta = s_mean[tid + s] - s_mean[tid], nn = na + nb;
+                s_mean[tid] += delta * nb / nn;
+                s_m2[tid] += s_m2[tid + s] + delta * delta * na * nb / nn;
+                s_n[tid] = nn;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { part[3 * blockIdx.x] = s_mean[0]; part[3 * blockIdx.x + 1] = s_m2[0]; part[3 * blockIdx.x + 2] = s_n[0]; }
+}
+
+__global__ void __launch_bounds__(1024)
+gae_stats_kernel(const double* __restrict__ part, int nparts, double* out_d, float* out_f) {
+    __shared__ double s_mean[1024], s_m2[1024], s_n[1024];
+    const int tid = threadIdx.x;
+    // contiguous slab per thread -> fixed combine order regardless of scheduling
+    const int per = (nparts + 1023) / 1024;
+    double mean = 0.0, m2 = 0.0, cnt = 0.0;
+    for (int i = tid * per; i < min(nparts, (tid + 1) * per); i++) {
+        const double mb = part[3 * i], m2b = part[3 * i + 1], nb = part[3 * i + 2];
+        if (nb > 0.0) {
+            const double delta = mb - mean, nn = cnt + nb;
+            mean += delta * nb / nn;
+            m2 += m2b + delta * delta * cnt * nb / nn;
             cnt = nn;
         }
     }
@@ -274,13 +360,17 @@ GaeWork gae_scan(const float* reward, const float* v, const float* v_next, const
                  float* adv_target) {
     GaeWork w{};
     if (n <= 0) return w;
-    const int nchunks = div_up(n, kGaeChunk);
-    const int nblocks = div_up(n, kGaeBlockElems);
-    // layout: [ticket (256 B)] [stats_d 3 doubles + stats_f 2 floats (256 B)] [desc] [wstats]
-    const size_t desc_bytes = (size_t)nchunks * sizeof(GaeDesc);
-    const size_t bytes = 512 + desc_bytes + (size_t)nchunks * sizeof(float4);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("PPO_B200_GAE_VARIANT"); variant = e ? atoi(e) : 4; }   // 4 = <4 tiles, streaming hints, 1 CTA/SM>: fastest measured (profiles/)
+    const int tiles = (variant == 1 || variant == 3) ? 2 : 4;
+    const int chunk = kGaeTile * tiles;
+    const int nchunks = div_up(n, chunk);
+    const int nblocks = div_up(nchunks, kGaeWarps);
+    // layout: [ticket (256 B)] [stats_d 3 doubles + stats_f 2 floats (256 B)] [desc] [wstats] [level-1 stats]
+    const size_t desc_bytes = (((size_t)nchunks * sizeof(GaeDesc)) + 255) & ~size_t(255);
+    const int nparts = div_up(nchunks, kStatsPerBlock);
+    const size_t bytes = 512 + desc_bytes + (size_t)nchunks * sizeof(float4) + (size_t)nparts * 3 * sizeof(double);
     char* ws = static_cast<char*>(scratch(kScratchGae, bytes));
-    int* ticket = reinterpret_cast<int*>(ws);
     w.stats_d = reinterpret_cast<double*>(ws + 256);
     w.stats_f = reinterpret_cast<float*>(ws + 256 + 64);
     GaeDesc* desc = reinterpret_cast<GaeDesc*>(ws + 512);
@@ -288,17 +378,30 @@ GaeWork gae_scan(const float* reward, const float* v, const float* v_next, const
     w.nchunks = nchunks;
     w.wstats = wstats;
     const unsigned epoch = ++g_gae_epoch;
-    if (epoch == 0) B200_FATAL("GAE epoch counter wrapped");
-    CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(int), stream()));
+    if ((epoch & 0x3FFFFFFFu) == 0) { g_gae_epoch = 1; }
     const float gl = gamma * lambda;  // formed first in float, src/ppo.cu:346
     const uintptr_t al = (uintptr_t)reward | (uintptr_t)v | (uintptr_t)v_next | (uintptr_t)advantage | (uintptr_t)adv_target;
     const uintptr_t alb = (uintptr_t)terminated | (uintptr_t)truncated;
     const int vec_ok = ((al & 15) == 0 && (alb & 3) == 0) ? 1 : 0;
-    B200_LAUNCH(gae_scan_kernel, nblocks, kGaeWarps * 32, 0, reward, v, v_next,
-                reinterpret_cast<const unsigned char*>(terminated),
-                reinterpret_cast<const unsigned char*>(truncated), n, gamma, gl, advantage,
-                adv_target, desc, ticket, epoch, wstats, vec_ok);
-    B200_LAUNCH(gae_stats_kernel, 1, 1024, 0, wstats, nchunks, w.stats_d, w.stats_f);
+    // persistent grid: never more CTAs than can be co-resident (the look-back relies on it)
+#define B200_GAE_LAUNCH(TILES, HINT, MINB)                                                                         \
+    do {                                                                                                           \
+        int per_sm = 0;                                                                                            \
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_scan_kernel<TILES, HINT, MINB>, kGaeWarps * 32, 0)); \
+        const int grid = std::min(nblocks, std::max(1, per_sm) * num_sms());                                       \
+        B200_LAUNCH((gae_scan_kernel<TILES, HINT, MINB>), grid, kGaeWarps * 32, 0, reward, v, v_next,              \
+                    reinterpret_cast<const unsigned char*>(terminated), reinterpret_cast<const unsigned char*>(truncated), \
+                    n, gamma, gl, advantage, adv_target, desc, g_gae_epoch & 0x3FFFFFFFu, wstats, vec_ok);          \
+    } while (0)
+    if (variant == 0) B200_GAE_LAUNCH(4, true, 2);
+    else if (variant == 1) B200_GAE_LAUNCH(2, true, 4);
+    else if (variant == 2) B200_GAE_LAUNCH(4, false, 2);
+    else if (variant == 3) B200_GAE_LAUNCH(2, false, 4);
+    else B200_GAE_LAUNCH(4, true, 1);
+#undef B200_GAE_LAUNCH
+    double* part = reinterpret_cast<double*>(ws + 512 + desc_bytes + (size_t)nchunks * sizeof(float4));
+    B200_LAUNCH(gae_stats_partial_kernel, nparts, 256, 0, wstats, nchunks, part);
+    B200_LAUNCH(gae_stats_kernel, 1, 1024, 0, part, nparts, w.stats_d, w.stats_f);
     return w;
 }
 
