@@ -1,22 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native PPO training path (contract: see DESIGN.md §6).
+"""bench.py — benchmarks of the B200-native PPO training path (contract: DESIGN.md §6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
-Default workload = BASELINE.json configs[1] ("c2"): Pendulum-v1 PPO with 4096 vectorised device
-envs per GPU, 2x64 tanh actor-critic, fp32.  One "step" = one PPO iteration = a 200-step rollout of
-every env (819 200 env-steps per GPU) + GAE + 10 value epochs + 4 policy epochs of minibatch 16 384
-(the reference's schedule, src/main.c:33-43, at a vectorised minibatch size).
+Workloads = BASELINE.json configs:
+  c2 (default, configs[1])  Pendulum-v1 PPO, 4096 device envs/GPU x T=200, 2x64 tanh, fp32.  One step =
+       one PPO iteration: fused device rollout (819 200 env-steps/GPU) + GAE + 10 value + 4 policy
+       epochs of minibatch 16 384 (the reference schedule, src/main.c:33-43).  Unit: env-steps/s.
+  c3 (configs[2])  HalfCheetah-shaped synthetic buffer (S=17, A=6), T=2048 x N=512 per GPU, 2x256 ReLU,
+       update only (GAE + 10 value + 4 policy epochs, minibatch 4096/GPU).  Unit: update samples/s.
+  c4 (configs[3])  3x1024 actor-critic, minibatch 65 536/GPU, TF32 tcgen05 GEMMs, 262 144-sample
+       synthetic buffer, update only.  Unit: update samples/s; roofline against tensor peak.
+  c5 (configs[4])  GAE/returns sweep, T=2048 x N=65 536 per GPU, synthetic r/v/v'/flags.  Unit:
+       env-steps/s (buffer elements/s); roofline against measured HBM bandwidth.
 
-  value : env-steps/s (rollout+update), whole job, device-resident (ppo_b200_train_iterations)
-  e2e   : the same through the reference-facing C-ABI call train_ppo_epoch(), which also refreshes
-          every host mirror (buffer, policy, V) each iteration like src/ppo.cu:536-538
-  roofline / kernels : per-kernel CUDA-event timing of one profiled step (ppo_b200_profile_*)
-  cpu_baseline : the plain-C restatement of the reference path (oracle/, "port") on host cores
-
-N > 1: launched by torchrun, one process per GPU, weak scaling (4096 envs per GPU, the global
-minibatch is the union of the rank-local ones), NCCL all-reduce of the flat gradients.
-`--impl reference` times the CPU path only (rank 0), on all host cores as independent replicas.
+Per line:  value = whole-job throughput, inputs resident in HBM (CUDA events, max over ranks);
+           e2e   = the same through the reference-facing C-ABI call with HOST buffers (pinned), every
+                   host<->device copy inside the timed region;
+           roofline / kernels = per-kernel CUDA-event timing of one extra profiled step
+                   (ppo_b200_profile_*: an event pair around every launch, on the launching stream);
+           cpu_baseline = plain-C restatement of the reference path (oracle/, "port") on one host core,
+                   on a bounded sample of the same workload.
+N > 1: torchrun, one process per GPU, weak scaling (per-GPU work fixed; the global minibatch is the union
+of the rank-local ones), NCCL all-reduce of the flat gradient / all-gather of the Welford triple; c5
+shards envs with no collective in the scan.  `--impl reference` times the CPU path only (rank 0), one
+replica per host core.
 """
 import argparse
 import ctypes as C
@@ -28,43 +36,427 @@ import sys
 import tempfile
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-SIZES = [3, 64, 64, 1]
-ACTS = ["tanh", "tanh", "none"]
-N_ENVS, T = 4096, 200
-MB, N_POL, N_VAL = 16384, 4, 10
-CPU_SAMPLE_STEPS, CPU_SAMPLE_MB = 8200, 2050     # 41 episodes of 200 steps, 4 minibatches per epoch
+f32, u8 = np.float32, np.uint8
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FMA lanes x 2 x 1.965 GHz (nominal)
 
 
-# --------------------------------------------------------------------------------------- CPU arm
-def cpu_iteration_seconds(n_iters, seed=1):
-    """Plain-C path (oracle port of src/ppo.cu:373-448 + C Pendulum), single thread.  Returns the list
-    of per-iteration wall times; one iteration = CPU_SAMPLE_STEPS env-steps (rollout + update)."""
-    import cabi
-    import oracle
-    cabi.srand(seed)
-    tr = oracle.Trainer(SIZES, ACTS, batch_size=CPU_SAMPLE_MB, n_epochs_policy=N_POL, n_epochs_value=N_VAL)
-    buf = tr.make_buffer(CPU_SAMPLE_STEPS)
-    times = []
-    for _ in range(n_iters):
-        t0 = time.perf_counter()
-        tr.collect(buf, CPU_SAMPLE_STEPS, 1)
-        tr.update(buf)
-        times.append(time.perf_counter() - t0)
-    return times
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm": p["hbm_gbs"], "bf16": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "bf16_burst": p["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json)"}
+    except (OSError, KeyError, ValueError):
+        return {"hbm": 6650.0, "bf16": 1400.0, "bf16_burst": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def mlp_weights(sizes):
+    return sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1))
+
+
+def mlp_params(sizes):
+    return mlp_weights(sizes) + sum(sizes[1:])
+
+
+def train_flops(sizes, rows):
+    """fwd 2*rows*W + dW 2*rows*W + dX 2*rows*(W - S*H0): layer-0 dX is never computed."""
+    w = mlp_weights(sizes)
+    return 2 * rows * w + 2 * rows * w + 2 * rows * (w - sizes[0] * sizes[1])
+
+
+# ======================================================================================= workloads
+class Workload:
+    name = "?"
+    metric = "env_steps_per_s"
+    unit = "env-steps/s"
+    dtype = "f32"
+
+    def __init__(self, L, rank, world):
+        self.L, self.rank, self.world = L, rank, world
+        self.init_sizes()
+
+    def init_sizes(self): ...
+
+    # -- GPU arm
+    def setup(self): ...
+    def step_device(self, k): ...          # k steps, inputs resident in HBM
+    def step_e2e(self, k): ...             # k steps through the host-buffer call
+    def units_per_step(self): ...          # per GPU
+    def e2e_bytes(self): return 0, 0
+    def config(self): return {}
+    def extra(self, ms): return {}
+    def roofline_work(self, kernels): return {}
+    def teardown(self): ...
+    # -- CPU arm: seconds per sample step + units in that sample
+    def cpu_sample(self, n_iters, seed=1): ...
+    def cpu_sample_desc(self): return ""
+
+
+def _fill_ppo_host_buffer(ppo, arrays):
+    buf = ppo.contents.buffer.contents
+    n = arrays["reward"].shape[0]
+    S, A = arrays["state"].shape[1], arrays["action"].shape[1]
+    np.ctypeslib.as_array(buf.h_state_p, shape=(n, S))[:] = arrays["state"]
+    np.ctypeslib.as_array(buf.h_next_state_p, shape=(n, S))[:] = arrays["next_state"]
+    np.ctypeslib.as_array(buf.h_action_p, shape=(n, A))[:] = arrays["action"]
+    np.ctypeslib.as_array(buf.h_reward_p, shape=(n,))[:] = arrays["reward"]
+    np.ctypeslib.as_array(buf.h_logprob_p, shape=(n,))[:] = arrays["logprob"]
+    np.ctypeslib.as_array(buf.h_terminated_p, shape=(n,))[:] = arrays["terminated"].astype(bool)
+    np.ctypeslib.as_array(buf.h_truncated_p, shape=(n,))[:] = arrays["truncated"].astype(bool)
+
+
+def synthetic_rollout(rng, T, N, S, A):
+    """SURVEY.md §8d C3 generator: N(0,1) states/actions/rewards, Bernoulli(1e-3) terminations,
+    truncation every 1000 steps and forced on each env's last step, env-major flatten."""
+    n = T * N
+    t = np.tile(np.arange(T), N)
+    trunc = (((t + 1) % 1000) == 0)
+    trunc[t == T - 1] = True
+    return dict(state=rng.standard_normal((n, S), dtype=f32), next_state=rng.standard_normal((n, S), dtype=f32),
+                action=rng.standard_normal((n, A), dtype=f32), reward=rng.standard_normal(n, dtype=f32),
+                logprob=np.zeros(n, f32), terminated=(rng.random(n) < 1e-3).astype(u8), truncated=trunc.astype(u8))
+
+
+class C2(Workload):
+    """Pendulum-v1 PPO, vectorised device envs (BASELINE.json configs[1])."""
+    name = "c2"
+    SIZES, ACTS = [3, 64, 64, 1], ["tanh", "tanh", "none"]
+    N_ENVS, T, MB, N_POL, N_VAL = 4096, 200, 16384, 4, 10
+    CPU_STEPS, CPU_MB = 8200, 2050           # 41 episodes of 200 steps, 4 minibatches per epoch
+
+    def init_sizes(self):
+        self.cap = self.N_ENVS * self.T
+
+    def setup(self):
+        import cabi
+        L = self.L
+        cabi.srand(1234)                      # same initial weights on every rank
+        self.env = L.create_pendulum_env_cuda(self.N_ENVS, 100 + self.rank)
+        self.ppo = L.create_ppo(cabi.cstr_array(self.ACTS), cabi.int_array(self.SIZES), len(self.SIZES), self.cap,
+                                3e-4, 3e-4, 0.95, 0.2, 0.0, 1.0, True)
+        L.ppo_b200_set_permutation_mode(self.ppo, -1, 7 + self.rank)
+
+    def step_device(self, k):
+        self.L.ppo_b200_train_iterations(self.ppo, self.env, k, self.MB, self.N_POL, self.N_VAL)
+
+    def step_e2e(self, k):
+        self.L.train_ppo_epoch(self.ppo, self.env, self.cap * k, self.MB, self.N_POL, self.N_VAL)
+
+    def units_per_step(self):
+        return self.cap
+
+    def e2e_bytes(self):
+        S, A = self.SIZES[0], self.SIZES[-1]
+        p_mu = mlp_params(self.SIZES)
+        p_v = mlp_params(self.SIZES[:-1] + [1])
+        return 0, self.cap * (4 * (2 * S + A + 4) + 2) + 4 * (p_mu + p_v + A)
+
+    def config(self):
+        return {"workload": "c2: Pendulum-v1 PPO, %d device envs/GPU x T=%d, 2x64 tanh MLP, fp32, minibatch %d/GPU, "
+                            "%d value + %d policy epochs (BASELINE.json configs[1])" % (self.N_ENVS, self.T, self.MB, self.N_VAL, self.N_POL),
+                "env_steps_per_step_per_gpu": self.cap, "parallelism": "dp%d" % self.world,
+                "l2": "inputs larger than L2: every step streams the 819200-row buffer (38 MB of rows + 14 permutations) "
+                      "through 700 minibatch launches and rewrites it in the rollout; no explicit flush",
+                "permutation": "device generator (auto mode after a device rollout)",
+                "e2e_call": "train_ppo_epoch (reference API): device rollout + update + buffer_to_host/policy_to_host/"
+                            "nn_write_weights_to_host every iteration (src/ppo.cu:536-538); the envs live on the device, "
+                            "so there is no per-step host input: h2d_bytes_per_step is 0 by construction"}
+
+    def extra(self, ms):
+        nb = self.cap // self.MB
+        return {"update_samples_per_s": self.world * (self.N_POL + self.N_VAL) * nb * self.MB / (ms * 1e-3),
+                "mean_episode_return": self.L.ppo_b200_last_mean_return(self.ppo)}
+
+    def roofline_work(self, kernels):
+        B, nb = self.cap, self.cap // self.MB
+        S, A = self.SIZES[0], self.SIZES[-1]
+        sv = self.SIZES[:-1] + [1]
+        upd_flops = self.N_VAL * nb * train_flops(sv, self.MB) + self.N_POL * nb * train_flops(self.SIZES, self.MB) \
+            + 2 * 2 * B * mlp_weights(sv)                                  # + the two V forwards of the GAE
+        slab_v, slab_p = mlp_params(sv) + 2, mlp_params(self.SIZES) + A + 1
+        ctas = -(-self.MB // 64)
+        red_bytes = (self.N_VAL * nb * (ctas * slab_v * 4 + 32 * mlp_params(sv))
+                     + self.N_POL * nb * (ctas * slab_p * 4 + 32 * mlp_params(self.SIZES)))
+        roll_flops = 2 * B * mlp_weights(self.SIZES)
+        return {"fused_update_kernel": ("fp32", upd_flops),
+                "fused_reduce_adam_kernel": ("hbm", red_bytes),      # slab reads + 28 B/param Adam + 4 B/param image
+                "rollout_kernel": ("fp32", roll_flops),
+                "gae_scan_kernel": ("hbm", 22.0 * B), "gae_normalize_kernel": ("hbm", 8.0 * B)}
+
+    def teardown(self):
+        self.L.free_ppo(self.ppo)
+        self.env.contents.free_env()
+
+    def cpu_sample(self, n_iters, seed=1):
+        import cabi
+        import oracle
+        cabi.srand(seed)
+        tr = oracle.Trainer(self.SIZES, self.ACTS, batch_size=self.CPU_MB, n_epochs_policy=self.N_POL, n_epochs_value=self.N_VAL)
+        buf = tr.make_buffer(self.CPU_STEPS)
+        times = []
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            tr.collect(buf, self.CPU_STEPS, 1)
+            tr.update(buf)
+            times.append(time.perf_counter() - t0)
+        return times, self.CPU_STEPS
+
+    def cpu_sample_desc(self):
+        return ("oracle port of the reference plain-C path (src/ppo.cu:373-448 + C Pendulum): 1 env, %d env-steps per step "
+                "(rollout + GAE + %d value / %d policy epochs, minibatch %d), 2x64 tanh"
+                % (self.CPU_STEPS, self.N_VAL, self.N_POL, self.CPU_MB))
+
+
+class UpdateOnly(Workload):
+    """Synthetic rollout buffer, PPO update only (GAE + value epochs + policy epochs)."""
+    metric, unit = "update_samples_per_s", "samples/s"
+    SIZES, ACTS = None, None
+    T, N, MB, N_POL, N_VAL = 0, 0, 0, 4, 10
+    TF32 = 0
+    CPU_B, CPU_MB, CPU_POL, CPU_VAL = 4096, 1024, 1, 1
+
+    def init_sizes(self):
+        self.cap = self.T * self.N
+
+    def setup(self):
+        import cabi
+        L = self.L
+        S, A = self.SIZES[0], self.SIZES[-1]
+        L.ppo_b200_set_matmul_precision(self.TF32)
+        cabi.srand(1234)
+        self.ppo = L.create_ppo(cabi.cstr_array(self.ACTS), cabi.int_array(self.SIZES), len(self.SIZES), self.cap,
+                                3e-4, 3e-4, 0.95, 0.2, 0.0, 1.0, True)
+        rng = np.random.default_rng(1000 + self.rank)
+        arrays = synthetic_rollout(rng, self.T, self.N, S, A)
+        _fill_ppo_host_buffer(self.ppo, arrays)
+        L.ppo_b200_buffer_upload(self.ppo)
+        # logprob_old = log-prob under the initial policy + N(0, 0.1): ratios near 1, both clip branches live
+        buf = self.ppo.contents.buffer.contents
+        L.compute_log_prob_cuda(self.ppo.contents.policy, buf.d_logprob_p, buf.d_state_p, buf.d_action_p, self.cap)
+        lp = np.empty(self.cap, f32)
+        L.ppo_b200_d2h(lp.ctypes.data, C.cast(buf.d_logprob_p, C.c_void_p), lp.nbytes)
+        lp += 0.1 * rng.standard_normal(self.cap, dtype=f32)
+        np.ctypeslib.as_array(buf.h_logprob_p, shape=(self.cap,))[:] = lp
+        L.ppo_b200_buffer_upload(self.ppo)
+        L.ppo_b200_set_permutation_mode(self.ppo, 1, 7 + self.rank)
+
+    def step_device(self, k):
+        for _ in range(k):
+            self.L.ppo_b200_update_device(self.ppo, 0.99, self.MB, self.N_POL, self.N_VAL)
+
+    def step_e2e(self, k):
+        for _ in range(k):
+            self.L.ppo_b200_update(self.ppo, 0.99, self.MB, self.N_POL, self.N_VAL)
+        self.L.ppo_b200_set_permutation_mode(self.ppo, 1, 7 + self.rank)
+
+    def units_per_step(self):
+        return (self.N_POL + self.N_VAL) * (self.cap // self.MB) * self.MB
+
+    def e2e_bytes(self):
+        S, A = self.SIZES[0], self.SIZES[-1]
+        per_row = 4 * (2 * S + A + 4) + 2
+        p = mlp_params(self.SIZES) + mlp_params(self.SIZES[:-1] + [1]) + A
+        return self.cap * per_row, self.cap * per_row + 4 * p
+
+    def base_config(self, label):
+        return {"workload": label, "buffer_rows_per_gpu": self.cap, "minibatch_per_gpu": self.MB,
+                "epochs": "%d value + %d policy" % (self.N_VAL, self.N_POL), "parallelism": "dp%d" % self.world,
+                "l2": "inputs larger than L2: the %d-row buffer (%.0f MB of gathered fields) is re-streamed by every epoch"
+                      % (self.cap, self.cap * 4 * (self.SIZES[0] + self.SIZES[-1] + 3) / 1e6),
+                "permutation": "device generator (mode 1); the reference's host rand() chain is the bit-exact mode "
+                               "used by the parity tests",
+                "e2e_call": "ppo_b200_update: buffer_to_device (all 9 arrays, pinned host) + GAE + epochs + "
+                            "buffer_to_host/policy_to_host/nn_write_weights_to_host"}
+
+    def teardown(self):
+        self.L.free_ppo(self.ppo)
+        self.L.ppo_b200_set_matmul_precision(0)
+
+    def cpu_sample(self, n_iters, seed=1):
+        import cabi
+        import oracle
+        cabi.srand(seed)
+        tr = oracle.Trainer(self.SIZES, self.ACTS, batch_size=self.CPU_MB, n_epochs_policy=self.CPU_POL,
+                            n_epochs_value=self.CPU_VAL, ref_index=False)
+        rng = np.random.default_rng(seed)
+        arrays = synthetic_rollout(rng, self.CPU_B, 1, self.SIZES[0], self.SIZES[-1])
+        b = tr.make_buffer(self.CPU_B)
+        for k, v in arrays.items():
+            b[k][:] = v
+        times = []
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            tr.update(b)
+            times.append(time.perf_counter() - t0)
+        return times, (self.CPU_POL + self.CPU_VAL) * (self.CPU_B // self.CPU_MB) * self.CPU_MB
+
+    def cpu_sample_desc(self):
+        return ("oracle port of the reference plain-C update (src/ppo.cu:373-448): %d-row synthetic buffer, GAE + %d value + %d "
+                "policy epochs, minibatch %d, nets %s" % (self.CPU_B, self.CPU_VAL, self.CPU_POL, self.CPU_MB, self.SIZES))
+
+
+class C3(UpdateOnly):
+    name = "c3"
+    SIZES, ACTS = [17, 256, 256, 6], ["relu", "relu", "none"]
+    T, N, MB = 2048, 512, 4096
+
+    def config(self):
+        return self.base_config("c3: HalfCheetah-shaped synthetic rollout buffer (S=17, A=6), T=2048 x N=512 per GPU, 2x256 ReLU "
+                                "MLP, fp32 FFMA layer kernels, PPO update only (BASELINE.json configs[2])")
+
+    def roofline_work(self, kernels):
+        nb = self.cap // self.MB
+        sv = self.SIZES[:-1] + [1]
+        w_mu, w_v = mlp_weights(self.SIZES), mlp_weights(sv)
+        steps_v, steps_p = self.N_VAL * nb, self.N_POL * nb
+        S, H = self.SIZES[0], self.SIZES[1]
+        return {"sgemm_kernel<kFwd>": ("fp32", 2 * self.MB * (steps_v * w_v + steps_p * w_mu) + 2 * 2 * self.cap * w_v),
+                "sgemm_kernel<kBwdInput>": ("fp32", 2 * self.MB * (steps_v * (w_v - S * H) + steps_p * (w_mu - S * H))),
+                "sgemm_kernel<kBwdParam>": ("fp32", 2 * self.MB * (steps_v * w_v + steps_p * w_mu)),
+                "gather_kernel": ("hbm", (steps_v + steps_p) * self.MB * (4 + 2 * 4 * (self.SIZES[0] + self.SIZES[-1] + 3))),
+                "adam_flat_kernel": ("hbm", 28.0 * (steps_v * mlp_params(sv) + steps_p * (mlp_params(self.SIZES) + self.SIZES[-1]))),
+                "gae_scan_kernel": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
+
+
+class C4(UpdateOnly):
+    name = "c4"
+    dtype = "tf32"
+    SIZES, ACTS = [17, 1024, 1024, 1024, 6], ["relu", "relu", "relu", "none"]
+    T, N, MB = 2048, 128, 65536
+    TF32 = 1
+    CPU_B, CPU_MB = 512, 256
+
+    def config(self):
+        c = self.base_config("c4: wide actor-critic 3x1024 ReLU MLP (S=17, A=6), minibatch 65536/GPU, TF32 tcgen05 GEMMs with fp32 "
+                             "accumulation in TMEM, 262144-row synthetic buffer per GPU, PPO update only (BASELINE.json configs[3])")
+        c["tolerance"] = "TF32 operands (RNA-rounded), stated separately from fp32: ~1e-3 norm-wise (tests/test_gpu_tc.py)"
+        return c
+
+    def roofline_work(self, kernels):
+        nb = self.cap // self.MB
+        sv = self.SIZES[:-1] + [1]
+        steps_v, steps_p = self.N_VAL * nb, self.N_POL * nb
+        # tensor-core layers = those with in/out >= 64: the three... two 1024x1024 layers fwd/dX/dW
+        wide = sum(self.SIZES[i] * self.SIZES[i + 1] for i in range(len(self.SIZES) - 1)
+                   if self.SIZES[i] >= 64 and self.SIZES[i + 1] >= 64)
+        tc = 6 * self.MB * wide * (steps_v + steps_p) + 2 * 2 * self.cap * wide
+        return {"tc_gemm_kernel": ("tensor_tf32", tc),
+                "adam_flat_kernel": ("hbm", 28.0 * (steps_v * mlp_params(sv) + steps_p * (mlp_params(self.SIZES) + self.SIZES[-1]))),
+                "gather_kernel": ("hbm", (steps_v + steps_p) * self.MB * (4 + 2 * 4 * (self.SIZES[0] + self.SIZES[-1] + 3))),
+                "gae_scan_kernel": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
+
+
+class C5(Workload):
+    """GAE/returns-only sweep on synthetic rewards/values/dones (BASELINE.json configs[4])."""
+    name = "c5"
+    T, N, BLOCK = 2048, 65536, 4096
+    CPU_N = 4096
+
+    def _block(self, rng, nb):
+        n = self.T * nb
+        t = np.tile(np.arange(self.T), nb)
+        trunc = (((t + 1) % 1000) == 0)
+        trunc[t == self.T - 1] = True
+        return (rng.standard_normal(n, dtype=f32), rng.standard_normal(n, dtype=f32), rng.standard_normal(n, dtype=f32),
+                (rng.random(n) < 1e-3).astype(u8), trunc.astype(u8))
+
+    def init_sizes(self):
+        self.n = self.T * self.N
+
+    def setup(self):
+        import b200
+        L = self.L
+        rng = np.random.default_rng(500 + self.rank)
+        blk = self._block(rng, self.BLOCK)
+        reps = self.N // self.BLOCK
+        self.dev = []
+        for a in blk:                       # the 4096-env block replicated 16x on the device (3.9 GB of inputs)
+            d = b200.dev_empty(self.n, a.dtype)
+            for i in range(reps):
+                L.ppo_b200_h2d(d.ptr + i * a.nbytes, a.ctypes.data, a.nbytes)
+            self.dev.append(d)
+        self.adv, self.tgt, self.st = b200.dev_empty(self.n), b200.dev_empty(self.n), b200.dev_empty(2)
+        self.blk, self.host = blk, None
+
+    def _gae(self):
+        self.L.ppo_b200_gae(*[d.ptr for d in self.dev], self.n, 0.99, 0.95, self.adv.ptr, self.tgt.ptr, 1, self.st.ptr)
+
+    def step_device(self, k):
+        for _ in range(k):
+            self._gae()
+
+    def _host_alloc(self):
+        L = self.L
+        sizes = [4 * self.n] * 3 + [self.n] * 2 + [4 * self.n] * 2
+        self.host = [L.ppo_b200_malloc_host(s) for s in sizes]
+        reps = self.N // self.BLOCK
+        for h, a in zip(self.host[:5], self.blk):
+            for i in range(reps):
+                C.memmove(h + i * a.nbytes, a.ctypes.data, a.nbytes)
+        self.host_sizes = sizes
+
+    def step_e2e(self, k):
+        L = self.L
+        if self.host is None:
+            self._host_alloc()
+        for _ in range(k):
+            for d, h, s in zip(self.dev, self.host[:5], self.host_sizes[:5]):
+                L.ppo_b200_h2d(d.ptr, h, s)
+            self._gae()
+            L.ppo_b200_d2h(self.host[5], self.adv.ptr, 4 * self.n)
+            L.ppo_b200_d2h(self.host[6], self.tgt.ptr, 4 * self.n)
+
+    def units_per_step(self):
+        return self.n
+
+    def e2e_bytes(self):
+        return 14 * self.n, 8 * self.n
+
+    def config(self):
+        return {"workload": "c5: GAE/returns + advantage normalisation on synthetic rewards/values/dones, T=%d x N=%d per GPU "
+                            "(BASELINE.json configs[4])" % (self.T, self.N),
+                "elements_per_step_per_gpu": self.n, "parallelism": "env-sharded x%d, no collective in the scan" % self.world,
+                "l2": "inputs larger than L2: 3.9 GB read + 1.1 GB written per step",
+                "e2e_call": "ppo_b200_gae on device staging of pinned HOST arrays: 5 H2D copies (14 B/element) + scan + "
+                            "normalise + 2 D2H copies (8 B/element)"}
+
+    def roofline_work(self, kernels):
+        return {"gae_scan_kernel": ("hbm", 22.0 * self.n), "gae_normalize_kernel": ("hbm", 8.0 * self.n)}
+
+    def teardown(self):
+        for d in self.dev + [self.adv, self.tgt, self.st]:
+            d.free()
+        if self.host:
+            for h in self.host:
+                self.L.ppo_b200_free_host(h)
+
+    def cpu_sample(self, n_iters, seed=1):
+        import oracle
+        blk = self._block(np.random.default_rng(seed), self.CPU_N)
+        times = []
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            oracle.gae(*blk, 0.99, 0.95)
+            times.append(time.perf_counter() - t0)
+        return times, self.T * self.CPU_N
+
+    def cpu_sample_desc(self):
+        return ("oracle port of compute_gae's delta / recurrence / returns / normalisation (src/ppo.cu:338-368) on a "
+                "T=%d x N=%d sample (%d elements)" % (self.T, self.CPU_N, self.T * self.CPU_N))
+
+
+WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5}
+
+
+# ======================================================================================= CPU arm
 def _cpu_worker(args):
-    n_iters, seed = args
-    return cpu_iteration_seconds(n_iters, seed)
-
-
-def cpu_sample_desc():
-    return ("oracle port of the reference plain-C path: 1 env Pendulum, %d env-steps per step "
-            "(rollout + GAE + %d value / %d policy epochs, minibatch %d), 2x64 tanh"
-            % (CPU_SAMPLE_STEPS, N_VAL, N_POL, CPU_SAMPLE_MB))
+    name, n_iters, seed = args
+    wl = WORKLOADS[name](None, 0, 1)
+    return wl.cpu_sample(n_iters, seed)
 
 
 def run_reference_arm(args):
@@ -72,97 +464,144 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = len(os.sched_getaffinity(0))
-    cores = max(1, min(cores, 128))
+    cls = WORKLOADS[args.workload]
+    cores = max(1, min(len(os.sched_getaffinity(0)), 128))
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(args.warmup + args.steps, 1 + i) for i in range(cores)])
-    # every worker ran its own replica; a "step" of the arm = all replicas doing one iteration
-    per_step = [max(r[args.warmup + k] for r in res) for k in range(args.steps)]
+        res = pool.map(_cpu_worker, [(args.workload, args.warmup + args.steps, 1 + i) for i in range(cores)])
+    units = res[0][1]
+    # every worker ran its own replica; a "step" of the arm = all replicas doing one sample step
+    per_step = [max(r[0][args.warmup + k] for r in res) for k in range(args.steps)]
     total = sum(per_step)
-    value = cores * CPU_SAMPLE_STEPS * args.steps / total
+    value = cores * units * args.steps / total
+    wl = cls(None, 0, args.gpus)
     line = {
-        "impl": "reference", "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s",
+        "impl": "reference", "metric": cls.metric, "value": value, "unit": cls.unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": cpu_sample_desc() + "; %d independent replicas, one per host core" % cores},
-        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": cores, "kind": "port",
+                         "sample": wl.cpu_sample_desc() + "; %d independent replicas, one per host core" % cores},
+        "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------------------- helpers
-def workload_config(n_gpus):
-    return {"workload": "c2: Pendulum-v1 PPO, %d device envs/GPU x T=%d, 2x64 tanh MLP, fp32, minibatch %d/GPU, "
-                        "%d value + %d policy epochs (BASELINE.json configs[1])" % (N_ENVS, T, MB, N_VAL, N_POL),
-            "env_steps_per_step_per_gpu": N_ENVS * T, "parallelism": "dp%d" % n_gpus,
-            "l2": "working set > L2: each step streams the 819200-row buffer (38 MB) and 420 MB of V-net activations",
-            "permutation": "device (auto mode after a device rollout)"}
-
-
+# ======================================================================================= helpers
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; mark() brackets the timed region."""
+
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
+        self.lo = self.hi = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
+    def _lines(self):
+        try:
+            return sum(1 for _ in open(self.path))
+        except OSError:
+            return 0
+
+    def wait_first_sample(self, timeout=3.0):
+        t0 = time.time()
+        while self.proc and self._lines() == 0 and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        if self.lo is None:
+            self.lo = self._lines()
+        else:
+            self.hi = self._lines()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         try:
             for ln in open(self.path):
                 f = [x.strip() for x in ln.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    rows.append((float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for name, val in zip(names, f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons)}
+        window = "timed region"
+        sel = rows[self.lo:(self.hi + 1 if self.hi is not None else None)] if self.lo is not None else rows
+        if not sel:                       # timed region shorter than one sampling period: use every sample of the run
+            sel, window = rows, "warm-up + timed region (timed region shorter than the 50 ms sampling period)"
+        if sel:
+            out = {"sm_mhz": statistics.median(r[0] for r in sel), "sm_max_mhz": max(r[1] for r in sel),
+                   "reasons": sorted({n for r in sel for n in r[2]}), "samples": len(sel), "window": window}
         return out
 
 
-def load_peaks():
+def build_roofline(kernels, work, traffic_file=None):
+    """Algorithmic work of one step per kernel over its CUDA-event time in the profiled step.
+    `work` maps a kernel-name prefix to (bound, amount): bytes for "hbm", FLOPs otherwise."""
+    pk = load_peaks()
+    agg = {}
+    for name, k in kernels.items():
+        for prefix in work:                     # a work key matches a kernel when it is a substring of its name
+            if prefix in name.replace(" ", ""):
+                a = agg.setdefault(prefix, {"launches": 0, "total_ms": 0.0})
+                a["launches"] += k["launches"]
+                a["total_ms"] += k["total_ms"]
+    out = {}
+    for prefix, (bound, amount) in work.items():
+        if prefix not in agg or agg[prefix]["total_ms"] <= 0:
+            continue
+        sec = agg[prefix]["total_ms"] * 1e-3
+        if bound == "hbm":
+            ach, peak, unit, psrc = amount / sec / 1e9, pk["hbm"], "GB/s", pk["src"] + ": HBM copy read+write"
+        elif bound == "tensor_tf32":
+            ach, peak, unit = amount / sec / 1e12, pk["bf16"] / 2, "TFLOP/s"
+            psrc = pk["src"] + ": sustained cuBLAS bf16 / 2 (TF32 dense rate is half of bf16)"
+            bound = "tensor"
+        else:
+            ach, peak, unit = amount / sec / 1e12, FP32_PEAK_TFLOPS, "TFLOP/s"
+            psrc = "nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)"
+        out[prefix] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                       "launches": agg[prefix]["launches"], "avg_us": 1e3 * agg[prefix]["total_ms"] / agg[prefix]["launches"],
+                       "peak_source": psrc}
+    total = sum(k["total_ms"] for k in kernels.values())
+    if not out:
+        return None
+    dom = max(out, key=lambda p: agg[p]["total_ms"])
+    r = dict(out[dom])
+    traffic = None
     try:
-        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return p["hbm_gbs"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
-    except (OSError, KeyError, ValueError):
-        return 6650.0, 1400.0, "fallback"
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    r.update({"kernel": dom, "share_of_step": agg[dom]["total_ms"] / total if total > 0 else None, "traffic": traffic,
+              "per_kernel": out})
+    return r
 
 
-def mlp_weights(sizes):
-    return sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1))
-
-
-# --------------------------------------------------------------------------------------- GPU arm
+# ======================================================================================= GPU arm
 def run_gpu_arm(args):
     import torch
     import b200
-    import cabi
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -171,6 +610,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     L = b200.lib()
     L.ppo_b200_set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -185,130 +625,89 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    cabi.srand(1234)                                  # same initial weights on every rank
-    env = L.create_pendulum_env_cuda(N_ENVS, 100 + rank)
-    cap = N_ENVS * T
-    ppo = L.create_ppo(cabi.cstr_array(ACTS), cabi.int_array(SIZES), len(SIZES), cap, 3e-4, 3e-4, 0.95, 0.2, 0.0, 1.0, True)
-    L.ppo_b200_set_permutation_mode(ppo, -1, 7 + rank)
+    wl = WORKLOADS[args.workload](L, rank, world)
+    wl.setup()
 
-    # ---- value: device-resident iterations ------------------------------------------------------
-    L.ppo_b200_train_iterations(ppo, env, args.warmup, MB, N_POL, N_VAL)
-    barrier()
+    # ---- value: inputs resident in HBM ------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first_sample()
+    wl.step_device(args.warmup)
+    barrier()
+    if sampler:
+        sampler.mark()
     launches0 = L.ppo_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    L.ppo_b200_train_iterations(ppo, env, args.steps, MB, N_POL, N_VAL)
+    wl.step_device(args.steps)
     e1.record(stream)
     barrier()
+    if sampler:
+        sampler.mark()
     ms = e0.elapsed_time(e1)
     launches = L.ppo_b200_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
-    mean_return = L.ppo_b200_last_mean_return(ppo)
+    extra = wl.extra(ms / args.steps) if rank == 0 else {}
 
-    # ---- e2e: the reference-facing call, host mirrors refreshed every iteration --------------------
-    L.train_ppo_epoch(ppo, env, cap, MB, N_POL, N_VAL)      # warm the pinned mirrors
+    # ---- e2e: the host-buffer call, copies inside the timed region -----------------------------------
+    e2e_steps = args.steps if args.e2e_steps <= 0 else args.e2e_steps
+    wl.step_e2e(1)                                       # warm the pinned mirrors
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     f0.record(stream)
-    L.train_ppo_epoch(ppo, env, cap * args.steps, MB, N_POL, N_VAL)
+    wl.step_e2e(e2e_steps)
     f1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     e2e_ms = max(f0.elapsed_time(f1), 0.0)
-    S, A = SIZES[0], SIZES[-1]
-    p_mu = mlp_weights(SIZES) + sum(SIZES[1:])
-    p_v = p_mu - (SIZES[-2] + 1) * (A - 1)
-    d2h = cap * (4 * (2 * S + A + 4) + 2) + 4 * (p_mu + p_v + A)
-
     if world > 1:
         tt = torch.tensor([ms, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms, wall_ms = (float(x) for x in tt.cpu())
+    e2e_ms = max(e2e_ms, wall_ms)                        # host-blocking copies: the wall clock is the honest one
 
-    # ---- per-kernel timing of one profiled step (rank 0) ----------------------------------------------
+    # ---- per-kernel timing of one profiled step (rank 0; other ranks run the same step unprofiled) -----
     kernels, roofline = {}, None
     if rank == 0:
         L.ppo_b200_profile_begin()
-        L.ppo_b200_train_iterations(ppo, env, 1, MB, N_POL, N_VAL)
+    wl.step_device(1)
+    if rank == 0:
         buf = C.create_string_buffer(1 << 16)
         L.ppo_b200_profile_end(buf, len(buf))
         for ln in buf.value.decode().splitlines():
             name, cnt, tot = ln.rsplit(" ", 2)
             kernels[name] = {"launches": int(cnt), "total_ms": float(tot)}
-        roofline = build_roofline(kernels)
+        roofline = build_roofline(kernels, wl.roofline_work(kernels))
     barrier()
 
     if rank == 0:
-        cpu_times = cpu_iteration_seconds(4)[1:] if world == 1 else None
-        steps_total = world * cap * args.steps
+        units = world * wl.units_per_step()
+        h2d, d2h = wl.e2e_bytes()
         line = {
-            "metric": "env_steps_per_s", "value": steps_total / (ms * 1e-3), "unit": "env-steps/s",
+            "metric": wl.metric, "value": units * args.steps / (ms * 1e-3), "unit": wl.unit,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
-            "e2e": {"value": steps_total / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                    "call": "train_ppo_epoch (reference API): rollout + update + buffer_to_host/policy_to_host/nn_write_weights_to_host"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+            "config": wl.config(),
+            "e2e": {"value": units * e2e_steps / (e2e_ms * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "update_samples_per_s": world * (N_POL + N_VAL) * (cap // MB) * MB * args.steps / (ms * 1e-3),
-            "mean_episode_return": mean_return,
-            "roofline": roofline,
-            "kernels": kernels,
         }
-        if cpu_times:
-            line["cpu_baseline"] = {"value": CPU_SAMPLE_STEPS / statistics.mean(cpu_times), "unit": "env-steps/s", "cores": 1,
-                                    "kind": "port", "sample": cpu_sample_desc() + "; %d timed steps" % len(cpu_times)}
+        line.update(extra)
+        line["roofline"] = roofline
+        line["kernels"] = kernels
+        if world == 1:
+            times, cpu_units = wl.cpu_sample(args.cpu_iters + 1)
+            times = times[1:]
+            line["cpu_baseline"] = {"value": cpu_units / statistics.mean(times), "unit": wl.unit, "cores": 1, "kind": "port",
+                                    "sample": wl.cpu_sample_desc() + "; %d timed steps, one thread (the reference is "
+                                              "single-threaded, src/main.c:18)" % len(times)}
         print(json.dumps(line), flush=True)
-    L.free_ppo(ppo)
-    env.contents.free_env()
+    wl.teardown()
     if world > 1:
         L.ppo_b200_dist_finalize()
         dist.destroy_process_group()
-
-
-def build_roofline(kernels):
-    """Algorithmic work of one c2 step per kernel class over its CUDA-event time."""
-    hbm, tens, src = load_peaks()
-    B, nb = N_ENVS * T, (N_ENVS * T) // MB
-    steps = (N_POL + N_VAL) * nb
-    W = mlp_weights(SIZES)
-    P = W + sum(SIZES[1:])
-    H = SIZES[1]
-    # fp32 FLOPs through the tiled kernels per minibatch (skinny last layer of the forward excluded):
-    fwd_tiled = 2 * MB * (SIZES[0] * H + H * H)                     # sgemm_kernel<kFwd>
-    bwd_in = 2 * MB * (H * H + H * 1)                               # sgemm_kernel<kBwdInput>: layers 2,1
-    bwd_par = 2 * MB * W                                            # sgemm_kernel<kBwdParam>
-    gae_fwd = 2 * 2 * B * (SIZES[0] * H + H * H)                    # two V forwards over the buffer
-    work = {
-        "gae_scan_kernel": ("hbm", 22.0 * B),
-        "gae_normalize_kernel": ("hbm", 8.0 * B),
-        "adam_flat_kernel": ("hbm", 28.0 * (steps * P + N_POL * nb * 1)),
-        "gather_kernel": ("hbm", steps * MB * (4 + 2 * 4 * (SIZES[0] + SIZES[-1] + 3))),
-        "sgemm_kernel<kFwd>": ("fp32", steps * fwd_tiled + gae_fwd),
-        "sgemm_kernel<kBwdInput>": ("fp32", steps * bwd_in),
-        "sgemm_kernel<kBwdParam>": ("fp32", steps * bwd_par),
-    }
-    out = {}
-    for name, (bound, amount) in work.items():
-        if name not in kernels or kernels[name]["total_ms"] <= 0:
-            continue
-        sec = kernels[name]["total_ms"] * 1e-3
-        if bound == "hbm":
-            ach, peak, unit = amount / sec / 1e9, hbm, "GB/s"
-        else:
-            ach, peak, unit = amount / sec / 1e12, 148 * 128 * 2 * 1.965e9 / 1e12, "TFLOP/s"
-        out[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                     "avg_us": 1e3 * kernels[name]["total_ms"] / kernels[name]["launches"]}
-    total = sum(k["total_ms"] for k in kernels.values())
-    dom = max(kernels, key=lambda k: kernels[k]["total_ms"])
-    r = dict(out.get(dom, {"bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None}))
-    r.update({"kernel": dom, "share_of_step": kernels[dom]["total_ms"] / total, "traffic": None,
-              "peak_source": src + (" HBM copy" if r["bound"] == "hbm" else "; fp32 peak = 148 SMs x 128 FMA x 2 x 1.965 GHz (nominal, no measured fp32 figure)"),
-              "per_kernel": out})
-    return r
 
 
 def main():
@@ -316,7 +715,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: --steps)")
+    ap.add_argument("--cpu-iters", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -94,7 +94,8 @@ struct NetDev {               // device-side view of one NeuralNetwork (side tab
     bool a0_borrowed = false;
     float* a0_owned = nullptr;
     int a0_cap = 0;
-    float* partials = nullptr;   // [splits][param_count]
+    float* partials = nullptr;   // [splits][slab_stride()]
+    size_t slab_stride() const { return (param_count + 31) & ~size_t(31); }   // 128-byte multiple: keeps every slab TMA/float4-aligned
     size_t partials_cap = 0;     // floats
     int last_splits = 1;
     int last_m = 0;

@@ -128,8 +128,16 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
     if (m != nd->last_m) B200_FATAL("backward with m=%d after forward with m=%d", m, nd->last_m);
     ensure_bwd_capacity(nn, nd, m);
     const int L = nn->num_layers - 1;
-    const int splits = choose_splits(m, nd->param_count);
-    const size_t need = (size_t)splits * nd->param_count;
+    int splits = choose_splits(m, nd->param_count);
+    if (matmul_precision() == 1 && m >= 128) {
+        // tensor-core dW: one 128x256 tile per CTA, so split-K only until ~2 CTAs per SM exist for the widest
+        // layer; more slabs would only add slab traffic (each slab is a full copy of the gradient).
+        int tiles = 0;
+        for (int i = 0; i < L; i++)
+            if (nd->sizes[i] >= 64 && nd->sizes[i + 1] >= 64) tiles = std::max(tiles, div_up(nd->sizes[i], 256) * div_up(nd->sizes[i + 1], 128));
+        if (tiles > 0) splits = std::min(splits, std::max(1, div_up(2 * num_sms(), tiles)));
+    }
+    const size_t need = (size_t)splits * nd->slab_stride();
     if (need > nd->partials_cap) {
         CUDA_CHECK(cudaStreamSynchronize(stream()));
         if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
@@ -146,7 +154,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
     }
     for (int i = L - 1; i >= 0; i--) {
         const int n = nd->sizes[i], l = nd->sizes[i + 1];
-        linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->param_count, splits, g,
+        linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->slab_stride(), splits, g,
                                nd->a[i], m, n, l);
         if (i > 0) {  // dX of layer 0 is unused by every caller (the reference computes it anyway)
             const float* wsrc = (matmul_precision() == 1 && nd->params_tf32) ? nd->params_tf32 : nd->params;
@@ -159,7 +167,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
 
 void net_reduce_grads(NeuralNetwork* nn) {
     NetDev* nd = net_dev(nn);
-    reduce_partials(nd->grads, nd->partials, nd->last_splits, nd->param_count, (int)nd->param_count);
+    reduce_partials(nd->grads, nd->partials, nd->last_splits, nd->slab_stride(), (int)nd->param_count);
 }
 
 static NeuralNetwork* alloc_host_net(int num_layers) {

@@ -102,14 +102,13 @@ static const int* next_permutation(Trainer* t, int n) {
 }
 
 // PPO_B200_FUSED=0 forces the generic layer-wise kernels (A/B testing, parity tests of both paths).
-static int g_force_path_decl_dummy = 0;
 static bool use_fused_env() {
     static int cached = -1;
     if (cached < 0) { const char* e = getenv("PPO_B200_FUSED"); cached = (e && e[0] == '0') ? 0 : 1; }
     return cached == 1;
 }
 static int g_force_path = -1;   // tests: -1 env default, 0 layer-wise, 1 fused
-static bool use_fused() { (void)g_force_path_decl_dummy; return g_force_path < 0 ? use_fused_env() : g_force_path == 1; }
+static bool use_fused() { return g_force_path < 0 ? use_fused_env() : g_force_path == 1; }
 
 // compute_gae on device arrays (src/ppo.cu:261-323): two V forwards, scan, global stats, normalise.
 static void gae_device(NeuralNetwork* V, TrajectoryBuffer* b, Trainer* t, int limit, float gamma, float lambda) {
@@ -199,7 +198,7 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
             } else {
                 adam_flat(ndV->params, ndV->grads, ppo->adam_V->m, ppo->adam_V->v, (int)ndV->param_count, ppo->lr_V,
                           ppo->adam_V->beta1, ppo->adam_V->beta2, ppo->adam_V->time_step, ndV->partials,
-                          ndV->last_splits, ndV->param_count);
+                          ndV->last_splits, ndV->slab_stride());
             }
         }
     }
@@ -249,7 +248,7 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
             else
                 adam_flat(ndP->params, ndP->grads, ppo->adam_policy->m, ppo->adam_policy->v, (int)ndP->param_count,
                           ppo->lr_policy, ppo->adam_policy->beta1, ppo->adam_policy->beta2, ppo->adam_policy->time_step,
-                          ndP->partials, ndP->last_splits, ndP->param_count);
+                          ndP->partials, ndP->last_splits, ndP->slab_stride());
         }
     }
 }
