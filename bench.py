@@ -649,6 +649,16 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if sampler else None
     extra = wl.extra(ms / args.steps) if rank == 0 else {}
 
+    if args.only_value:
+        if rank == 0:
+            print(json.dumps({"only_value": True, "workload": args.workload, "ms_per_step": ms / args.steps,
+                              "gpu_launches": int(launches)}), flush=True)
+        wl.teardown()
+        if world > 1:
+            L.ppo_b200_dist_finalize()
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: the host-buffer call, copies inside the timed region -----------------------------------
     e2e_steps = args.steps if args.e2e_steps <= 0 else args.e2e_steps
     wl.step_e2e(1)                                       # warm the pinned mirrors
@@ -719,6 +729,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: --steps)")
     ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--only-value", action="store_true",
+                    help="skip the e2e / per-kernel / CPU legs (short command for ncu passes; not a bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

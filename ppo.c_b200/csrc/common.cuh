@@ -77,6 +77,24 @@ extern bool g_profiling;
         if (::b200::g_profiling) ::b200::profile_mark(#kernel, false);           \
     } while (0)
 
+// Same, through cudaLaunchKernelEx with programmatic dependent launch: when `pdl` is true the kernel may
+// start while its predecessor in the stream is still running; it must execute griddepcontrol.wait before
+// touching anything the predecessor writes.
+#define B200_LAUNCH_PDL(kernel, grid, block, smem, pdl, ...)                                    \
+    do {                                                                                        \
+        if (::b200::g_profiling) ::b200::profile_mark(#kernel, true);                           \
+        cudaLaunchConfig_t cfg__ = {};                                                          \
+        cfg__.gridDim = dim3(grid); cfg__.blockDim = dim3(block);                               \
+        cfg__.dynamicSmemBytes = (smem); cfg__.stream = ::b200::stream();                       \
+        cudaLaunchAttribute attr__[1];                                                          \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+        attr__[0].val.programmaticStreamSerializationAllowed = (pdl) ? 1 : 0;                   \
+        cfg__.attrs = attr__; cfg__.numAttrs = 1;                                               \
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__));                            \
+        ++::b200::g_launches;                                                                   \
+        if (::b200::g_profiling) ::b200::profile_mark(#kernel, false);                          \
+    } while (0)
+
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers -----------------------------------------------------------------------------

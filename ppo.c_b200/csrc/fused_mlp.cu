@@ -41,7 +41,8 @@ struct FusedNet {
     int sizes[kFusedMaxLayers + 1];
     int acts[kFusedMaxLayers];
     int w_off[kFusedMaxLayers], b_off[kFusedMaxLayers];   // offsets in the flat parameter vector
-    int wt_off[kFusedMaxLayers];        // offsets of Wt[in][out_pad] inside the weight image (floats)
+    int wt_off[kFusedMaxLayers];        // offsets of Wt[in][ldw] inside the weight image (floats)
+    int ldw[kFusedMaxLayers];           // row stride of Wt (>= pad4(out); the 64-wide tile kernel pads it by 4)
     int bs_off[kFusedMaxLayers];        // offsets of the layer biases inside the weight image (floats)
     int img_floats;                     // image size (multiple of 32 floats = 128 B; TMA bulk needs 16 B)
     int a_off[kFusedMaxLayers + 1];     // offsets of At buffers in shared memory (floats, after the image)
@@ -115,7 +116,7 @@ __device__ __forceinline__ void store_rows(float* base, const float (&a)[RT]) {
 template <int TM, int RT>
 __device__ __forceinline__ void fused_forward_layer(const float* __restrict__ Xt, const float* __restrict__ Wt,
                                                     const float* __restrict__ bias, float* __restrict__ Yt,
-                                                    int n_in, int n_out, int act) {
+                                                    int n_in, int n_out, int act, int ldw) {
     constexpr int TMP = TM + 4, RL = TM / RT;
     const int tr = threadIdx.x % RL, tc = threadIdx.x / RL;
     const int out_pad = pad4(n_out);
@@ -133,7 +134,7 @@ __device__ __forceinline__ void fused_forward_layer(const float* __restrict__ Xt
     for (int k = 0; k < n_in; k++) {
         float a[RT];
         load_rows<TM, RT>(xp + k * TMP, a);
-        const float4 w = *reinterpret_cast<const float4*>(wp + k * out_pad);
+        const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
         const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int r = 0; r < RT; r++)
@@ -153,10 +154,10 @@ __device__ __forceinline__ void fused_forward_layer(const float* __restrict__ Xt
 template <int TM, int RT>
 __device__ __forceinline__ void fused_backward_input(const float* __restrict__ Gt, const float* __restrict__ Wt,
                                                      const float* __restrict__ Ht, float* __restrict__ GXt,
-                                                     int n_in, int n_out, int act_prev) {
+                                                     int n_in, int n_out, int act_prev, int ldw) {
     constexpr int TMP = TM + 4, RL = TM / RT;
     const int tr = threadIdx.x % RL, tc = threadIdx.x / RL;
-    const int out_pad = pad4(n_out);
+    const int out_pad = ldw;
     if (4 * tc >= pad4(n_in)) return;
     float acc[RT][4];
 #pragma unroll
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kFusedThreads, (TM == 64 && RT == 4) ? 2 : 1) 
     // ---- forward
     for (int l = 0; l < net.L; l++) {
         fused_forward_layer<TM, RT>(act0 + net.a_off[l], img + net.wt_off[l], img + net.bs_off[l], act0 + net.a_off[l + 1],
-                                    net.sizes[l], net.sizes[l + 1], net.acts[l]);
+                                    net.sizes[l], net.sizes[l + 1], net.acts[l], net.ldw[l]);
         __syncthreads();
     }
     const float* Yt = act0 + net.a_off[net.L];
@@ -404,9 +405,374 @@ __global__ void __launch_bounds__(kFusedThreads, (TM == 64 && RT == 4) ? 2 : 1) 
         const float* Xt = act0 + net.a_off[l];
         fused_weights_dispatch<TM>(G, Xt, slab + net.w_off[l], slab + net.b_off[l], n_in, n_out);
         if (l > 0) {
-            fused_backward_input<TM, RT>(G, img + net.wt_off[l], Xt, Gn, n_in, n_out, net.acts[l - 1]);
+            fused_backward_input<TM, RT>(G, img + net.wt_off[l], Xt, Gn, n_in, n_out, net.acts[l - 1], net.ldw[l]);
             __syncthreads();
             float* tmp = G; G = Gn; Gn = tmp;
+        }
+    }
+}
+
+
+// ===================================================================================================
+// 64-wide tile kernel (every layer width <= 64: the reference's Pendulum / 2x64 nets).
+//
+// 128 threads, 64-row tiles, up to 3 CTAs per SM.  Compared with fused_update_kernel above:
+//   * 8 rows x 4 columns per thread in forward and dX: 3 conflict-free LDS.128 (= 3 shared-memory
+//     wavefronts) feed 32 FFMAs (the 4x4 tile needed 3 wavefronts per 16 -> the LSU pipe was 65% busy);
+//   * dX walks the reduction 4 j's at a time on the SAME k-major weight image (Wt rows padded to
+//     ldw = pad4(out)+4 floats so the four k-rows a warp touches sit in different banks): 12 LDS.128 per
+//     128 FFMAs instead of 5 loads per 16;
+//   * gradients are written IN PLACE over the activations they belong to (no separate G buffers), which
+//     is what makes 3 CTAs per SM fit;
+//   * skinny layers (out <= 8: value head, action mean) and the bias gradients have their own
+//     thread mappings instead of running a mostly-empty 64x64 tile.
+// Rows of a thread: {4tr..4tr+3} U {32+4tr..32+4tr+3}, tr = tid & 7; column group tc = tid >> 3.
+// ===================================================================================================
+constexpr int kT64Threads = 128;
+constexpr int kT64TM = 64;
+constexpr int kT64TMP = 68;      // feature row stride in floats; 68 % 32 == 4 keeps feature-strided LDS.128 conflict-free
+
+__device__ __forceinline__ void t64_load8(const float* base, float (&a)[8]) {
+    const float4 a0 = *reinterpret_cast<const float4*>(base);
+    const float4 a1 = *reinterpret_cast<const float4*>(base + 32);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+}
+__device__ __forceinline__ void t64_store8(float* base, const float (&a)[8]) {
+    *reinterpret_cast<float4*>(base) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(base + 32) = make_float4(a[4], a[5], a[6], a[7]);
+}
+
+// Yt[j][r] = act(sum_k Xt[k][r] * Wt[k][j] + b[j]),  n_out in (8, 64]
+__device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
+                                            const float* __restrict__ bias, float* __restrict__ Yt, int n_in, int n_out, int act) {
+    const int tr = threadIdx.x & 7, tc = threadIdx.x >> 3;
+    if (4 * tc >= pad4(n_out)) return;
+    float acc[8][4];
+    {
+        const float4 b = *reinterpret_cast<const float4*>(bias + 4 * tc);     // bias block is zero-padded to pad4
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = bv[c];
+    }
+    const float* xp = Xt + 4 * tr;
+    const float* wp = Wt + 4 * tc;
+#pragma unroll 4
+    for (int k = 0; k < n_in; k++) {
+        float a[8];
+        t64_load8(xp + k * kT64TMP, a);
+        const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float o[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) o[r] = act_apply(acc[r][c], act);
+        t64_store8(Yt + (4 * tc + c) * kT64TMP + 4 * tr, o);
+    }
+}
+
+// Skinny forward, n_out <= 8: thread = (row, k-half); the two halves meet through `scratch` (>= 8*64 floats).
+// Contains one __syncthreads: every thread of the CTA must call it.
+__device__ __forceinline__ void t64_forward_skinny(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
+                                                   const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ scratch,
+                                                   int n_in, int n_out, int act) {
+    const int r = threadIdx.x & 63, h = threadIdx.x >> 6;
+    const int kh = (n_in + 1) >> 1;
+    const int k0 = h ? kh : 0, k1 = h ? n_in : kh;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    for (int k = k0; k < k1; k++) {
+        const float x = Xt[k * kT64TMP + r];
+        const float4 w0 = *reinterpret_cast<const float4*>(Wt + k * ldw);
+        acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+        if (n_out > 4) {
+            const float4 w1 = *reinterpret_cast<const float4*>(Wt + k * ldw + 4);
+            acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+        }
+    }
+    if (h) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j < n_out) scratch[j * 64 + r] = acc[j];
+    }
+    __syncthreads();
+    if (!h) {
+        const int out_pad = pad4(n_out);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (j < out_pad) Yt[j * kT64TMP + r] = (j < n_out) ? act_apply(acc[j] + scratch[j * 64 + r] + bias[j], act) : 0.f;
+    }
+}
+
+// In place: Ht[k][r] <- (sum_j Gt[j][r] * Wt[k][j]) * act'(Ht[k][r]);  k = tc + 16c (interleaved so the four
+// Wt rows a warp reads per load are consecutive -> different banks).  Gt rows [n_out, pad4(n_out)) are zero.
+__device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt, const float* __restrict__ Wt, int ldw,
+                                                   float* __restrict__ Ht, int n_in, int n_out, int act_prev) {
+    const int tr = threadIdx.x & 7, tc = threadIdx.x >> 3;
+    if (tc >= n_in) return;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+    const float* wrow[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) wrow[c] = Wt + (size_t)min(tc + 16 * c, n_in - 1) * ldw;
+    const float* gp = Gt + 4 * tr;
+    const int jpad = pad4(n_out);
+#pragma unroll 1
+    for (int j0 = 0; j0 < jpad; j0 += 4) {
+        float wv[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float4 w = *reinterpret_cast<const float4*>(wrow[c] + j0);
+            wv[c][0] = w.x; wv[c][1] = w.y; wv[c][2] = w.z; wv[c][3] = w.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            float g[8];
+            t64_load8(gp + (j0 + jj) * kT64TMP, g);
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = fmaf(g[r], wv[c][jj], acc[r][c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int k = tc + 16 * c;
+        if (k >= n_in) continue;
+        float h[8], o[8];
+        t64_load8(Ht + k * kT64TMP + 4 * tr, h);
+#pragma unroll
+        for (int r = 0; r < 8; r++) o[r] = act_grad(h[r], acc[r][c], act_prev);
+        t64_store8(Ht + k * kT64TMP + 4 * tr, o);
+    }
+}
+
+// gW[j][k] = sum_r Gt[j][r] * Xt[k][r];  j = tj + 16a (tj = tid >> 3), k = tk + 8b (tk = tid & 7): the 4 G rows
+// and 8 X rows a warp loads per instruction are consecutive features -> one wavefront each.
+template <int JJ, int KK>
+__device__ __forceinline__ void t64_backward_weights(const float* __restrict__ Gt, const float* __restrict__ Xt,
+                                                     float* __restrict__ gW, int n_in, int n_out) {
+    const int tk = threadIdx.x & 7, tj = threadIdx.x >> 3;
+    if ((tj & ~3) >= n_out) return;          // warp-uniform: this warp owns no valid output row
+    float acc[JJ][KK];
+#pragma unroll
+    for (int a = 0; a < JJ; a++)
+#pragma unroll
+        for (int b = 0; b < KK; b++) acc[a][b] = 0.f;
+    int jrow[JJ], krow[KK];
+#pragma unroll
+    for (int a = 0; a < JJ; a++) jrow[a] = min(tj + 16 * a, n_out - 1) * kT64TMP;
+#pragma unroll
+    for (int b = 0; b < KK; b++) krow[b] = min(tk + 8 * b, n_in - 1) * kT64TMP;
+#pragma unroll 2
+    for (int r = 0; r < kT64TM; r += 4) {
+        float4 g[JJ], x[KK];
+#pragma unroll
+        for (int a = 0; a < JJ; a++) g[a] = *reinterpret_cast<const float4*>(Gt + jrow[a] + r);
+#pragma unroll
+        for (int b = 0; b < KK; b++) x[b] = *reinterpret_cast<const float4*>(Xt + krow[b] + r);
+#pragma unroll
+        for (int a = 0; a < JJ; a++)
+#pragma unroll
+            for (int b = 0; b < KK; b++) {
+                acc[a][b] = fmaf(g[a].x, x[b].x, acc[a][b]);
+                acc[a][b] = fmaf(g[a].y, x[b].y, acc[a][b]);
+                acc[a][b] = fmaf(g[a].z, x[b].z, acc[a][b]);
+                acc[a][b] = fmaf(g[a].w, x[b].w, acc[a][b]);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < JJ; a++) {
+        const int j = tj + 16 * a;
+        if (j >= n_out) continue;
+#pragma unroll
+        for (int b = 0; b < KK; b++) {
+            const int k = tk + 8 * b;
+            if (k < n_in) gW[(size_t)j * n_in + k] = acc[a][b];
+        }
+    }
+}
+
+__device__ __forceinline__ void t64_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out) {
+    const int jj = (n_out + 15) / 16, kk = (n_in + 7) / 8;
+#define B200_DW(J, K) t64_backward_weights<J, K>(Gt, Xt, gW, n_in, n_out)
+#define B200_DWK(J) do { if (kk <= 1) B200_DW(J, 1); else if (kk <= 2) B200_DW(J, 2); else if (kk <= 4) B200_DW(J, 4); else B200_DW(J, 8); } while (0)
+    if (jj <= 1) B200_DWK(1); else if (jj <= 2) B200_DWK(2); else B200_DWK(4);
+#undef B200_DWK
+#undef B200_DW
+}
+
+// gb[j] = sum_r Gt[j][r]: thread = (j, row half), fixed-order sums
+__device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out) {
+    const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
+    float s = 0.f;
+    if (j < n_out) {
+        const float* gp = Gt + j * kT64TMP + 32 * h;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 g = *reinterpret_cast<const float4*>(gp + 4 * i);
+            s += (g.x + g.y) + (g.z + g.w);
+        }
+    }
+    s += __shfl_xor_sync(kFull, s, 1);
+    if (h == 0 && j < n_out) gb[j] = s;
+}
+
+__global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const FusedArgs p) {
+    constexpr int TM = kT64TM, TMP = kT64TMP;
+    extern __shared__ __align__(128) float smem[];
+    const FusedNet& net = p.net;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * TM;
+    const int S = net.sizes[0], OUT = net.sizes[net.L];
+    float* img = smem;
+    float* act0 = smem + net.img_floats;
+    float* red = smem + p.smem_red_off;                  // 64 floats
+    int* src_rows = reinterpret_cast<int*>(red + 64);    // TM ints
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64 + TM);
+    float* scratch = smem + p.smem_g_off;                // 8 * 64 floats (skinny forward halves)
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    float h_target = 0.f, h_adv = 0.f, h_lp_old = 0.f, h_act[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) h_act[j] = 0.f;
+    int my_src = -1;
+    if (tid < TM) {
+        const int r = row0 + tid;
+        if (r < p.m) my_src = p.idx ? p.idx[(p.offset + r) % p.limit] : p.offset + r;
+        src_rows[tid] = my_src;
+    }
+    __syncthreads();
+    {   // gather the input tile: Xt[k][r] = state[src][k]; padded feature rows are zero
+        float* Xt = act0 + net.a_off[0];
+        const int SP = pad4(S);
+        for (int e = tid; e < TM * SP; e += kT64Threads) {
+            const int r = e / SP, k = e - r * SP;
+            const int src = src_rows[r];
+            Xt[k * TMP + r] = (src >= 0 && k < S) ? p.state[(size_t)src * S + k] : 0.f;
+        }
+    }
+    if (my_src >= 0) {
+        if (p.mode == kFusedValue) {
+            h_target = p.adv_target[my_src];
+        } else if (p.mode == kFusedPolicy) {
+            h_adv = p.advantage[my_src];
+            h_lp_old = p.logprob[my_src];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < OUT) h_act[j] = p.action[(size_t)my_src * OUT + j];
+        }
+    }
+    // Everything above reads only rollout data and the permutation.  The weight image is written by the
+    // previous minibatch's Adam kernel: under programmatic dependent launch this is where we wait for it.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
+        mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+        tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    mbar_wait(mbar, 0);
+    __syncthreads();
+    // ---- forward
+    for (int l = 0; l < net.L; l++) {
+        const float* Xt = act0 + net.a_off[l];
+        float* Yt = act0 + net.a_off[l + 1];
+        if (net.sizes[l + 1] <= 8)
+            t64_forward_skinny(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, scratch, net.sizes[l], net.sizes[l + 1], net.acts[l]);
+        else
+            t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, net.sizes[l], net.sizes[l + 1], net.acts[l]);
+        __syncthreads();
+    }
+    float* Yt = act0 + net.a_off[net.L];
+    if (p.mode == kFusedForward) {
+        for (int e = tid; e < TM * OUT; e += kT64Threads) {
+            const int r = e / OUT, j = e - r * OUT;
+            if (row0 + r < p.m) p.y_out[(size_t)(row0 + r) * OUT + j] = Yt[j * TMP + r];
+        }
+        return;
+    }
+    float* slab = p.partials + (size_t)blockIdx.x * p.slab;
+    // ---- fused loss head: dLoss/dy written IN PLACE over the output tile (rows >= OUT of it stay zero)
+    {
+        float loss_term = 0.f;
+        float gls[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) gls[j] = 0.f;
+        if (tid < TM) {
+            float gout[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) gout[j] = 0.f;
+            float yv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) yv[j] = (j < OUT) ? Yt[j * TMP + tid] : 0.f;
+            if (my_src >= 0) {
+                if (p.mode == kFusedValue) {            // src/loss.cu:5-23
+                    gout[0] = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(yv[0], h_target)), (float)p.m_total);
+                    const float d = __fsub_rn(h_target, yv[0]);
+                    loss_term = __fmul_rn(d, d);
+                } else {                                // src/policy.cu:67-111 + src/ppo.cu:89-98
+                    const float lp = fused_log_prob(yv, p.log_std, h_act, OUT);
+                    const float ratio = expf(__fsub_rn(lp, h_lp_old));
+                    const bool adv_pos = h_adv > 0.f;
+                    const bool hi = ratio > 1.f + p.epsilon, lo = ratio < 1.f - p.epsilon;
+                    const float sel = adv_pos ? (hi ? 1.f + p.epsilon : ratio) : (lo ? 1.f - p.epsilon : ratio);
+                    loss_term = __fmul_rn(h_adv, sel);
+                    const int keep = adv_pos ? !hi : !lo;
+                    const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)p.m_total);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (j < OUT) {
+                            const float e2 = expf(-2.f * p.log_std[j]);
+                            const float diff = __fsub_rn(h_act[j], yv[j]);
+                            gout[j] = __fmul_rn(__fmul_rn(diff, e2), g);
+                            gls[j] = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), g);
+                        }
+                }
+            }
+            const int out_act = net.acts[net.L - 1];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < OUT) Yt[j * TMP + tid] = act_grad(yv[j], gout[j], out_act);
+        }
+        const int warp = tid >> 5, lane = tid & 31;       // warps 0..1 hold data, the others contribute zeros
+        float v = warp_sum(loss_term);
+        if (lane == 0) red[warp] = v;
+        if (p.mode == kFusedPolicy) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < OUT) { const float s = warp_sum(gls[j]); if (lane == 0) red[8 + j * 4 + warp] = s; }
+        }
+        __syncthreads();
+        if (tid == 0) slab[net.P + OUT] = (red[0] + red[1]) + (red[2] + red[3]);
+        if (p.mode == kFusedPolicy && tid < OUT) {
+            const float* q = red + 8 + tid * 4;
+            slab[net.P + tid] = (q[0] + q[1]) + (q[2] + q[3]);
+        }
+    }
+    // ---- backward: G_{l+1} lives in the slot of A_{l+1}; dX overwrites A_l in place
+    for (int l = net.L - 1; l >= 0; l--) {
+        const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
+        float* Xt = act0 + net.a_off[l];
+        const float* G = act0 + net.a_off[l + 1];
+        t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out);
+        t64_bias_grad(G, slab + net.b_off[l], n_out);
+        if (l > 0) {
+            __syncthreads();                       // every reader of A_l's forward values is done
+            t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, n_in, n_out, net.acts[l - 1]);
+            __syncthreads();
         }
     }
 }
@@ -430,8 +796,7 @@ struct ReduceAdamArgs {
     float* reduced;
 };
 
-__device__ __forceinline__ float adam_apply(const AdamSeg& s, int i, float g) {
-    float m = s.m[i], v = s.v[i], w = s.w[i];
+__device__ __forceinline__ float adam_apply(const AdamSeg& s, int i, float g, float m, float v, float w) {
     m = __fadd_rn(__fmul_rn(s.beta1, m), __fmul_rn(s.omb1, g));
     v = __fadd_rn(__fmul_rn(s.beta2, v), __fmul_rn(s.omb2, __fmul_rn(g, g)));
     const float denom = (float)((double)__fsqrt_rn(__fdiv_rn(v, s.bc2)) + 1e-8);
@@ -446,31 +811,55 @@ __host__ __device__ inline int image_index(const FusedNet& n, int e) {
         const int n_in = n.sizes[l], n_out = n.sizes[l + 1];
         if (e < n.b_off[l]) {
             const int q = e - n.w_off[l], j = q / n_in, k = q - j * n_in;
-            return n.wt_off[l] + k * pad4(n_out) + j;
+            return n.wt_off[l] + k * n.ldw[l] + j;
         }
         if (e < n.b_off[l] + n_out) return n.bs_off[l] + (e - n.b_off[l]);
     }
     return -1;
 }
 
-// One CTA per 32 consecutive slab entries; 8 warps split the slabs, fixed-order combine.
-__global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const ReduceAdamArgs p) {
-    __shared__ float red[8][33];
+// One CTA per 32 consecutive slab entries; 16 warps split the slabs (each keeps up to 16 independent loads in
+// flight, so 256 slabs cost one L2 round trip), fixed-order combine -> deterministic gradients.
+constexpr int kRedWarps = 16;
+__global__ void __launch_bounds__(32 * kRedWarps) fused_reduce_adam_kernel(const ReduceAdamArgs p) {
+    __shared__ float red[kRedWarps][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * 32 + lane;
     const int total = p.P + p.A + 1;
+    // Optimiser state of this thread's element: written by the PREVIOUS Adam launch (complete long ago), so it can
+    // be fetched before the dependency wait and its latency hides behind the tail of the update kernel.
+    float pm = 0.f, pv = 0.f, pw = 0.f;
+    const bool is_net = e < p.P, is_ls = !is_net && e < p.P + p.A && p.mode == kFusedPolicy;
+    if (warp == 0 && p.apply) {
+        if (is_net) { pm = p.net.m[e]; pv = p.net.v[e]; pw = p.net.w[e]; }
+        else if (is_ls) { pm = p.ls.m[e - p.P]; pv = p.ls.v[e - p.P]; pw = p.ls.w[e - p.P]; }
+        else if (e == p.P + p.A && p.mode == kFusedPolicy) {          // entropy of the policy that produced this loss
+            pw = (float)(p.A * 0.5 * (1 + log(2 * kPiF)));            // src/policy.cu:171-178
+            for (int j = 0; j < p.A; j++) pw += p.log_std[j];
+        }
+    }
+    // programmatic dependent launch: the slabs are written by the update kernel that precedes us in the stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     float s = 0.f;
     if (e < total) {
-        const int per = (p.nparts + 7) / 8;
+        const int per = (p.nparts + kRedWarps - 1) / kRedWarps;
         const int b0 = warp * per, b1 = min(p.nparts, b0 + per);
         const float* src = p.partials + e;
         int b = b0;
-        for (; b + 8 <= b1; b += 8) {       // 8 independent loads in flight, added in slab order
-            float t[8];
+        for (; b + 16 <= b1; b += 16) {     // 16 independent loads in flight, added in slab order
+            float t[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++) t[u] = src[(size_t)(b + u) * p.slab];
+            for (int u = 0; u < 16; u++) t[u] = src[(size_t)(b + u) * p.slab];
 #pragma unroll
-            for (int u = 0; u < 8; u++) s += t[u];
+            for (int u = 0; u < 16; u++) s += t[u];
+        }
+        for (; b + 4 <= b1; b += 4) {
+            float t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = src[(size_t)(b + u) * p.slab];
+#pragma unroll
+            for (int u = 0; u < 4; u++) s += t[u];
         }
         for (; b < b1; b++) s += src[(size_t)b * p.slab];
     }
@@ -479,21 +868,19 @@ __global__ void __launch_bounds__(256) fused_reduce_adam_kernel(const ReduceAdam
     if (warp != 0 || e >= total) return;
     float g = red[0][lane];
 #pragma unroll
-    for (int w = 1; w < 8; w++) g += red[w][lane];
+    for (int w = 1; w < kRedWarps; w++) g += red[w][lane];
     if (!p.apply) { p.reduced[e] = g; return; }
-    if (e < p.P) {
-        const float w = adam_apply(p.net, e, g);
+    if (is_net) {
+        const float w = adam_apply(p.net, e, g, pm, pv, pw);
         const int ii = image_index(p.layout, e);
         if (ii >= 0) p.image[ii] = w;
     } else if (e < p.P + p.A) {
-        if (p.mode == kFusedPolicy) adam_apply(p.ls, e - p.P, g + (-p.ent_coeff));   // src/ppo.cu:436-438
+        if (is_ls) adam_apply(p.ls, e - p.P, g + (-p.ent_coeff), pm, pv, pw);   // src/ppo.cu:436-438
     } else {
         if (p.mode == kFusedValue) {
             *p.loss_slot += g / (float)p.m_total;
         } else {
-            float entropy = (float)(p.A * 0.5 * (1 + log(2 * kPiF)));
-            for (int j = 0; j < p.A; j++) entropy += p.log_std[j];
-            *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * entropy;
+            *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
         }
     }
 }
@@ -508,11 +895,12 @@ __global__ void __launch_bounds__(256) build_image_kernel(const float* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-struct FusedPlan { bool ok; int tm, rt; size_t smem_bytes; FusedNet net; int g_off, red_off; };
+struct FusedPlan { bool ok; int tm, rt; size_t smem_bytes; FusedNet net; int g_off, red_off; int kind; };   // kind 1: 64-wide tile kernel
 
 static FusedPlan make_plan(NetDev* nd, int tm, int rt) {
     FusedPlan pl{};
     pl.ok = false;
+    pl.kind = 0;
     const int L = nd->num_layers - 1;
     if (L < 1 || L > kFusedMaxLayers) return pl;
     const int tmp = tm + 4;
@@ -529,7 +917,8 @@ static FusedPlan make_plan(NetDev* nd, int tm, int rt) {
         if (l > 0 && (pad4(n.sizes[l]) > 4 * cg || n.sizes[l] > 128)) return pl;   // dX column coverage
         if (n.sizes[l] > 128) return pl;
         n.wt_off[l] = off;
-        off += n.sizes[l] * pad4(n.sizes[l + 1]);
+        n.ldw[l] = pad4(n.sizes[l + 1]);
+        off += n.sizes[l] * n.ldw[l];
     }
     for (int l = 0; l < L; l++) { n.bs_off[l] = off; off += pad4(n.sizes[l + 1]); }
     n.img_floats = (off + 31) & ~31;                 // 128-byte multiple
@@ -555,7 +944,56 @@ static FusedPlan make_plan(NetDev* nd, int tm, int rt) {
     return pl;
 }
 
+// Plan for fused_tile64_kernel: every width <= 64, <= 8 outputs.
+static FusedPlan make_plan64(NetDev* nd) {
+    FusedPlan pl{};
+    pl.ok = false;
+    pl.kind = 1;
+    const int L = nd->num_layers - 1;
+    if (L < 1 || L > kFusedMaxLayers) return pl;
+    FusedNet& n = pl.net;
+    n.L = L;
+    for (int l = 0; l <= L; l++) { n.sizes[l] = nd->sizes[l]; if (n.sizes[l] > 64 || n.sizes[l] < 1) return pl; }
+    if (n.sizes[L] > 8) return pl;
+    int off = 0, maxw = 4;
+    for (int l = 0; l < L; l++) {
+        n.acts[l] = nd->acts[l];
+        n.w_off[l] = (int)nd->w_off[l];
+        n.b_off[l] = (int)nd->b_off[l];
+        n.wt_off[l] = off;
+        n.ldw[l] = pad4(n.sizes[l + 1]) + 4;         // +4: consecutive Wt rows start 4 banks apart (dX reads)
+        if (n.sizes[l + 1] <= 8) n.ldw[l] = 8;       // skinny layers read up to 8 columns per row
+        off += n.sizes[l] * n.ldw[l];
+    }
+    for (int l = 0; l < L; l++) { n.bs_off[l] = off; off += std::max(8, pad4(n.sizes[l + 1])); }
+    n.img_floats = (off + 31) & ~31;
+    n.P = (int)nd->param_count;
+    off = 0;
+    for (int l = 0; l <= L; l++) {
+        n.a_off[l] = off;
+        off += std::max(pad4(n.sizes[l]), l == L ? 8 : 4) * kT64TMP;
+        maxw = std::max(maxw, pad4(n.sizes[l]));
+    }
+    n.max_width_pad = maxw;
+    off += n.img_floats;
+    pl.g_off = off;            // skinny-forward scratch: 8 x 64 floats
+    off += 8 * 64;
+    pl.red_off = off;
+    off += 64 + kT64TM + 4;
+    pl.smem_bytes = (size_t)off * sizeof(float);
+    pl.tm = kT64TM;
+    pl.rt = 8;
+    pl.ok = pl.smem_bytes <= 220 * 1024;
+    return pl;
+}
+
+static int g_fused_variant = -1;     // PPO_B200_FUSED_KERNEL=old forces the 256-thread kernel (A/B runs)
 static FusedPlan choose_plan(NetDev* nd) {
+    if (g_fused_variant < 0) { const char* e = getenv("PPO_B200_FUSED_KERNEL"); g_fused_variant = (e && strcmp(e, "old") == 0) ? 0 : 1; }
+    if (g_fused_variant == 1) {
+        FusedPlan q = make_plan64(nd);
+        if (q.ok) return q;
+    }
     FusedPlan p = make_plan(nd, 64, 4);
     if (p.ok) return p;
     return make_plan(nd, 64, 8);
@@ -579,14 +1017,20 @@ static float* ensure_image(NetDev* nd, const FusedPlan& pl) {
     return nd->image;
 }
 
-static void launch_fused(NetDev* nd, const FusedPlan& pl, FusedArgs& a) {
+static void launch_fused(NetDev* nd, const FusedPlan& pl, FusedArgs& a, bool pdl = false) {
     a.net = pl.net;
     a.image = ensure_image(nd, pl);
     a.smem_g_off = pl.g_off;
     a.smem_red_off = pl.red_off;
     const int blocks = div_up(a.m, pl.tm);
-    static size_t configured[2] = {0, 0};
-    if (pl.rt == 4) {
+    static size_t configured[3] = {0, 0, 0};
+    if (pl.kind == 1) {
+        if (pl.smem_bytes > configured[2]) {
+            CUDA_CHECK(cudaFuncSetAttribute(fused_tile64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+            configured[2] = pl.smem_bytes;
+        }
+        B200_LAUNCH_PDL(fused_tile64_kernel, blocks, kT64Threads, pl.smem_bytes, pdl, a);
+    } else if (pl.rt == 4) {
         if (pl.smem_bytes > configured[0]) {
             CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
             configured[0] = pl.smem_bytes;
@@ -626,9 +1070,17 @@ static AdamSeg make_seg(float* w, float* g, Adam* adam, float lr) {
 // reduced_out != nullptr (data-parallel path): no Adam; the reduced slab [grads | grad_log_std | loss
 // term] is written there and the caller all-reduces and applies the optimiser.
 // Returns false when the net is outside the fused kernel's limits (caller uses the layer-wise path).
+static bool pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("PPO_B200_PDL"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
+
+// `chained`: the kernel that precedes this call in the stream is the fused_reduce_adam_kernel of the previous
+// minibatch of the same net (so the update kernel may be launched programmatically dependent on it).
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
-                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out) {
+                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained) {
     NetDev* nd = net_dev(nn);
     const FusedPlan pl = choose_plan(nd);
     if (!pl.ok) return false;
@@ -650,7 +1102,9 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
     a.log_std = policy ? policy->d_log_std : nullptr;
     a.epsilon = epsilon; a.ent_coeff = ent_coeff;
     a.partials = nd->partials; a.slab = slab;
-    launch_fused(nd, pl, a);
+    const bool image_clean = nd->image && !nd->image_dirty && nd->image_floats == pl.net.img_floats;
+    const bool pdl = pdl_enabled() && pl.kind == 1 && !reduced_out;
+    launch_fused(nd, pl, a, pdl && chained && image_clean);
     nd->last_splits = blocks;
 
     ReduceAdamArgs r{};
@@ -670,7 +1124,7 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
     } else {
         nd->image_dirty = true;     // the caller updates the parameters with the generic Adam kernel
     }
-    B200_LAUNCH(fused_reduce_adam_kernel, div_up(slab, 32), 256, 0, r);
+    B200_LAUNCH_PDL(fused_reduce_adam_kernel, div_up(slab, 32), 32 * kRedWarps, 0, pdl, r);
     return true;
 }
 

@@ -117,7 +117,7 @@ bool fused_supported(NeuralNetwork* nn);
 void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out);
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
-                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out);
+                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained = false);
 
 // ---- policy.cu --------------------------------------------------------------------------------
 void launch_log_prob(const float* mu, const float* log_std, const float* action, float* out, int m, int A);

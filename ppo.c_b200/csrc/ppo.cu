@@ -174,7 +174,7 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
             if (fusedV) {
                 float* red = G > 1 ? static_cast<float*>(scratch(kScratchMisc, (ndV->param_count + 2) * sizeof(float))) : nullptr;
                 fused_minibatch_update(ppo->V, nullptr, ppo->adam_V, nullptr, ppo->lr_V, perm, k * batch_size + row0, limit,
-                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, red);
+                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, red, k > 0);
                 if (G > 1) {   // slab-reduce -> NCCL all-reduce -> Adam
                     dist_allreduce_sum(red, ndV->param_count + 2);
                     ppo->adam_V->time_step += 1;
@@ -210,7 +210,7 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
                 float* red = G > 1 ? static_cast<float*>(scratch(kScratchMisc, (ndP->param_count + A + 1) * sizeof(float))) : nullptr;
                 fused_minibatch_update(pol->mu, pol, ppo->adam_policy, ppo->adam_entropy, ppo->lr_policy, perm,
                                        k * batch_size + row0, limit, mb_local, mb_total, b, ppo->epsilon, ppo->ent_coeff,
-                                       t->d_scalars + 1, red);
+                                       t->d_scalars + 1, red, k > 0);
                 if (G > 1) {
                     if (ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
                     dist_allreduce_sum(red, ndP->param_count + A + 1);
