@@ -69,6 +69,7 @@ struct FusedArgs {
     int slab;
     int smem_g_off;            // offset of the two gradient buffers
     int smem_red_off;          // 64 floats of reduction scratch, TM ints of source rows, 1 mbarrier
+    unsigned long long* dbg;   // phase timestamps (PPO_B200_PHASE_DEBUG), [block][16]
 };
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
@@ -416,21 +417,31 @@ __global__ void __launch_bounds__(kFusedThreads, (TM == 64 && RT == 4) ? 2 : 1) 
 // ===================================================================================================
 // 64-wide tile kernel (every layer width <= 64: the reference's Pendulum / 2x64 nets).
 //
-// 128 threads, 64-row tiles, up to 3 CTAs per SM.  Compared with fused_update_kernel above:
-//   * 8 rows x 4 columns per thread in forward and dX: 3 conflict-free LDS.128 (= 3 shared-memory
-//     wavefronts) feed 32 FFMAs (the 4x4 tile needed 3 wavefronts per 16 -> the LSU pipe was 65% busy);
+// 256 threads = two groups of four warps working on one 64-row tile, two CTAs per SM (16 warps per SM).
+// Compared with fused_update_kernel above:
+//   * 8 rows x 4 columns per thread in forward and dX: 3 LDS.128 feed 32 FFMAs (the 4x4 tile needed 2 per 16;
+//     shared memory delivers 128 B/clk/SM, so floats-loaded-per-FFMA is what bounds an fp32 tile kernel);
+//   * the two groups split the WORK, not the tile: forward = split-K halves that meet through one
+//     exchange buffer; backward = group 0 computes dW_l/db_l while group 1 computes dX_l (independent given
+//     G_{l+1} and A_l), so the backward critical path is max(dW, dX) instead of their sum;
 //   * dX walks the reduction 4 j's at a time on the SAME k-major weight image (Wt rows padded to
-//     ldw = pad4(out)+4 floats so the four k-rows a warp touches sit in different banks): 12 LDS.128 per
-//     128 FFMAs instead of 5 loads per 16;
-//   * gradients are written IN PLACE over the activations they belong to (no separate G buffers), which
-//     is what makes 3 CTAs per SM fit;
-//   * skinny layers (out <= 8: value head, action mean) and the bias gradients have their own
-//     thread mappings instead of running a mostly-empty 64x64 tile.
-// Rows of a thread: {4tr..4tr+3} U {32+4tr..32+4tr+3}, tr = tid & 7; column group tc = tid >> 3.
+//     ldw = pad4(out)+4 floats so the four k-rows a warp touches sit in different banks);
+//   * skinny layers (out <= 8: value head, action mean) and the bias gradients have their own thread
+//     mappings instead of running a mostly-empty 64x64 tile.
+// Rows of a thread: {4tr..4tr+3} U {32+4tr..32+4tr+3}, tr = lt & 7; column group tc = lt >> 3 (lt = tid & 127).
 // ===================================================================================================
-constexpr int kT64Threads = 128;
+constexpr int kT64Threads = 256;
 constexpr int kT64TM = 64;
 constexpr int kT64TMP = 68;      // feature row stride in floats; 68 % 32 == 4 keeps feature-strided LDS.128 conflict-free
+constexpr int kT64Ebuf = 64 * kT64TMP;
+
+__device__ __forceinline__ void t64_stamp(const FusedArgs& p, int slot) {
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.dbg[(size_t)blockIdx.x * 16 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void t64_load8(const float* base, float (&a)[8]) {
     const float4 a0 = *reinterpret_cast<const float4*>(base);
@@ -442,50 +453,101 @@ __device__ __forceinline__ void t64_store8(float* base, const float (&a)[8]) {
     *reinterpret_cast<float4*>(base + 32) = make_float4(a[4], a[5], a[6], a[7]);
 }
 
-// Yt[j][r] = act(sum_k Xt[k][r] * Wt[k][j] + b[j]),  n_out in (8, 64]
+// Yt[j][r] = act(sum_k Xt[k][r] * Wt[k][j] + b[j]),  n_out in (8, 64].
+// n_in >= 16: split-K.  Both groups accumulate the full 8x4 tile of (tr, tc) over their half of k; then group 0
+//   finalises the tile's first row quad and group 1 the second: each thread passes the quad it does not
+//   finalise through `xch` ([64][TMP]) and adds (lower-k partial) + (upper-k partial) for its own quad, so
+//   the activation epilogue is spread over all 256 threads.
+// n_in < 16: no split; group g simply computes its own row quad (4x4 tile) over all of k.
+// Contains one __syncthreads.
 __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
-                                            const float* __restrict__ bias, float* __restrict__ Yt, int n_in, int n_out, int act) {
-    const int tr = threadIdx.x & 7, tc = threadIdx.x >> 3;
-    if (4 * tc >= pad4(n_out)) return;
-    float acc[8][4];
-    {
+                                            const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ xch,
+                                            int n_in, int n_out, int act, int lt, int g) {
+    const int tr = lt & 7, tc = lt >> 3;
+    const bool live = 4 * tc < pad4(n_out);
+    const bool split = n_in >= 16;
+    float mine[4][4];                       // [row of my quad][col]
+    if (split) {
+        const int kh = (n_in + 1) >> 1;
+        const int k0 = g ? kh : 0, k1 = g ? n_in : kh;
+        float acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+        if (live) {
+            const float* xp = Xt + 4 * tr;
+            const float* wp = Wt + 4 * tc;
+#pragma unroll 2
+            for (int k = k0; k < k1; k++) {
+                float a[8];
+                t64_load8(xp + k * kT64TMP, a);
+                const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
+                const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
+            }
+            // pass the other group's quad: group 0 sends rows 32+4tr.. (acc[4..7]), group 1 sends rows 4tr.. (acc[0..3])
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float* dst = xch + (4 * tc + c) * kT64TMP + 4 * tr + (g ? 0 : 32);
+                *reinterpret_cast<float4*>(dst) = g ? make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c])
+                                                    : make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) mine[r][c] = g ? acc[4 + r][c] : acc[r][c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) mine[r][c] = 0.f;
+        if (live) {
+            const float* xp = Xt + 4 * tr + 32 * g;
+            const float* wp = Wt + 4 * tc;
+            for (int k = 0; k < n_in; k++) {
+                const float4 a = *reinterpret_cast<const float4*>(xp + k * kT64TMP);
+                const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
+                const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) mine[r][c] = fmaf(av[r], wv[c], mine[r][c]);
+            }
+        }
+    }
+    __syncthreads();
+    if (live) {
         const float4 b = *reinterpret_cast<const float4*>(bias + 4 * tc);     // bias block is zero-padded to pad4
         const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int c = 0; c < 4; c++) {
+            float o[4] = {mine[0][c], mine[1][c], mine[2][c], mine[3][c]};
+            if (split) {
+                const float4 q = *reinterpret_cast<const float4*>(xch + (4 * tc + c) * kT64TMP + 4 * tr + 32 * g);
+                const float qv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = bv[c];
-    }
-    const float* xp = Xt + 4 * tr;
-    const float* wp = Wt + 4 * tc;
-#pragma unroll 4
-    for (int k = 0; k < n_in; k++) {
-        float a[8];
-        t64_load8(xp + k * kT64TMP, a);
-        const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
-        const float wv[4] = {w.x, w.y, w.z, w.w};
+                for (int r = 0; r < 4; r++) o[r] = g ? qv[r] + o[r] : o[r] + qv[r];     // lower-k partial + upper-k partial
+            }
 #pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        float o[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) o[r] = act_apply(acc[r][c], act);
-        t64_store8(Yt + (4 * tc + c) * kT64TMP + 4 * tr, o);
+            for (int r = 0; r < 4; r++) o[r] = act_apply(o[r] + bv[c], act);
+            *reinterpret_cast<float4*>(Yt + (4 * tc + c) * kT64TMP + 4 * tr + 32 * g) = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
-// Skinny forward, n_out <= 8: thread = (row, k-half); the two halves meet through `scratch` (>= 8*64 floats).
+// Skinny forward, n_out <= 8: thread = (row, k-quarter); the quarters meet through `scratch` (>= 3*8*64 floats).
 // Contains one __syncthreads: every thread of the CTA must call it.
 __device__ __forceinline__ void t64_forward_skinny(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
                                                    const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ scratch,
                                                    int n_in, int n_out, int act) {
-    const int r = threadIdx.x & 63, h = threadIdx.x >> 6;
-    const int kh = (n_in + 1) >> 1;
-    const int k0 = h ? kh : 0, k1 = h ? n_in : kh;
+    const int r = threadIdx.x & 63, h = threadIdx.x >> 6;      // h = 0..3
+    const int kq = (n_in + 3) >> 2;
+    const int k0 = min(n_in, h * kq), k1 = min(n_in, k0 + kq);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
@@ -500,23 +562,28 @@ __device__ __forceinline__ void t64_forward_skinny(const float* __restrict__ Xt,
     }
     if (h) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) if (j < n_out) scratch[j * 64 + r] = acc[j];
+        for (int j = 0; j < 8; j++) if (j < n_out) scratch[((h - 1) * 8 + j) * 64 + r] = acc[j];
     }
     __syncthreads();
     if (!h) {
         const int out_pad = pad4(n_out);
 #pragma unroll
         for (int j = 0; j < 8; j++)
-            if (j < out_pad) Yt[j * kT64TMP + r] = (j < n_out) ? act_apply(acc[j] + scratch[j * 64 + r] + bias[j], act) : 0.f;
+            if (j < out_pad) {
+                const float s = ((acc[j] + scratch[j * 64 + r]) + scratch[(8 + j) * 64 + r]) + scratch[(16 + j) * 64 + r];
+                Yt[j * kT64TMP + r] = (j < n_out) ? act_apply(s + bias[j], act) : 0.f;
+            }
     }
 }
 
-// In place: Ht[k][r] <- (sum_j Gt[j][r] * Wt[k][j]) * act'(Ht[k][r]);  k = tc + 16c (interleaved so the four
-// Wt rows a warp reads per load are consecutive -> different banks).  Gt rows [n_out, pad4(n_out)) are zero.
+// Gout[k][r] = (sum_j Gt[j][r] * Wt[k][j]) * act'(Ht[k][r]);  k = tc + 16c (interleaved so the four Wt rows a
+// warp reads per load are consecutive -> different banks).  Gt rows [n_out, pad4(n_out)) are zero.
+// Rows [n_in, pad4(n_in)) of Gout are zero-filled (they are read as padding by the next dX).
 __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt, const float* __restrict__ Wt, int ldw,
-                                                   float* __restrict__ Ht, int n_in, int n_out, int act_prev) {
-    const int tr = threadIdx.x & 7, tc = threadIdx.x >> 3;
-    if (tc >= n_in) return;
+                                                   const float* __restrict__ Ht, float* __restrict__ Gout, int n_in, int n_out,
+                                                   int act_prev, int lt) {
+    const int tr = lt & 7, tc = lt >> 3;
+    if (tc >= pad4(n_in)) return;
     float acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; r++)
@@ -548,21 +615,21 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const int k = tc + 16 * c;
-        if (k >= n_in) continue;
+        if (k >= pad4(n_in)) continue;
         float h[8], o[8];
         t64_load8(Ht + k * kT64TMP + 4 * tr, h);
 #pragma unroll
-        for (int r = 0; r < 8; r++) o[r] = act_grad(h[r], acc[r][c], act_prev);
-        t64_store8(Ht + k * kT64TMP + 4 * tr, o);
+        for (int r = 0; r < 8; r++) o[r] = (k < n_in) ? act_grad(h[r], acc[r][c], act_prev) : 0.f;
+        t64_store8(Gout + k * kT64TMP + 4 * tr, o);
     }
 }
 
-// gW[j][k] = sum_r Gt[j][r] * Xt[k][r];  j = tj + 16a (tj = tid >> 3), k = tk + 8b (tk = tid & 7): the 4 G rows
-// and 8 X rows a warp loads per instruction are consecutive features -> one wavefront each.
+// gW[j][k] = sum_r Gt[j][r] * Xt[k][r];  j = tj + 16a (tj = lt >> 3), k = tk + 8b (tk = lt & 7): the 4 G rows
+// and 8 X rows a warp loads per instruction are consecutive features.
 template <int JJ, int KK>
 __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                     float* __restrict__ gW, int n_in, int n_out) {
-    const int tk = threadIdx.x & 7, tj = threadIdx.x >> 3;
+                                                     float* __restrict__ gW, int n_in, int n_out, int lt) {
+    const int tk = lt & 7, tj = lt >> 3;
     if ((tj & ~3) >= n_out) return;          // warp-uniform: this warp owns no valid output row
     float acc[JJ][KK];
 #pragma unroll
@@ -574,7 +641,7 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
     for (int a = 0; a < JJ; a++) jrow[a] = min(tj + 16 * a, n_out - 1) * kT64TMP;
 #pragma unroll
     for (int b = 0; b < KK; b++) krow[b] = min(tk + 8 * b, n_in - 1) * kT64TMP;
-#pragma unroll 2
+#pragma unroll 1
     for (int r = 0; r < kT64TM; r += 4) {
         float4 g[JJ], x[KK];
 #pragma unroll
@@ -603,18 +670,53 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
     }
 }
 
-__device__ __forceinline__ void t64_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out) {
-    const int jj = (n_out + 15) / 16, kk = (n_in + 7) / 8;
-#define B200_DW(J, K) t64_backward_weights<J, K>(Gt, Xt, gW, n_in, n_out)
-#define B200_DWK(J) do { if (kk <= 1) B200_DW(J, 1); else if (kk <= 2) B200_DW(J, 2); else if (kk <= 4) B200_DW(J, 4); else B200_DW(J, 8); } while (0)
-    if (jj <= 1) B200_DWK(1); else if (jj <= 2) B200_DWK(2); else B200_DWK(4);
-#undef B200_DWK
-#undef B200_DW
+// Skinny dW.  WIDE_IS_K = true : n_out <= 8 (value head / action mean): thread = (k, row half), acc[j]
+//            WIDE_IS_K = false: n_in  <= 8 (first layer of a low-dimensional env): thread = (j, row half), acc[k]
+// The two row halves meet through one shuffle; sums run in a fixed order.
+template <bool WIDE_IS_K>
+__device__ __forceinline__ void t64_backward_weights_skinny(const float* __restrict__ Gt, const float* __restrict__ Xt,
+                                                            float* __restrict__ gW, int n_in, int n_out, int lt) {
+    const int wide = lt >> 1, h = lt & 1;
+    const int n_wide = WIDE_IS_K ? n_in : n_out, n_small = WIDE_IS_K ? n_out : n_in;
+    const float* wide_base = (WIDE_IS_K ? Xt : Gt) + min(wide, n_wide - 1) * kT64TMP + 32 * h;
+    const float* small_base = (WIDE_IS_K ? Gt : Xt) + 32 * h;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < 8; i++) {
+        const float4 w = *reinterpret_cast<const float4*>(wide_base + 4 * i);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (q < n_small) {
+                const float4 sv = *reinterpret_cast<const float4*>(small_base + q * kT64TMP + 4 * i);
+                acc[q] = fmaf(w.x, sv.x, acc[q]); acc[q] = fmaf(w.y, sv.y, acc[q]);
+                acc[q] = fmaf(w.z, sv.z, acc[q]); acc[q] = fmaf(w.w, sv.w, acc[q]);
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] += __shfl_xor_sync(kFull, acc[q], 1);
+    if (h == 0 && wide < n_wide) {
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (q < n_small) {
+                if (WIDE_IS_K) gW[(size_t)q * n_in + wide] = acc[q];
+                else gW[(size_t)wide * n_in + q] = acc[q];
+            }
+    }
+}
+
+__device__ __forceinline__ void t64_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out, int lt) {
+    // few tile shapes only (instruction-cache footprint)
+    if (n_out <= 8) t64_backward_weights_skinny<true>(Gt, Xt, gW, n_in, n_out, lt);
+    else if (n_in <= 8) t64_backward_weights_skinny<false>(Gt, Xt, gW, n_in, n_out, lt);
+    else if (n_out <= 16) t64_backward_weights<1, 8>(Gt, Xt, gW, n_in, n_out, lt);
+    else t64_backward_weights<4, 8>(Gt, Xt, gW, n_in, n_out, lt);
 }
 
 // gb[j] = sum_r Gt[j][r]: thread = (j, row half), fixed-order sums
-__device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out) {
-    const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
+__device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out, int lt) {
+    const int j = lt >> 1, h = lt & 1;
     float s = 0.f;
     if (j < n_out) {
         const float* gp = Gt + j * kT64TMP + 32 * h;
@@ -628,11 +730,11 @@ __device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, floa
     if (h == 0 && j < n_out) gb[j] = s;
 }
 
-__global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const FusedArgs p) {
+__global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const FusedArgs p) {
     constexpr int TM = kT64TM, TMP = kT64TMP;
     extern __shared__ __align__(128) float smem[];
     const FusedNet& net = p.net;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lt = tid & 127, grp = tid >> 7;
     const int row0 = blockIdx.x * TM;
     const int S = net.sizes[0], OUT = net.sizes[net.L];
     float* img = smem;
@@ -640,8 +742,10 @@ __global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const Fuse
     float* red = smem + p.smem_red_off;                  // 64 floats
     int* src_rows = reinterpret_cast<int*>(red + 64);    // TM ints
     uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64 + TM);
-    float* scratch = smem + p.smem_g_off;                // 8 * 64 floats (skinny forward halves)
+    float* ebuf = smem + p.smem_g_off;                   // E0 | E1: forward exchange / out-of-place dX ping-pong
+    float* scratch = ebuf;                               // skinny forward: 3*8*64 floats (aliases E0)
 
+    t64_stamp(p, 0);
     if (tid == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -678,7 +782,9 @@ __global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const Fuse
     }
     // Everything above reads only rollout data and the permutation.  The weight image is written by the
     // previous minibatch's Adam kernel: under programmatic dependent launch this is where we wait for it.
+    t64_stamp(p, 1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    t64_stamp(p, 2);
     if (tid == 0) {
         mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
         tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
@@ -686,6 +792,7 @@ __global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const Fuse
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     mbar_wait(mbar, 0);
     __syncthreads();
+    t64_stamp(p, 3);
     // ---- forward
     for (int l = 0; l < net.L; l++) {
         const float* Xt = act0 + net.a_off[l];
@@ -693,8 +800,9 @@ __global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const Fuse
         if (net.sizes[l + 1] <= 8)
             t64_forward_skinny(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, scratch, net.sizes[l], net.sizes[l + 1], net.acts[l]);
         else
-            t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, net.sizes[l], net.sizes[l + 1], net.acts[l]);
+            t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp);
         __syncthreads();
+        t64_stamp(p, 4 + l);
     }
     float* Yt = act0 + net.a_off[net.L];
     if (p.mode == kFusedForward) {
@@ -747,33 +855,36 @@ __global__ void __launch_bounds__(kT64Threads, 3) fused_tile64_kernel(const Fuse
             for (int j = 0; j < 8; j++)
                 if (j < OUT) Yt[j * TMP + tid] = act_grad(yv[j], gout[j], out_act);
         }
-        const int warp = tid >> 5, lane = tid & 31;       // warps 0..1 hold data, the others contribute zeros
-        float v = warp_sum(loss_term);
-        if (lane == 0) red[warp] = v;
-        if (p.mode == kFusedPolicy) {
+        if (tid < 64) {                                    // warps 0..1 hold the data
+            const int warp = tid >> 5, lane = tid & 31;
+            const float v = warp_sum(loss_term);
+            if (lane == 0) red[warp] = v;
+            if (p.mode == kFusedPolicy) {
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (j < OUT) { const float s = warp_sum(gls[j]); if (lane == 0) red[8 + j * 4 + warp] = s; }
+                for (int j = 0; j < 8; j++)
+                    if (j < OUT) { const float s = warp_sum(gls[j]); if (lane == 0) red[8 + j * 2 + warp] = s; }
+            }
         }
         __syncthreads();
-        if (tid == 0) slab[net.P + OUT] = (red[0] + red[1]) + (red[2] + red[3]);
-        if (p.mode == kFusedPolicy && tid < OUT) {
-            const float* q = red + 8 + tid * 4;
-            slab[net.P + tid] = (q[0] + q[1]) + (q[2] + q[3]);
-        }
+        if (tid == 0) slab[net.P + OUT] = red[0] + red[1];
+        if (p.mode == kFusedPolicy && tid < OUT) slab[net.P + tid] = red[8 + tid * 2] + red[8 + tid * 2 + 1];
     }
-    // ---- backward: G_{l+1} lives in the slot of A_{l+1}; dX overwrites A_l in place
+    t64_stamp(p, 9);
+    // ---- backward: group 0 -> dW_l, db_l; group 1 -> dX_l into the ping-pong buffer (both read G_{l+1}, A_l)
+    const float* G = Yt;
     for (int l = net.L - 1; l >= 0; l--) {
         const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
-        float* Xt = act0 + net.a_off[l];
-        const float* G = act0 + net.a_off[l + 1];
-        t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out);
-        t64_bias_grad(G, slab + net.b_off[l], n_out);
-        if (l > 0) {
-            __syncthreads();                       // every reader of A_l's forward values is done
-            t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, n_in, n_out, net.acts[l - 1]);
-            __syncthreads();
+        const float* Xt = act0 + net.a_off[l];
+        float* Gout = ebuf + ((net.L - 1 - l) & 1) * kT64Ebuf;
+        if (grp == 0) {
+            t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt);
+            t64_bias_grad(G, slab + net.b_off[l], n_out, lt);
+        } else if (l > 0) {
+            t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt);
         }
+        if (l > 0) __syncthreads();
+        t64_stamp(p, 10 + l);
+        G = Gout;
     }
 }
 
@@ -976,8 +1087,8 @@ static FusedPlan make_plan64(NetDev* nd) {
     }
     n.max_width_pad = maxw;
     off += n.img_floats;
-    pl.g_off = off;            // skinny-forward scratch: 8 x 64 floats
-    off += 8 * 64;
+    pl.g_off = off;            // E0 | E1: forward split-K exchange, out-of-place dX ping-pong, skinny-forward scratch
+    off += 2 * kT64Ebuf;
     pl.red_off = off;
     off += 64 + kT64TM + 4;
     pl.smem_bytes = (size_t)off * sizeof(float);
@@ -1017,7 +1128,16 @@ static float* ensure_image(NetDev* nd, const FusedPlan& pl) {
     return nd->image;
 }
 
+static unsigned long long* g_phase_dbg = nullptr;
+static unsigned long long* phase_dbg() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("PPO_B200_PHASE_DEBUG"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (on && !g_phase_dbg) { g_phase_dbg = dmalloc<unsigned long long>(16 * 65536); CUDA_CHECK(cudaMemset(g_phase_dbg, 0, 16 * 65536 * 8)); }
+    return g_phase_dbg;
+}
+
 static void launch_fused(NetDev* nd, const FusedPlan& pl, FusedArgs& a, bool pdl = false) {
+    a.dbg = (a.mode != kFusedForward) ? phase_dbg() : nullptr;
     a.net = pl.net;
     a.image = ensure_image(nd, pl);
     a.smem_g_off = pl.g_off;
@@ -1129,3 +1249,10 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
 }
 
 }  // namespace b200
+
+// debug: copy the phase timestamps of the last fused_tile64_kernel launch ([blocks][16] u64) to the host
+extern "C" void ppo_b200_debug_phase_stamps(unsigned long long* out, int blocks) {
+    if (!b200::g_phase_dbg) return;
+    CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    CUDA_CHECK(cudaMemcpy(out, b200::g_phase_dbg, (size_t)blocks * 16 * 8, cudaMemcpyDeviceToHost));
+}
