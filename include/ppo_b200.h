@@ -409,8 +409,14 @@ void ppo_b200_set_matmul_precision(int mode);
  * (aux = post-activation input), 2 backward-weights (out = `splits` slabs of l*n floats). */
 void ppo_b200_tc_linear(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l,
                         int act, int splits);
-/* Running observation normalisation (new; Welford merge of include/welford_var.h:33-40): 0 = off. */
+/* Running observation normalisation for the device rollout (new capability; the reference only has the
+ * Welford merge, include/welford_var.h:33-40,58-66, applied to advantages).  The rollout kernel keeps a
+ * Welford triple of the RAW observations per lane, merges them per CTA, and a one-thread-per-feature kernel
+ * folds the CTA triples into a running float64 state in fixed order.  Rollout i feeds the policy / value
+ * nets and fills the buffer with (obs - mean) / (std + 1e-8) using the statistics of rollouts < i (identity
+ * for the first).  Needs a device env (create it first) and a policy net the 64-wide kernels support. */
 void ppo_b200_set_obs_norm(PPO* ppo, int enabled);
+void ppo_b200_get_obs_norm(const Env* env, float* mean3, float* std3, double* count);
 /* mean undiscounted return per episode of the last device rollout (eval_ppo's "R", src/ppo.cu:581) */
 float ppo_b200_last_mean_return(PPO* ppo);
 float ppo_b200_last_value_loss(PPO* ppo);

@@ -63,6 +63,7 @@ EXTENSION_API = {
     "ppo_b200_train_iterations": (None, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ppo_b200_set_permutation_mode": (None, [vp, C.c_int, C.c_ulonglong]),
     "ppo_b200_set_obs_norm": (None, [vp, C.c_int]),
+    "ppo_b200_get_obs_norm": (None, [vp, vp, vp, vp]),
     "ppo_b200_set_kernel_path": (None, [C.c_int]),
     "ppo_b200_set_matmul_precision": (None, [C.c_int]),
     "ppo_b200_tc_linear": (None, [C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

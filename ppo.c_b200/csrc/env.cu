@@ -131,6 +131,13 @@ struct DeviceEnv {
     int host_steps;
     float* d_ret_sum;              // [n_envs] sum of rewards of finished episodes
     int* d_ret_cnt;                // [n_envs]
+    // running observation normalisation (new capability; merge formula of include/welford_var.h:33-40,58-66)
+    bool obs_norm;
+    double* d_obs_stat;            // [3 features][mean, M2, n] running Welford state (float64)
+    float* d_obs_mean;             // [3]
+    float* d_obs_inv_std;          // [3]  1 / (std + 1e-8)
+    float* d_obs_partial;          // [CTAs][3][mean, M2, n] per-CTA Welford triples of the last rollout
+    int obs_partial_cap;
 };
 constexpr unsigned long long kDeviceEnvMagic = 0xB200E17Full;
 static DeviceEnv* g_device_env = nullptr;
@@ -140,6 +147,19 @@ DeviceEnv* as_device_env(Env* env) {
     return (g_device_env == e && e && e->magic == kDeviceEnvMagic) ? e : nullptr;
 }
 int device_env_count(DeviceEnv* e) { return e->n_envs; }
+void device_env_reset_obs_norm(DeviceEnv* e) {
+    const float one[3] = {1.f, 1.f, 1.f};
+    CUDA_CHECK(cudaMemsetAsync(e->d_obs_stat, 0, 9 * sizeof(double), stream()));
+    CUDA_CHECK(cudaMemsetAsync(e->d_obs_mean, 0, 3 * sizeof(float), stream()));
+    CUDA_CHECK(cudaMemcpyAsync(e->d_obs_inv_std, one, sizeof(one), cudaMemcpyHostToDevice, stream()));
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+void device_env_set_obs_norm(bool enabled) {
+    if (!g_device_env) B200_FATAL("ppo_b200_set_obs_norm: create the device env first (create_pendulum_env_cuda)");
+    if (enabled && !g_device_env->obs_norm) device_env_reset_obs_norm(g_device_env);
+    g_device_env->obs_norm = enabled;
+}
+
 
 constexpr int kRollE = 32;        // envs per CTA (one per lane)
 constexpr int kRollWarps = 4;
@@ -255,6 +275,230 @@ rollout_kernel(const RolloutArgs p) {
     }
 }
 
+
+// ================================ 64-wide fused rollout ===============================================
+// Same contract as rollout_kernel, for nets the 64-wide tile kernels support (all widths <= 64): the weight
+// image [Wt_l | biases] maintained by the Adam kernel is staged once per CTA; per step each thread owns a
+// 4 envs x 4 units register tile of the hidden layers (2 LDS.128 per 16 FFMAs instead of 1 scalar load per
+// FFMA), the action-mean layer is split over the four warps, and warp 0 (lane = env) samples, steps the
+// env in float64 and writes the env-major buffer row.  sincos(theta) is computed once per step and shared
+// by the observation and the next step's dynamics.
+constexpr int kR64E = 32;
+constexpr int kR64Threads = 128;
+
+struct Rollout64Args {
+    FusedNet net;
+    const float* image;
+    const float* log_std;
+    int n_envs, T;
+    unsigned long long seed, rollout;
+    float *state, *next_state, *action, *reward, *logprob;
+    unsigned char *terminated, *truncated;
+    const float* obs_mean;        // null: no observation normalisation
+    const float* obs_inv_std;
+    float* ret_sum;
+    int* ret_cnt;
+    float* obs_partial;           // [blocks][3][3] Welford triples of the RAW observations, may be null
+    int horizon;
+};
+
+__device__ __forceinline__ void welford_merge(float& mean, float& m2, float& n, float mb, float m2b, float nb) {
+    if (nb <= 0.f) return;
+    const float nn = n + nb, delta = mb - mean;          // include/welford_var.h:33-40
+    mean += delta * nb / nn;
+    m2 += m2b + delta * delta * n * nb / nn;
+    n = nn;
+}
+
+__global__ void __launch_bounds__(kR64Threads) rollout64_kernel(const Rollout64Args p) {
+    constexpr int E = kR64E;
+    extern __shared__ __align__(16) float smem[];
+    const FusedNet& net = p.net;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* img = smem;
+    float* hA = img + net.img_floats;       // [64][E]: feature-major, one column per env
+    float* hB = hA + 64 * E;
+    float* part = hB + 64 * E;              // [4][8][E] partial action means
+    for (int i = tid * 4; i < net.img_floats; i += kR64Threads * 4)
+        *reinterpret_cast<float4*>(img + i) = *reinterpret_cast<const float4*>(p.image + i);
+    const int L = net.L, A = net.sizes[L];
+    const int env = blockIdx.x * E + lane;
+    const bool live = env < p.n_envs;
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    double th = 0.0, thd = 0.0, sn = 0.0, cs = 1.0;
+    int ep_steps = 0, episode = 0, ret_cnt = 0;
+    float ep_ret = 0.f, ret_sum = 0.f;
+    float wmean[3] = {0.f, 0.f, 0.f}, wm2[3] = {0.f, 0.f, 0.f}, wn = 0.f;
+    float om[3] = {0.f, 0.f, 0.f}, oi[3] = {1.f, 1.f, 1.f};
+    if (p.obs_mean) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { om[k] = p.obs_mean[k]; oi[k] = p.obs_inv_std[k]; }
+    }
+    auto reset = [&]() {   // theta ~ U(-pi,pi), theta_dot ~ U(-1,1)  (gymnasium reset)
+        const uint4 r = philox4x32(make_uint4((uint32_t)env, (uint32_t)episode, (uint32_t)p.rollout, 0xFFFFFFFFu), key);
+        th = (2.0 * (double)u01_open(r.x) - 1.0) * kPiD;
+        thd = 2.0 * (double)u01_open(r.y) - 1.0;
+        sincos(th, &sn, &cs);
+        ep_steps = 0;
+        ep_ret = 0.f;
+    };
+    if (warp == 0 && live) reset();         // src/ppo.cu:55: every collect starts with a reset
+    // zero the padding row of the input tile once (the first layer reads pad4(S) = 4 feature rows)
+    if (tid < E) hA[3 * E + tid] = 0.f;
+    __syncthreads();
+
+    const int eg = tid & 7, ug = tid >> 3;  // 4 envs x 4 units per thread
+    for (int t = 0; t < p.T; t++) {
+        const size_t row = (size_t)env * p.T + t;   // env-major flat index
+        if (warp == 0) {
+            const float raw[3] = {(float)cs, (float)sn, (float)thd};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float x = live ? (raw[k] - om[k]) * oi[k] : 0.f;
+                hA[k * E + lane] = x;
+                if (live) p.state[row * 3 + k] = x;
+            }
+            if (live) {                     // Welford update with the raw observation
+                wn += 1.f;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const float d = raw[k] - wmean[k]; wmean[k] += d / wn; wm2[k] += d * (raw[k] - wmean[k]); }
+            }
+        }
+        __syncthreads();
+        // ---- hidden layers: hin -> hout, 4x4 register tiles
+        float* hin = hA;
+        float* hout = hB;
+        for (int l = 0; l < L - 1; l++) {
+            const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
+            if (4 * ug < pad4(n_out)) {
+                const float* wp = img + net.wt_off[l] + 4 * ug;
+                const int ldw = net.ldw[l];
+                const float4 b = *reinterpret_cast<const float4*>(img + net.bs_off[l] + 4 * ug);
+                float acc[4][4];
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[c][e] = bv[c];
+                const float* xp = hin + 4 * eg;
+#pragma unroll 4
+                for (int k = 0; k < n_in; k++) {
+                    const float4 a = *reinterpret_cast<const float4*>(xp + k * E);
+                    const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
+                    const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc[c][e] = fmaf(av[e], wv[c], acc[c][e]);
+                }
+                const int act = net.acts[l];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    *reinterpret_cast<float4*>(hout + (4 * ug + c) * E + 4 * eg) =
+                        make_float4(act_apply(acc[c][0], act), act_apply(acc[c][1], act), act_apply(acc[c][2], act), act_apply(acc[c][3], act));
+            }
+            __syncthreads();
+            float* tmp = hin; hin = hout; hout = tmp;
+        }
+        // ---- action-mean layer (A <= 8): each warp takes a quarter of k, lane = env
+        {
+            const int n_in = net.sizes[L - 1];
+            const int kq = (n_in + 3) >> 2;
+            const int k0 = min(n_in, warp * kq), k1 = min(n_in, k0 + kq);
+            const float* wt = img + net.wt_off[L - 1];
+            const int ldw = net.ldw[L - 1];
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = 0.f;
+            for (int k = k0; k < k1; k++) {
+                const float x = hin[k * E + lane];
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (j < A) acc[j] = fmaf(x, wt[k * ldw + j], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (j < A) part[(warp * 8 + j) * E + lane] = acc[j];
+        }
+        __syncthreads();
+        // ---- sample, log-prob, env step (A == 1 for Pendulum), buffer write
+        if (warp == 0 && live) {
+            float mu = ((part[lane] + part[8 * E + lane]) + part[16 * E + lane]) + part[24 * E + lane] + img[net.bs_off[L - 1]];
+            mu = act_apply(mu, net.acts[L - 1]);
+            const uint4 r = philox4x32(make_uint4((uint32_t)env, (uint32_t)t, (uint32_t)p.rollout, 0u), key);
+            const float z = sqrtf(-2.f * logf(u01_open(r.x))) * cosf(6.283185307179586f * u01_open(r.y));
+            const float ls = p.log_std[0];
+            const float a = mu + z * expf(ls);                       // src/policy.cu:85
+            const float lp = log_prob_dev(&mu, &ls, &a, 1);
+            // gymnasium PendulumEnv.step (same arithmetic as pendulum_step above, sin(theta) reused from the observation)
+            double u = a;
+            u = u > 2.0 ? 2.0 : (u < -2.0 ? -2.0 : u);
+            const double an = angle_normalize(th);
+            const double cost = an * an + 0.1 * thd * thd + 0.001 * u * u;
+            double nthd = thd + (3 * 10.0 / (2 * 1.0) * sn + 3.0 / (1.0 * 1.0 * 1.0) * u) * 0.05;
+            nthd = nthd > 8.0 ? 8.0 : (nthd < -8.0 ? -8.0 : nthd);
+            th = th + nthd * 0.05;
+            thd = nthd;
+            sincos(th, &sn, &cs);
+            const float rew = (float)(-cost);
+            ep_steps++;
+            ep_ret += rew;
+            bool trunc = ep_steps >= p.horizon;                       // TimeLimit(200)
+            p.action[row] = a;
+            p.logprob[row] = lp;
+            p.reward[row] = rew;
+            p.next_state[row * 3 + 0] = ((float)cs - om[0]) * oi[0];
+            p.next_state[row * 3 + 1] = ((float)sn - om[1]) * oi[1];
+            p.next_state[row * 3 + 2] = ((float)thd - om[2]) * oi[2];
+            if (trunc) { ret_sum += ep_ret; ret_cnt++; episode++; }
+            if (t == p.T - 1) trunc = true;                           // src/ppo.cu:70-74
+            p.terminated[row] = 0;
+            p.truncated[row] = trunc ? 1 : 0;
+            if (trunc && t < p.T - 1) reset();                        // src/ppo.cu:64-66
+        }
+        // no barrier needed here: the next writers of hA (warp 0, rows 0..2) only race with readers of the
+        // action-mean layer, which all passed the barrier above
+    }
+    if (warp == 0) {
+        if (live) { p.ret_sum[env] = ret_sum; p.ret_cnt[env] = ret_cnt; }
+        if (p.obs_partial) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float mean = wmean[k], m2 = wm2[k], n = wn;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {       // fixed butterfly order -> deterministic
+                    const float mb = __shfl_xor_sync(kFull, mean, o), m2b = __shfl_xor_sync(kFull, m2, o), nb = __shfl_xor_sync(kFull, n, o);
+                    if ((lane & o) == 0) welford_merge(mean, m2, n, mb, m2b, nb);
+                    else { float ma = mb, m2a = m2b, na = nb; welford_merge(ma, m2a, na, mean, m2, n); mean = ma; m2 = m2a; n = na; }
+                }
+                if (lane == 0) {
+                    float* o3 = p.obs_partial + ((size_t)blockIdx.x * 3 + k) * 3;
+                    o3[0] = mean; o3[1] = m2; o3[2] = n;
+                }
+            }
+        }
+    }
+}
+
+// Fold the per-CTA triples of one rollout into the running float64 state (fixed order) and refresh mean / 1/(std+eps).
+__global__ void obs_stats_merge_kernel(const float* __restrict__ partial, int blocks, double* __restrict__ stat,
+                                       float* __restrict__ mean_out, float* __restrict__ inv_std_out) {
+    const int k = threadIdx.x;
+    if (k >= 3) return;
+    double mean = stat[k * 3], m2 = stat[k * 3 + 1], n = stat[k * 3 + 2];
+    for (int b = 0; b < blocks; b++) {
+        const float* q = partial + ((size_t)b * 3 + k) * 3;
+        const double mb = q[0], m2b = q[1], nb = q[2];
+        if (nb > 0.0) {
+            const double delta = mb - mean, nn = n + nb;
+            mean += delta * nb / nn;
+            m2 += m2b + delta * delta * n * nb / nn;
+            n = nn;
+        }
+    }
+    stat[k * 3] = mean; stat[k * 3 + 1] = m2; stat[k * 3 + 2] = n;
+    mean_out[k] = (float)mean;
+    inv_std_out[k] = (float)(1.0 / (sqrt(n > 0.0 ? m2 / n : 1.0) + 1e-8));
+}
+
 // fixed-order reduction of the per-env episode returns -> {sum of returns, episodes}
 __global__ void __launch_bounds__(1024) return_stats_kernel(const float* ret_sum, const int* ret_cnt, int n, float* out) {
     __shared__ double s_sum[1024];
@@ -275,6 +519,42 @@ void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buff
                     const float* obs_mean, const float* obs_inv_std, float* return_stats) {
     if (policy->state_size != 3 || policy->action_size != 1) B200_FATAL("device Pendulum needs state_size 3 / action_size 1");
     if ((long long)e->n_envs * T > buffer->capacity) B200_FATAL("buffer capacity %d < n_envs*T = %lld", buffer->capacity, (long long)e->n_envs * T);
+    (void)obs_mean; (void)obs_inv_std;
+    static int use64 = -1;
+    if (use64 < 0) { const char* v = getenv("PPO_B200_ROLLOUT"); use64 = (v && strcmp(v, "old") == 0) ? 0 : 1; }
+    Rollout64Args r{};
+    if (use64 && fused_image64(policy->mu, &r.net, &r.image)) {
+        const int blocks = div_up(e->n_envs, kR64E);
+        if (e->obs_norm && blocks > e->obs_partial_cap) {
+            CUDA_CHECK(cudaStreamSynchronize(stream()));
+            if (e->d_obs_partial) CUDA_CHECK(cudaFree(e->d_obs_partial));
+            e->d_obs_partial = dmalloc<float>((size_t)blocks * 9);
+            e->obs_partial_cap = blocks;
+        }
+        r.log_std = policy->d_log_std;
+        r.n_envs = e->n_envs; r.T = T;
+        r.seed = e->seed; r.rollout = e->rollouts++;
+        r.state = buffer->d_state_p; r.next_state = buffer->d_next_state_p; r.action = buffer->d_action_p;
+        r.reward = buffer->d_reward_p; r.logprob = buffer->d_logprob_p;
+        r.terminated = reinterpret_cast<unsigned char*>(buffer->d_terminated_p);
+        r.truncated = reinterpret_cast<unsigned char*>(buffer->d_truncated_p);
+        r.obs_mean = e->obs_norm ? e->d_obs_mean : nullptr;
+        r.obs_inv_std = e->obs_norm ? e->d_obs_inv_std : nullptr;
+        r.ret_sum = e->d_ret_sum; r.ret_cnt = e->d_ret_cnt;
+        r.obs_partial = e->obs_norm ? e->d_obs_partial : nullptr;
+        r.horizon = e->base.horizon;
+        const size_t smem = ((size_t)r.net.img_floats + 2 * 64 * kR64E + 4 * 8 * kR64E) * sizeof(float);
+        static size_t configured64 = 0;
+        if (smem > configured64) {
+            CUDA_CHECK(cudaFuncSetAttribute(rollout64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured64 = smem;
+        }
+        B200_LAUNCH(rollout64_kernel, blocks, kR64Threads, smem, r);
+        if (e->obs_norm) B200_LAUNCH(obs_stats_merge_kernel, 1, 32, 0, e->d_obs_partial, blocks, e->d_obs_stat, e->d_obs_mean, e->d_obs_inv_std);
+        if (return_stats) B200_LAUNCH(return_stats_kernel, 1, 1024, 0, e->d_ret_sum, e->d_ret_cnt, e->n_envs, return_stats);
+        return;
+    }
+    if (e->obs_norm) B200_FATAL("observation normalisation needs a policy net the 64-wide kernels support");
     RolloutArgs a{};
     a.net = make_view(policy->mu);
     a.log_std = policy->d_log_std;
@@ -457,6 +737,10 @@ static void free_device_env() {
     CUDA_CHECK(cudaStreamSynchronize(stream()));
     CUDA_CHECK(cudaFree(e->d_ret_sum));
     CUDA_CHECK(cudaFree(e->d_ret_cnt));
+    CUDA_CHECK(cudaFree(e->d_obs_stat));
+    CUDA_CHECK(cudaFree(e->d_obs_mean));
+    CUDA_CHECK(cudaFree(e->d_obs_inv_std));
+    if (e->d_obs_partial) CUDA_CHECK(cudaFree(e->d_obs_partial));
     e->magic = 0;
     g_device_env = nullptr;
 }
@@ -499,6 +783,19 @@ Env* create_gym_env(int id, int seed) {
     return create_pendulum_env(id, seed);
 }
 
+extern "C" void ppo_b200_get_obs_norm(const Env* env, float* mean, float* std_, double* count) {
+    b200::DeviceEnv* e = b200::as_device_env(const_cast<Env*>(env));
+    if (!e) B200_FATAL("ppo_b200_get_obs_norm: not a device env");
+    double st[9];
+    CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    CUDA_CHECK(cudaMemcpy(st, e->d_obs_stat, sizeof(st), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) {
+        mean[k] = (float)st[k * 3];
+        std_[k] = (float)sqrt(st[k * 3 + 2] > 0 ? st[k * 3 + 1] / st[k * 3 + 2] : 1.0);
+    }
+    if (count) *count = st[2];
+}
+
 Env* create_pendulum_env_cuda(int n_envs, int seed) {
     ensure_device();
     if (g_device_env) B200_FATAL("only one device env may exist at a time (context-free Env hooks)");
@@ -516,6 +813,13 @@ Env* create_pendulum_env_cuda(int n_envs, int seed) {
     e->rollouts = 0;
     e->d_ret_sum = dmalloc<float>(n_envs);
     e->d_ret_cnt = dmalloc<int>(n_envs);
+    e->obs_norm = false;
+    e->d_obs_stat = dmalloc<double>(9);
+    e->d_obs_mean = dmalloc<float>(3);
+    e->d_obs_inv_std = dmalloc<float>(3);
+    e->d_obs_partial = nullptr;
+    e->obs_partial_cap = 0;
+    device_env_reset_obs_norm(e);
     dev_host_rng = 0xd00d0000ull + (uint64_t)(uint32_t)seed;
     g_device_env = e;
     return &e->base;

@@ -32,23 +32,8 @@
 
 namespace b200 {
 
-constexpr int kFusedMaxLayers = 5;     // weight layers
 constexpr int kFusedThreads = 256;
 constexpr double kPiF = 3.14159265358979323846;
-
-struct FusedNet {
-    int L;                              // weight layers
-    int sizes[kFusedMaxLayers + 1];
-    int acts[kFusedMaxLayers];
-    int w_off[kFusedMaxLayers], b_off[kFusedMaxLayers];   // offsets in the flat parameter vector
-    int wt_off[kFusedMaxLayers];        // offsets of Wt[in][ldw] inside the weight image (floats)
-    int ldw[kFusedMaxLayers];           // row stride of Wt (>= pad4(out); the 64-wide tile kernel pads it by 4)
-    int bs_off[kFusedMaxLayers];        // offsets of the layer biases inside the weight image (floats)
-    int img_floats;                     // image size (multiple of 32 floats = 128 B; TMA bulk needs 16 B)
-    int a_off[kFusedMaxLayers + 1];     // offsets of At buffers in shared memory (floats, after the image)
-    int P;
-    int max_width_pad;
-};
 
 enum FusedMode { kFusedForward = 0, kFusedValue = 1, kFusedPolicy = 2 };
 
@@ -72,7 +57,6 @@ struct FusedArgs {
     unsigned long long* dbg;   // phase timestamps (PPO_B200_PHASE_DEBUG), [block][16]
 };
 
-__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 
 // ---- TMA bulk copy + mbarrier (SASS: UBLKCP + SYNCS) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1111,6 +1095,17 @@ static FusedPlan choose_plan(NetDev* nd) {
 }
 
 bool fused_supported(NeuralNetwork* nn) { return choose_plan(net_dev(nn)).ok; }
+
+// Layout + up-to-date device pointer of the 64-wide weight image (shared with the rollout kernel).
+static float* ensure_image(NetDev* nd, const FusedPlan& pl);
+bool fused_image64(NeuralNetwork* nn, FusedNet* layout, const float** image) {
+    NetDev* nd = net_dev(nn);
+    const FusedPlan pl = choose_plan(nd);
+    if (!pl.ok || pl.kind != 1) return false;
+    *layout = pl.net;
+    *image = ensure_image(nd, pl);
+    return true;
+}
 
 static float* ensure_image(NetDev* nd, const FusedPlan& pl) {
     if (!nd->image || nd->image_floats != pl.net.img_floats) {

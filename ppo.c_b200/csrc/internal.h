@@ -113,6 +113,23 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m);
 void net_reduce_grads(NeuralNetwork* nn);   // partials -> nd->grads (fixed order)
 
 // ---- fused_mlp.cu -----------------------------------------------------------------------------
+constexpr int kFusedMaxLayers = 5;     // weight layers
+struct FusedNet {
+    int L;                              // weight layers
+    int sizes[kFusedMaxLayers + 1];
+    int acts[kFusedMaxLayers];
+    int w_off[kFusedMaxLayers], b_off[kFusedMaxLayers];   // offsets in the flat parameter vector
+    int wt_off[kFusedMaxLayers];        // offsets of Wt[in][ldw] inside the weight image (floats)
+    int ldw[kFusedMaxLayers];           // row stride of Wt (>= pad4(out); the 64-wide tile kernel pads it by 4)
+    int bs_off[kFusedMaxLayers];        // offsets of the layer biases inside the weight image (floats)
+    int img_floats;                     // image size (multiple of 32 floats = 128 B; TMA bulk needs 16 B)
+    int a_off[kFusedMaxLayers + 1];     // offsets of At buffers in shared memory (floats, after the image)
+    int P;
+    int max_width_pad;
+};
+
+__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
+bool fused_image64(NeuralNetwork* nn, FusedNet* layout, const float** image);   // false: net outside the 64-wide kernels
 bool fused_supported(NeuralNetwork* nn);
 void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out);
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
@@ -142,6 +159,8 @@ int device_env_count(DeviceEnv* e);
 // fused rollout: T steps for every env; writes the env-major buffer (index = env*T + t)
 void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buffer, int T,
                     const float* obs_mean, const float* obs_inv_std, float* return_stats /* dev: sum, episodes */);
+void device_env_reset_obs_norm(DeviceEnv* e);
+void device_env_set_obs_norm(bool enabled);
 void launch_sample_action(GaussianPolicy* policy, const float* state_hostmapped, float* action_hostmapped,
                           float* logprob_hostmapped, const int* rand_draws, int n_draws);
 

@@ -497,7 +497,10 @@ void ppo_b200_set_permutation_mode(PPO* ppo, int mode, unsigned long long seed) 
 
 void ppo_b200_set_kernel_path(int path) { g_force_path = path; }
 
-void ppo_b200_set_obs_norm(PPO* ppo, int enabled) { trainer(ppo)->obs_norm = enabled != 0; }
+void ppo_b200_set_obs_norm(PPO* ppo, int enabled) {
+    trainer(ppo)->obs_norm = enabled != 0;
+    device_env_set_obs_norm(enabled != 0);
+}
 
 static float read_scalar(Trainer* t, int i) {
     float h[4];

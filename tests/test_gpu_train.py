@@ -198,6 +198,42 @@ def test_device_rollout_is_self_consistent(L):
     env.contents.free_env()
 
 
+def test_obs_normalisation_running_statistics(L):
+    """[EXT] Welford running observation normalisation (no reference counterpart; merge formula of
+    include/welford_var.h:33-40).  Rollout 1 runs with identity statistics, so its stored states ARE the raw
+    observations: the running mean/std must equal numpy's over them.  Rollout 2 stores
+    (raw - mean1) / (std1 + 1e-8); un-normalising it and pooling both rollouts must give the merged statistics."""
+    n_envs, T = 512, 50
+    cabi.srand(3)
+    env = L.create_pendulum_env_cuda(n_envs, 11)
+    ppo = make_ppo(L, [3, 64, 64, 1], RELU3, n_envs * T)
+    L.ppo_b200_set_obs_norm(ppo, 1)
+    mean, std, cnt = np.zeros(3, f32), np.zeros(3, f32), C.c_double()
+    n = n_envs * T
+    L.collect_trajectories(ppo.contents.buffer, env, ppo.contents.policy, n)
+    L.ppo_b200_sync_host(ppo)
+    raw1 = host_field(ppo, "state", (n, 3)).astype(np.float64)
+    L.ppo_b200_get_obs_norm(env, mean.ctypes.data, std.ctypes.data, C.byref(cnt))
+    assert cnt.value == n
+    assert np.max(np.abs(mean - raw1.mean(0))) < 1e-5 and np.max(np.abs(std - raw1.std(0))) < 1e-5
+    m1, s1 = mean.copy(), std.copy()
+    L.collect_trajectories(ppo.contents.buffer, env, ppo.contents.policy, n)
+    L.ppo_b200_sync_host(ppo)
+    norm2 = host_field(ppo, "state", (n, 3)).astype(np.float64)
+    assert abs(norm2[:, 2].std() - 1) < 0.5          # roughly unit scale now (theta_dot spreads out as episodes go on)
+    raw2 = norm2 * (s1.astype(np.float64) + 1e-8) + m1
+    assert np.max(np.abs(raw2[:, 0] ** 2 + raw2[:, 1] ** 2 - 1)) < 1e-4   # un-normalised cos/sin are on the unit circle
+    L.ppo_b200_get_obs_norm(env, mean.ctypes.data, std.ctypes.data, C.byref(cnt))
+    both = np.concatenate([raw1, raw2])
+    assert cnt.value == 2 * n
+    assert np.max(np.abs(mean - both.mean(0))) < 1e-4 and np.max(np.abs(std - both.std(0))) < 1e-4
+    # next_state rows use the same statistics as the state rows of the same rollout (src/ppo.cu:68 carry-over)
+    st, ns = host_field(ppo, "state", (n_envs, T, 3)), host_field(ppo, "next_state", (n_envs, T, 3))
+    assert np.array_equal(st[:, 1:], ns[:, :-1])
+    L.free_ppo(ppo)
+    env.contents.free_env()
+
+
 def test_pendulum_learns_on_device(L):
     """Learning-curve check: 1024 vectorised envs, full 200-step episodes, reference
     hyper-parameters except minibatch 4096: mean episode return must rise well above the random
