@@ -484,7 +484,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ======================================================================================= helpers
@@ -651,8 +651,7 @@ def run_gpu_arm(args):
 
     if args.only_value:
         if rank == 0:
-            print(json.dumps({"only_value": True, "workload": args.workload, "ms_per_step": ms / args.steps,
-                              "gpu_launches": int(launches)}), flush=True)
+            emit({"only_value": True, "workload": args.workload, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)})
         wl.teardown()
         if world > 1:
             L.ppo_b200_dist_finalize()
@@ -713,14 +712,32 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": cpu_units / statistics.mean(times), "unit": wl.unit, "cores": 1, "kind": "port",
                                     "sample": wl.cpu_sample_desc() + "; %d timed steps, one thread (the reference is "
                                               "single-threaded, src/main.c:18)" % len(times)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     wl.teardown()
     if world > 1:
         L.ppo_b200_dist_finalize()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints lands on stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # NCCL (NCCL_DEBUG=VERSION/INFO), torchrun banners etc. write to fd 1: keep stdout clean for the JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

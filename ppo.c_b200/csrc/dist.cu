@@ -76,6 +76,102 @@ void dist_allgather_doubles(const double* send, double* recv, int count_per_rank
     ++g_launches;
 }
 
+// ---- peer arena: NVLink peer memory for the fused small-net gradient exchange -----------------------------
+// For the reference-width nets the gradient is 18 KB: an NCCL all-reduce is pure launch + protocol latency
+// (three extra launches per minibatch).  Instead every rank owns one cudaMalloc'd RECEIVE buffer
+//     u64 recv[2 parities][source rank][element]         (element = {epoch tag : 32 | fp32 bits : 32})
+// exported with cudaIpcGetMemHandle; the handles travel once through the NCCL communicator and every rank maps
+// every other buffer (cudaIpcOpenMemHandle = peer stores over NVLink).  The slab-reduce + Adam kernel
+// (fused_mlp.cu: fused_reduce_adam_kernel with a PeerView) reduces its own slabs, PUSHES each element together
+// with the epoch tag into lane [my rank] of every peer's buffer with one 64-bit store (value and flag are one
+// naturally atomic word, so no fence and no separate flag round trip: one NVLink hop of latency), then polls its
+// own buffer until every source lane carries the tag and adds the G values in rank order before Adam.  Every rank
+// adds the same numbers in the same order, so the replicas stay bit-identical.  The two parities alternate per
+// exchange: a lane is rewritten two exchanges later, which its owner can only reach after the reader has
+// finished the kernel that consumed it (stream order), see DESIGN.md §7.
+static PeerArena g_peer;
+
+static void peer_setup() {
+    if (g_peer.tried) return;
+    g_peer.tried = true;
+    const char* off = getenv("PPO_B200_PEER");
+    if (off && off[0] == '0') return;
+    if (g_world > kPeerMaxRanks) return;
+    const size_t bytes = 2 * kPeerMaxRanks * kPeerCap * sizeof(unsigned long long);
+    char* local = nullptr;
+    CUDA_CHECK(cudaMalloc(&local, bytes));
+    CUDA_CHECK(cudaMemset(local, 0, bytes));
+    cudaIpcMemHandle_t mine;
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine, local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char *d_send = nullptr, *d_recv = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_send, 64));
+    CUDA_CHECK(cudaMalloc(&d_recv, 64 * g_world));
+    CUDA_CHECK(cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice));
+    NCCL_CHECK(g_nccl.AllGather(d_send, d_recv, 64, ncclChar, g_comm, stream()));
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    std::vector<cudaIpcMemHandle_t> all(g_world);
+    CUDA_CHECK(cudaMemcpy(all.data(), d_recv, 64 * g_world, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaFree(d_send));
+    CUDA_CHECK(cudaFree(d_recv));
+    bool ok = true;
+    for (int r = 0; r < g_world; r++) {
+        if (r == g_rank) { g_peer.base[r] = local; continue; }
+        void* ptr = nullptr;
+        const cudaError_t err = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) { (void)cudaGetLastError(); ok = false; break; }
+        g_peer.base[r] = static_cast<char*>(ptr);
+    }
+    // everybody must agree (a rank that cannot map its peers would otherwise wait for flags nobody writes)
+    int* d_ok = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_ok, sizeof(int)));
+    const int mine_ok = ok ? 1 : 0;
+    CUDA_CHECK(cudaMemcpy(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+    NCCL_CHECK(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, g_comm, stream()));
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    int all_ok = 0;
+    CUDA_CHECK(cudaMemcpy(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaFree(d_ok));
+    g_peer.local = local;
+    g_peer.ready = all_ok == 1;
+    g_peer.epoch = 0;
+    if (!g_peer.ready && g_rank == 0) fprintf(stderr, "ppo_b200: peer memory not available, small-net gradients go through NCCL\n");
+}
+
+static void peer_teardown() {
+    if (g_peer.local) {
+        for (int r = 0; r < g_world; r++)
+            if (r != g_rank && g_peer.base[r]) (void)cudaIpcCloseMemHandle(g_peer.base[r]);
+        CUDA_CHECK(cudaFree(g_peer.local));
+    }
+    g_peer = PeerArena{};
+}
+
+bool dist_peer_ready() {
+    if (!dist_active()) return false;
+    peer_setup();
+    return g_peer.ready;
+}
+
+// PeerView of the next exchange (advances the epoch), or ready == 0 when peer memory is not in use.
+PeerView dist_peer_next(size_t vec_floats) {
+    PeerView v{};
+    if (!dist_active()) return v;
+    peer_setup();
+    if (!g_peer.ready || vec_floats > kPeerCap) return v;
+    const unsigned long long epoch = ++g_peer.epoch;
+    if ((epoch & 0xffffffffull) == 0) B200_FATAL("peer exchange epoch wrapped");
+    const size_t parity_off = (epoch & 1) * kPeerMaxRanks * kPeerCap;
+    v.ready = 1;
+    v.world = g_world;
+    v.rank = g_rank;
+    v.epoch = (unsigned int)epoch;
+    v.my_recv = reinterpret_cast<unsigned long long*>(g_peer.local) + parity_off;
+    for (int r = 0; r < g_world; r++)
+        v.peer_recv[r] = reinterpret_cast<unsigned long long*>(g_peer.base[r]) + parity_off + (size_t)g_rank * kPeerCap;
+    return v;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -106,6 +202,16 @@ void ppo_b200_dist_init(const char id[PPO_B200_NCCL_ID_BYTES], int rank, int wor
 void ppo_b200_dist_finalize(void) {
     if (g_comm) {
         CUDA_CHECK(cudaStreamSynchronize(stream()));
+        // every rank must be past its last peer read before anybody unmaps / frees an arena
+        if (g_peer.ready) {
+            int* d_tok = nullptr;
+            CUDA_CHECK(cudaMalloc(&d_tok, sizeof(int)));
+            CUDA_CHECK(cudaMemset(d_tok, 0, sizeof(int)));
+            NCCL_CHECK(g_nccl.AllReduce(d_tok, d_tok, 1, ncclInt, ncclSum, g_comm, stream()));
+            CUDA_CHECK(cudaStreamSynchronize(stream()));
+            CUDA_CHECK(cudaFree(d_tok));
+        }
+        peer_teardown();
         NCCL_CHECK(g_nccl.CommDestroy(g_comm));
         g_comm = nullptr;
     }

@@ -887,8 +887,9 @@ struct ReduceAdamArgs {
     const float* log_std;
     FusedNet layout;         // to refresh the transposed weight image
     float* image;
-    int apply;               // 0: only write the reduced slab to `reduced` (data-parallel path)
+    int apply;               // 0: only write the reduced slab to `reduced` (data-parallel path through NCCL)
     float* reduced;
+    PeerView peer;           // peer.ready: data-parallel exchange over NVLink peer memory inside this kernel
 };
 
 __device__ __forceinline__ float adam_apply(const AdamSeg& s, int i, float g, float m, float v, float w) {
@@ -960,10 +961,40 @@ __global__ void __launch_bounds__(32 * kRedWarps) fused_reduce_adam_kernel(const
     }
     red[warp][lane] = s;
     __syncthreads();
-    if (warp != 0 || e >= total) return;
-    float g = red[0][lane];
+    if (warp != 0) return;
+    float g = 0.f;
+    if (e < total) {
+        g = red[0][lane];
 #pragma unroll
-    for (int w = 1; w < kRedWarps; w++) g += red[w][lane];
+        for (int w = 1; w < kRedWarps; w++) g += red[w][lane];
+    }
+    if (p.peer.ready && e < total) {
+        // ---- gradient exchange over NVLink peer memory (dist.cu "peer arena"): push {tag, value}, poll, ordered sum
+        const PeerView& pv = p.peer;
+        const unsigned long long packed = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(g);
+        for (int r = 0; r < pv.world; r++)
+            if (r != pv.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(pv.peer_recv[r] + e), "l"(packed) : "memory");
+        const long long t0 = clock64();
+        float sum = 0.f;
+        for (int r = 0; r < pv.world; r++) {
+            float x = g;
+            if (r != pv.rank) {
+                const unsigned long long* src = pv.my_recv + (size_t)r * kPeerCap + e;
+                unsigned long long w;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                    if ((unsigned int)(w >> 32) != pv.epoch && clock64() - t0 > 8000000000ll) {
+                        printf("ppo_b200: peer exchange timed out (rank %d waiting for rank %d, epoch %u)\n", pv.rank, r, pv.epoch);
+                        __trap();
+                    }
+                } while ((unsigned int)(w >> 32) != pv.epoch);
+                x = __uint_as_float((unsigned int)w);
+            }
+            sum += x;                                               // same numbers, same (rank) order on every GPU
+        }
+        g = sum;
+    }
+    if (e >= total) return;
     if (!p.apply) { p.reduced[e] = g; return; }
     if (is_net) {
         const float w = adam_apply(p.net, e, g, pm, pv, pw);
@@ -1195,7 +1226,7 @@ static bool pdl_enabled() {
 // minibatch of the same net (so the update kernel may be launched programmatically dependent on it).
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
-                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained) {
+                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained, bool dp_peer) {
     NetDev* nd = net_dev(nn);
     const FusedPlan pl = choose_plan(nd);
     if (!pl.ok) return false;
@@ -1229,6 +1260,10 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
     r.layout = pl.net; r.image = nd->image;
     r.apply = reduced_out ? 0 : 1;
     r.reduced = reduced_out;
+    if (dp_peer) {
+        r.peer = dist_peer_next((size_t)slab);
+        if (!r.peer.ready) B200_FATAL("peer exchange requested but the peer arena is not available (slab %d floats)", slab);
+    }
     if (!reduced_out) {
         adam_net->time_step += 1;
         r.net = make_seg(nd->params, nd->grads, adam_net, lr);

@@ -134,7 +134,8 @@ bool fused_supported(NeuralNetwork* nn);
 void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out);
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
-                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained = false);
+                            float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained = false,
+                            bool dp_peer = false);
 
 // ---- policy.cu --------------------------------------------------------------------------------
 void launch_log_prob(const float* mu, const float* log_std, const float* action, float* out, int m, int A);
@@ -165,6 +166,22 @@ void launch_sample_action(GaussianPolicy* policy, const float* state_hostmapped,
                           float* logprob_hostmapped, const int* rand_draws, int n_draws);
 
 // ---- dist.cu ----------------------------------------------------------------------------------
+constexpr int kPeerMaxRanks = 8;
+constexpr size_t kPeerCap = 1 << 15;                 // elements per (parity, source rank) receive lane: nets up to 32768 parameters
+struct PeerArena {
+    bool tried = false, ready = false;
+    char* local = nullptr;                           // receive buffer: u64 [2 parities][kPeerMaxRanks sources][kPeerCap]
+    char* base[kPeerMaxRanks] = {};
+    unsigned long long epoch = 0;
+};
+struct PeerView {                                    // kernel argument: one gradient exchange over NVLink peer memory
+    int ready, world, rank;
+    unsigned int epoch;                              // tag of this exchange (never 0)
+    unsigned long long* my_recv;                     // my receive lanes of this epoch's parity: [source rank][kPeerCap]
+    unsigned long long* peer_recv[kPeerMaxRanks];    // lane [my rank] inside rank r's receive buffer (same parity)
+};
+PeerView dist_peer_next(size_t vec_floats);
+bool dist_peer_ready();
 bool dist_active();
 int dist_rank();
 int dist_world();

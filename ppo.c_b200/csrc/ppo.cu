@@ -163,6 +163,8 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     NetDev* ndP = net_dev(pol->mu);
     const bool fusedV = use_fused() && fused_supported(ppo->V);
     const bool fusedP = use_fused() && fused_supported(pol->mu);
+    // small-net gradients cross the GPUs inside the Adam kernel over NVLink peer memory when it can be mapped
+    const bool peer = G > 1 && (fusedV || fusedP) && dist_peer_ready();
     CUDA_CHECK(cudaMemsetAsync(t->d_scalars, 0, 2 * sizeof(float), stream()));
     t->n_v_steps = n_epochs_value * num_batches;
     t->n_p_steps = n_epochs_policy * num_batches;
@@ -172,10 +174,10 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
             if (fusedV) {
-                float* red = G > 1 ? static_cast<float*>(scratch(kScratchMisc, (ndV->param_count + 2) * sizeof(float))) : nullptr;
+                float* red = (G > 1 && !peer) ? static_cast<float*>(scratch(kScratchMisc, (ndV->param_count + 2) * sizeof(float))) : nullptr;
                 fused_minibatch_update(ppo->V, nullptr, ppo->adam_V, nullptr, ppo->lr_V, perm, k * batch_size + row0, limit,
-                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, red, k > 0);
-                if (G > 1) {   // slab-reduce -> NCCL all-reduce -> Adam
+                                       mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, red, k > 0, peer);
+                if (G > 1 && !peer) {   // slab-reduce -> NCCL all-reduce -> Adam
                     dist_allreduce_sum(red, ndV->param_count + 2);
                     ppo->adam_V->time_step += 1;
                     adam_flat(ndV->params, red, ppo->adam_V->m, ppo->adam_V->v, (int)ndV->param_count, ppo->lr_V,
@@ -207,11 +209,12 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
             if (fusedP) {
-                float* red = G > 1 ? static_cast<float*>(scratch(kScratchMisc, (ndP->param_count + A + 1) * sizeof(float))) : nullptr;
+                float* red = (G > 1 && !peer) ? static_cast<float*>(scratch(kScratchMisc, (ndP->param_count + A + 1) * sizeof(float))) : nullptr;
+                if (G > 1 && ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
                 fused_minibatch_update(pol->mu, pol, ppo->adam_policy, ppo->adam_entropy, ppo->lr_policy, perm,
                                        k * batch_size + row0, limit, mb_local, mb_total, b, ppo->epsilon, ppo->ent_coeff,
-                                       t->d_scalars + 1, red, k > 0);
-                if (G > 1) {
+                                       t->d_scalars + 1, red, k > 0, peer);
+                if (G > 1 && !peer) {
                     if (ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
                     dist_allreduce_sum(red, ndP->param_count + A + 1);
                     ppo->adam_entropy->time_step += 1;
