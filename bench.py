@@ -449,7 +449,142 @@ class C5(Workload):
                 "T=%d x N=%d sample (%d elements)" % (self.T, self.CPU_N, self.T * self.CPU_N))
 
 
-WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5}
+class StageWorkload(Workload):
+    """Single-kernel stage benchmark on flat synthetic arrays (HBM roofline evidence for north-star items d, g)."""
+    host_arrays = ()
+
+    def _mk(self, shape, dtype=f32, rng=None, scale=1.0):
+        import b200
+        a = (rng.standard_normal(shape, dtype=f32) * scale).astype(dtype) if rng is not None else np.zeros(shape, dtype)
+        return b200.dev(a), a
+
+    def step_device(self, k):
+        for _ in range(k):
+            self._call()
+
+    def teardown(self):
+        for d in self.devs:
+            d.free()
+
+
+class AdamStage(StageWorkload):
+    """Adam over one flat fp32 vector of 2^26 parameters (src/adam.cu:53-74): 28 B/parameter."""
+    name = "adam"
+    metric, unit = "adam_params_per_s", "params/s"
+    P = 1 << 26
+    CPU_P = 1 << 22
+
+    def setup(self):
+        rng = np.random.default_rng(3 + self.rank)
+        (self.w, hw), (self.g, hg) = self._mk(self.P, rng=rng, scale=0.1), self._mk(self.P, rng=rng, scale=0.01)
+        (self.m, _), (self.v, _) = self._mk(self.P), self._mk(self.P)
+        self.devs = [self.w, self.g, self.m, self.v]
+        self.hw, self.hg, self.t = hw, hg, 0
+
+    def _call(self):
+        self.t += 1
+        self.L.ppo_b200_adam_flat(self.w.ptr, self.g.ptr, self.m.ptr, self.v.ptr, self.P, 3e-4, 0.9, 0.999, self.t)
+
+    def step_e2e(self, k):
+        for _ in range(k):          # gradient arrives from the host, updated weights go back
+            self.L.ppo_b200_h2d(self.g.ptr, self.hg.ctypes.data, self.hg.nbytes)
+            self._call()
+            self.L.ppo_b200_d2h(self.hw.ctypes.data, self.w.ptr, self.hw.nbytes)
+
+    def units_per_step(self):
+        return self.P
+
+    def e2e_bytes(self):
+        return 4 * self.P, 4 * self.P
+
+    def config(self):
+        return {"workload": "adam: one multi-tensor Adam launch over a flat vector of %d fp32 parameters (g, m, v, w resident; 1.07 GB "
+                            "of state, larger than L2)" % self.P, "parallelism": "replicated x%d" % self.world,
+                "l2": "inputs larger than L2 (4 x 268 MB)", "e2e_call": "ppo_b200_adam_flat with the gradient uploaded from and the "
+                "weights downloaded to pageable host memory each step"}
+
+    def roofline_work(self, kernels):
+        return {"adam_flat_kernel": ("hbm", 28.0 * self.P)}
+
+    def cpu_sample(self, n_iters, seed=1):
+        import oracle
+        rng = np.random.default_rng(seed)
+        w, g = rng.standard_normal(self.CPU_P, dtype=f32), rng.standard_normal(self.CPU_P, dtype=f32)
+        m, v = np.zeros(self.CPU_P, f32), np.zeros(self.CPU_P, f32)
+        times, t = [], 0
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            t = oracle.adam(w, g, m, v, 3e-4, t)
+            times.append(time.perf_counter() - t0)
+        return times, self.CPU_P
+
+    def cpu_sample_desc(self):
+        return "oracle port of adam_update (src/adam.cu:53-74) over %d parameters" % self.CPU_P
+
+
+class GatherStage(StageWorkload):
+    """Minibatch gather by permutation on the C3-shaped buffer (src/trajectory_buffer.cu:168-220): 212 B/sample."""
+    name = "gather"
+    metric, unit = "gather_samples_per_s", "samples/s"
+    S, A, B = 17, 6, 2048 * 512
+    CPU_B = 1 << 18
+
+    def setup(self):
+        import b200
+        rng = np.random.default_rng(5 + self.rank)
+        S, A, B = self.S, self.A, self.B
+        self.src = [self._mk((B, S), rng=rng)[0], self._mk((B, A), rng=rng)[0]] + [self._mk(B, rng=rng)[0] for _ in range(3)]
+        self.dst = [self._mk((B, S))[0], self._mk((B, A))[0]] + [self._mk(B)[0] for _ in range(3)]
+        self.idx = b200.dev_empty(B, np.int32)
+        self.L.ppo_b200_permutation(self.idx.ptr, B, 17, 0)
+        self.devs = self.src + self.dst + [self.idx]
+
+    def _call(self):
+        self.L.ppo_b200_gather(self.idx.ptr, 0, self.B, self.B, self.S, self.A, *[d.ptr for d in self.src], *[d.ptr for d in self.dst])
+
+    def step_e2e(self, k):
+        out = [np.empty(d.shape, f32) for d in self.dst]
+        for _ in range(k):
+            self._call()
+            for d, o in zip(self.dst, out):
+                self.L.ppo_b200_d2h(o.ctypes.data, d.ptr, o.nbytes)
+
+    def units_per_step(self):
+        return self.B
+
+    def e2e_bytes(self):
+        return 0, 4 * self.B * (self.S + self.A + 3)
+
+    def config(self):
+        return {"workload": "gather: all %d rows of a HalfCheetah-shaped buffer (S=17, A=6) gathered by a device permutation in one "
+                            "launch (states, actions, logprob, advantage, adv_target)" % self.B,
+                "parallelism": "replicated x%d" % self.world, "l2": "buffer 109 MB + 109 MB output; random 68-byte rows",
+                "e2e_call": "ppo_b200_gather on the resident buffer + download of the gathered minibatch"}
+
+    def roofline_work(self, kernels):
+        return {"gather_kernel": ("hbm", float(self.B) * (4 + 2 * 4 * (self.S + self.A + 3)))}
+
+    def cpu_sample(self, n_iters, seed=1):
+        import oracle
+        import cabi
+        rng = np.random.default_rng(seed)
+        n = self.CPU_B
+        st, ac = rng.standard_normal((n, self.S), dtype=f32), rng.standard_normal((n, self.A), dtype=f32)
+        lp, ad, at = (rng.standard_normal(n, dtype=f32) for _ in range(3))
+        cabi.srand(seed)
+        idx = oracle.shuffle(n)
+        times = []
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            oracle.get_batch(idx, 0, n, st, ac, lp, ad, at)
+            times.append(time.perf_counter() - t0)
+        return times, n
+
+    def cpu_sample_desc(self):
+        return "oracle port of get_batch (src/trajectory_buffer.cu:202-220) over %d rows" % self.CPU_B
+
+
+WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5, "adam": AdamStage, "gather": GatherStage}
 
 
 # ======================================================================================= CPU arm
@@ -626,6 +761,8 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     wl = WORKLOADS[args.workload](L, rank, world)
+    if args.mb > 0 and hasattr(wl, "MB"):
+        wl.MB = args.mb
     wl.setup()
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------
@@ -746,6 +883,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: --steps)")
     ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--mb", type=int, default=0, help="override the workload's minibatch size per GPU (c2/c3/c4)")
     ap.add_argument("--only-value", action="store_true",
                     help="skip the e2e / per-kernel / CPU legs (short command for ncu passes; not a bench line)")
     args = ap.parse_args()

@@ -160,23 +160,121 @@ linear_forward_skinny_kernel(float* __restrict__ y, const float* __restrict__ x,
     }
 }
 
-// db slabs: gb_part[s][col] = sum over rows of split s of g[row][col]
+// db slabs: gb_part[s][col] = sum over rows of split s of g[row][col].
+// Thread = (float4 column group, row lane): 8 column groups x 32 row lanes, four independent 128-bit loads in
+// flight per thread; fixed-order combine of the row lanes.
 __global__ void __launch_bounds__(256)
 colsum_kernel(float* __restrict__ gb_part, size_t stride, const float* __restrict__ g, int m, int l, int rows_per_split) {
-    __shared__ float red[8][33];
-    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + cx;
+    __shared__ float4 red[32][9];
+    const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+    const int col = blockIdx.x * 32 + 4 * cx;
     const int r0 = blockIdx.y * rows_per_split, r1 = min(m, r0 + rows_per_split);
-    float s = 0.f;
-    if (col < l)
-        for (int r = r0 + ry; r < r1; r += 8) s += g[(size_t)r * l + col];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool vec = (l & 3) == 0 && col + 3 < l && (((uintptr_t)g) & 15) == 0;
+    if (vec) {
+        int r = r0 + ry;
+        for (; r + 96 < r1; r += 128) {
+            float4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = __ldg(reinterpret_cast<const float4*>(g + (size_t)(r + 32 * u) * l + col));
+#pragma unroll
+            for (int u = 0; u < 4; u++) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+        }
+        for (; r < r1; r += 32) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(g + (size_t)r * l + col));
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+    } else {
+        for (int r = r0 + ry; r < r1; r += 32) {
+            if (col + 0 < l) s.x += g[(size_t)r * l + col + 0];
+            if (col + 1 < l) s.y += g[(size_t)r * l + col + 1];
+            if (col + 2 < l) s.z += g[(size_t)r * l + col + 2];
+            if (col + 3 < l) s.w += g[(size_t)r * l + col + 3];
+        }
+    }
     red[ry][cx] = s;
     __syncthreads();
-    if (ry == 0 && col < l) {
-        float t = red[0][cx];
+    if (ry == 0) {
+        float4 t = red[0][cx];
+#pragma unroll 8
+        for (int k = 1; k < 32; k++) { const float4 q = red[k][cx]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+        float* out = gb_part + (size_t)blockIdx.y * stride + col;
+        if (col + 0 < l) out[0] = t.x;
+        if (col + 1 < l) out[1] = t.y;
+        if (col + 2 < l) out[2] = t.z;
+        if (col + 3 < l) out[3] = t.w;
+    }
+}
+
+// Skinny dW (+db): one side of the layer is <= 32 wide (first layer of a low-dimensional env: n = S; value / action
+// heads: l <= 8).  gW[j][k] = sum_r g[r][j] * x[r][k].  The WIDE side is spread over threads (64 consecutive columns
+// per CTA, coalesced), the SMALL side lives in registers; rows are split over 4 row lanes per CTA and `splits` CTAs.
+// A 64x64 tile kernel would run these layers at a few percent utilisation (17 of 64 columns live).
+//   WIDE_IS_L = true : wide = g columns (l), small = x columns (n <= 32); also emits db (column sums of g)
+//   WIDE_IS_L = false: wide = x columns (n), small = g columns (l <= 32)
+template <int SP, bool WIDE_IS_L>     // SP = padded small width (multiple of 4)
+__global__ void __launch_bounds__(256)
+skinny_dw_kernel(float* __restrict__ gW_part, float* __restrict__ gb_part, size_t stride, const float* __restrict__ g,
+                 const float* __restrict__ x, int m, int n, int l, int rows_per_split) {
+    constexpr int CH = 64;                                   // rows staged per chunk
+    __shared__ __align__(16) float sm[CH][SP];
+    __shared__ float red[3][64][SP + 1];
+    const int cx = threadIdx.x & 63, q = threadIdx.x >> 6;   // q = row lane 0..3
+    const int wide_n = WIDE_IS_L ? l : n, small_n = WIDE_IS_L ? n : l;
+    const float* wide = WIDE_IS_L ? g : x;
+    const float* small = WIDE_IS_L ? x : g;
+    const int col = blockIdx.x * 64 + cx;
+    const bool live = col < wide_n;
+    const int r0 = blockIdx.y * rows_per_split, r1 = min(m, r0 + rows_per_split);
+    float acc[SP], bsum = 0.f;
 #pragma unroll
-        for (int k = 1; k < 8; k++) t += red[k][cx];
-        gb_part[(size_t)blockIdx.y * stride + col] = t;
+    for (int k = 0; k < SP; k++) acc[k] = 0.f;
+    for (int c0 = r0; c0 < r1; c0 += CH) {
+        const int rows = min(CH, r1 - c0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < CH * SP; e += 256) {
+            const int r = e / SP, k = e - r * SP;
+            sm[r][k] = (r < rows && k < small_n) ? small[(size_t)(c0 + r) * small_n + k] : 0.f;
+        }
+        __syncthreads();
+        float wv[CH / 4];
+#pragma unroll
+        for (int i = 0; i < CH / 4; i++) {
+            const int r = 4 * i + q;
+            wv[i] = (live && r < rows) ? __ldg(wide + (size_t)(c0 + r) * wide_n + col) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < CH / 4; i++) {
+            const int r = 4 * i + q;
+            bsum += wv[i];
+#pragma unroll
+            for (int k4 = 0; k4 < SP / 4; k4++) {
+                const float4 sv = *reinterpret_cast<const float4*>(&sm[r][4 * k4]);
+                acc[4 * k4 + 0] = fmaf(wv[i], sv.x, acc[4 * k4 + 0]);
+                acc[4 * k4 + 1] = fmaf(wv[i], sv.y, acc[4 * k4 + 1]);
+                acc[4 * k4 + 2] = fmaf(wv[i], sv.z, acc[4 * k4 + 2]);
+                acc[4 * k4 + 3] = fmaf(wv[i], sv.w, acc[4 * k4 + 3]);
+            }
+        }
+    }
+    __syncthreads();
+    if (q > 0) {
+#pragma unroll
+        for (int k = 0; k < SP; k++) red[q - 1][cx][k] = acc[k];
+        red[q - 1][cx][SP] = bsum;
+    }
+    __syncthreads();
+    if (q == 0 && live) {
+        float* outW = gW_part + (size_t)blockIdx.y * stride;
+#pragma unroll
+        for (int k = 0; k < SP; k++) {
+            const float t = ((acc[k] + red[0][cx][k]) + red[1][cx][k]) + red[2][cx][k];
+            if (k < small_n) {
+                if (WIDE_IS_L) outW[(size_t)col * n + k] = t;      // gW[j = col][k]
+                else outW[(size_t)k * n + col] = t;                // gW[j = k][col]
+            }
+        }
+        if (WIDE_IS_L) gb_part[(size_t)blockIdx.y * stride + col] = ((bsum + red[0][cx][SP]) + red[1][cx][SP]) + red[2][cx][SP];
     }
 }
 
@@ -238,6 +336,21 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
     rows = div_up(rows, 32) * 32;          // multiple of both tile depths (16 FFMA, 32 TF32)
     if (use_tc(m, n, l, g, x, l, n) && ((stride * 4) % 16) == 0 && ((uintptr_t)gW_part & 15) == 0) {
         tc_linear_backward_weights(gW_part, stride, splits, g, x, m, n, l);
+        dim3 grid2(div_up(l, 32), splits, 1);
+        B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+        return;
+    }
+    if (m >= 1024 && n <= 32 && l >= 64) {          // narrow input layer: wide side = l, also emits db
+        dim3 gs(div_up(l, 64), splits, 1);
+        if (n <= 8) B200_LAUNCH((skinny_dw_kernel<8, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
+        else if (n <= 16) B200_LAUNCH((skinny_dw_kernel<16, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
+        else if (n <= 24) B200_LAUNCH((skinny_dw_kernel<24, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
+        else B200_LAUNCH((skinny_dw_kernel<32, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
+        return;
+    }
+    if (m >= 1024 && l <= 8 && n >= 64) {           // value / action heads: wide side = n; db is a tiny column sum
+        dim3 gs(div_up(n, 64), splits, 1);
+        B200_LAUNCH((skinny_dw_kernel<8, false>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
         dim3 grid2(div_up(l, 32), splits, 1);
         B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
         return;
