@@ -18,23 +18,44 @@
 
 namespace b200 {
 
+// One warp per gathered row, lane = element of the packed row [state(S) | action(A) | logprob | advantage |
+// adv_target]; U rows per warp iteration so that U independent index loads and then U independent payload loads
+// are in flight per lane (the gather is latency-bound: bytes in flight per SM set its bandwidth).
+constexpr int kGatherU = 8;
 __global__ void __launch_bounds__(256)
 gather_kernel(const int* __restrict__ idx, int offset, int limit, int batch_size, int S, int A,
               const float* __restrict__ state, const float* __restrict__ action,
               const float* __restrict__ logprob, const float* __restrict__ advantage,
               const float* __restrict__ adv_target, float* __restrict__ states, float* __restrict__ actions,
               float* __restrict__ logprobs, float* __restrict__ advantages, float* __restrict__ adv_targets) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int W = S + A + 3;
-    const long long total = (long long)batch_size * W;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int row = (int)(e / W), c = (int)(e - (long long)row * W);
-        const int src = __ldg(idx + (offset + row) % limit);   // src/trajectory_buffer.cu:171-173
-        if (c < S) states[(size_t)row * S + c] = state[(size_t)src * S + c];
-        else if (c < S + A) actions[(size_t)row * A + (c - S)] = action[(size_t)src * A + (c - S)];
-        else if (c == S + A) logprobs[row] = logprob[src];
-        else if (c == S + A + 1) advantages[row] = advantage[src];
-        else adv_targets[row] = adv_target[src];
+    for (int row0 = warp * kGatherU; row0 < batch_size; row0 += nwarps * kGatherU) {
+        int src[kGatherU];
+#pragma unroll
+        for (int u = 0; u < kGatherU; u++) {
+            const int r = row0 + u;
+            src[u] = r < batch_size ? __ldg(idx + (offset + r) % limit) : -1;   // src/trajectory_buffer.cu:171-173
+        }
+        for (int c0 = 0; c0 < W; c0 += 32) {
+            const int c = c0 + lane;
+            const float* sp;
+            float* dp;
+            int stride, off;
+            if (c < S) { sp = state; dp = states; stride = S; off = c; }
+            else if (c < S + A) { sp = action; dp = actions; stride = A; off = c - S; }
+            else if (c == S + A) { sp = logprob; dp = logprobs; stride = 1; off = 0; }
+            else if (c == S + A + 1) { sp = advantage; dp = advantages; stride = 1; off = 0; }
+            else { sp = adv_target; dp = adv_targets; stride = 1; off = 0; }
+            float v[kGatherU];
+#pragma unroll
+            for (int u = 0; u < kGatherU; u++)
+                if (c < W && src[u] >= 0) v[u] = sp[(size_t)src[u] * stride + off];
+#pragma unroll
+            for (int u = 0; u < kGatherU; u++)
+                if (c < W && src[u] >= 0) dp[(size_t)(row0 + u) * stride + off] = v[u];
+        }
     }
 }
 
@@ -42,8 +63,8 @@ void launch_gather(const int* idx, int offset, int limit, int batch_size, int S,
                    const float* action, const float* logprob, const float* advantage, const float* adv_target,
                    float* states, float* actions, float* logprobs, float* advantages, float* adv_targets) {
     if (batch_size <= 0) return;
-    const long long total = (long long)batch_size * (S + A + 3);
-    const int blocks = (int)std::min<long long>(div_up(total, 256), (long long)num_sms() * 16);
+    const int warps = div_up(batch_size, kGatherU);
+    const int blocks = std::max(1, std::min(div_up(warps, 8), num_sms() * 8));
     B200_LAUNCH(gather_kernel, blocks, 256, 0, idx, offset, limit, batch_size, S, A, state, action, logprob,
                 advantage, adv_target, states, actions, logprobs, advantages, adv_targets);
 }

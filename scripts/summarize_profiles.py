@@ -130,7 +130,9 @@ def main():
     for path in sorted(glob.glob(os.path.join(OUT, "launches_*.csv"))):
         print("launches ->", summarize_launches(path, tag))
     table = []
-    for path in sorted(glob.glob(os.path.join(OUT, "bench_c?.json")) + glob.glob(os.path.join(OUT, "bench_c?_g?.json"))):
+    for path in sorted(glob.glob(os.path.join(OUT, "bench_*.json"))):
+        if os.path.basename(path) in ("bench_default.json", "bench_ref.json"):
+            continue
         try:
             line = json.loads(open(path).read().strip().splitlines()[-1])
         except (ValueError, IndexError):
@@ -142,7 +144,29 @@ def main():
         table.append((name.replace("bench_", "").replace(".json", ""), line["n_gpus"], line["value"], line["unit"], line["ms_per_step"],
                       line["e2e"]["value"], r.get("kernel"), r.get("bound"), r.get("achieved"), r.get("unit"), r.get("frac"),
                       r.get("share_of_step"), cb.get("value")))
+    write_readme(tag, table)
     return table
+
+
+def write_readme(tag, table):
+    lines = ["# profiles/ — measured evidence (round %s)" % tag.lstrip("r"), "",
+             "All numbers: one B200 box through `gpurun`, CUDA-event timing on the library's stream, inputs larger than L2,",
+             "peaks from `MEASURED_PEAKS.json` (HBM 6452.8 GB/s measured copy; TF32 tensor = measured sustained cuBLAS bf16 / 2;",
+             "fp32 = nominal 74.4 TFLOP/s).  `value` = inputs resident in HBM, `e2e` = host-buffer call, `cpu` = oracle port on one host core.",
+             "Files: `%s_bench_<workload>[_gN].json` full bench lines; `%s_launches_<workload>.txt` ncu launch lists;" % (tag, tag),
+             "`%s_ncu_<capture>.txt` per-launch metrics of the `ncu --set full` captures; `traffic.json` DRAM bytes per launch;" % tag,
+             "`%s_learning_curve_*.json` Pendulum return curves (`scripts/train_pendulum.py`)." % tag, "",
+             "| workload | GPUs | value | unit | ms/step | e2e | dominant kernel | bound | achieved | frac of peak | share of step | CPU (1 core) |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for (name, n, v, unit, ms, e2e, kern, bound, ach, aunit, frac, share, cpu) in table:
+        lines.append("| %s | %d | %.4g | %s | %.3f | %.4g | %s | %s | %s | %s | %s | %s |" % (
+            name, n, v, unit, ms, e2e, kern, bound, ("%.4g %s" % (ach, aunit)) if ach else "-", ("%.3f" % frac) if frac else "-",
+            ("%.2f" % share) if share else "-", ("%.4g" % cpu) if cpu else "-"))
+    lines.append("")
+    extra = os.path.join(PROF, "NOTES.md")
+    if os.path.exists(extra):
+        lines.append(open(extra).read())
+    open(os.path.join(PROF, "README.md"), "w").write("\n".join(lines) + "\n")
 
 
 if __name__ == "__main__":
