@@ -33,7 +33,8 @@ constexpr int kTcBKBytes = 128;            // one 128B swizzle row per k-block
 constexpr int kTcBK = kTcBKBytes / 4;      // 32 tf32 elements
 constexpr int kTcUmmaK = 8;                // tf32: 32 bytes
 constexpr int kTcStages = 4;
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 8;               // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 
 enum TcEpilogue { kTcFwd = 0, kTcDx = 1, kTcDw = 2 };
 
@@ -69,6 +70,23 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tc_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 :: "r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(s_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -117,7 +135,12 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = round_tf32(src[i]);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// CL = CTAs per cluster along the M-tile axis (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically
+// adjacent output tiles, i.e. they need the SAME B tile: each loads half of it and TMA-multicasts it into both
+// shared memories, which halves the B traffic out of L2 (a 128x256 TF32 tile pulls 1.5 MB of operands through L2
+// per 67 MFLOP - the kernel is L2-bandwidth bound, not tensor bound).  A ring slot may be refilled only after BOTH
+// CTAs' MMAs released it, so tcgen05.commit arrives on the empty barrier of both CTAs (count = CL).
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
     constexpr uint32_t A_BYTES = kTcBM * kTcBKBytes;           // 16 KB per stage
@@ -143,7 +166,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
-        for (int s = 0; s < kTcStages; s++) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kTcStages; s++) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], CL); }
         tc_mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -155,6 +178,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = CL > 1 ? tc_cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    if (CL > 1) tc_cluster_sync();          // the peer's barriers are initialised before anything is multicast into them
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -174,12 +200,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int i = 0; i < kTcBM / 32; i++)                                        // box {32 mn, 32 k-rows}
                         tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + 32 * i, k0, &full_bar[s]);
                 }
-                if (!B_MN) {
-                    tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
-                } else {
+                if (CL == 1) {
+                    if (!B_MN) {
+                        tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < BN / 32; i++)
-                        tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * i, k0, &full_bar[s]);
+                        for (int i = 0; i < BN / 32; i++)
+                            tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * i, k0, &full_bar[s]);
+                    }
+                } else {                     // my half of the shared B tile, multicast to both CTAs of the cluster
+                    if (!B_MN) {             // box {32 k, BN/CL rows}
+                        constexpr int HR = BN / CL;
+                        tc_tma_load_2d_mc(sb + crank * (HR * kTcBKBytes), &tmB, k0, n0 + (int)crank * HR, &full_bar[s], kMask);
+                    } else {
+                        constexpr int HB = BN / 32 / CL;
+#pragma unroll
+                        for (int i = 0; i < HB; i++) {
+                            const int bi = (int)crank * HB + i;
+                            tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * bi, k0, &full_bar[s], kMask);
+                        }
+                    }
                 }
             }
         }
@@ -201,19 +241,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t db = B_MN ? tc_make_desc(sb + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sb + k * 32, 16, 1024, 2);
                     tc_umma_tf32(tmem_base, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                 }
-                tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
+                if (CL == 1) tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
+                else tc_umma_commit_mc(&empty_bar[s], kMask);        // ... in both CTAs (each writes into the other's slot)
             }
             tc_umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
-        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4; warps 2..5 take columns [0, BN/2), warps 6..9 the rest =====
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = m0 + q * 32 + lane;
         tc_mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* Crow = p.C + (EPI == kTcDw ? (size_t)blockIdx.z * p.c_split_stride : 0) + (size_t)row * p.ldc;
+        const bool rows_ok = row < p.M;
+        constexpr int CPW = BN / (kTcEpiWarps / 4);          // columns per warp
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * CPW; c0 < (half + 1) * CPW; c0 += 32) {
+            const int nb = n0 + c0;
+            // the activation-derivative operand is fetched while the TMEM load is in flight
+            float4 hv[8];
+            const bool full32 = nb + 32 <= p.N;
+            const bool need_h = EPI == kTcDx && p.act != kActNone && rows_ok;
+            if (need_h && full32 && (p.N & 3) == 0) {
+                const float4* hrow4 = reinterpret_cast<const float4*>(p.xin + (size_t)row * p.N + nb);
+#pragma unroll
+                for (int j = 0; j < 8; j++) hv[j] = __ldg(hrow4 + j);
+            }
             uint32_t r[32];
             if (num_kb > 0) {
                 tc_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -221,8 +275,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; j++) r[j] = 0u;
             }
-            if (row < p.M) {
-                const int nb = n0 + c0;
+            if (rows_ok) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -231,16 +284,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; j++)
                         if (nb + j < p.N) v[j] = round_tf32(act_apply(v[j] + __ldg(p.bias + nb + j), p.act));
                 } else if (EPI == kTcDx) {
-                    if (p.act != kActNone) {
-                        const float* hrow = p.xin + (size_t)row * p.N + nb;
+                    if (need_h) {
+                        if (full32 && (p.N & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
+                            for (int j = 0; j < 8; j++) {
+                                v[4 * j + 0] = act_grad(hv[j].x, v[4 * j + 0], p.act);
+                                v[4 * j + 1] = act_grad(hv[j].y, v[4 * j + 1], p.act);
+                                v[4 * j + 2] = act_grad(hv[j].z, v[4 * j + 2], p.act);
+                                v[4 * j + 3] = act_grad(hv[j].w, v[4 * j + 3], p.act);
+                            }
+                        } else {
+                            const float* hrow = p.xin + (size_t)row * p.N + nb;
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
                 }
-                if (nb + 32 <= p.N && (p.ldc & 3) == 0) {
+                if (full32 && (p.ldc & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4*>(Crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -258,6 +321,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
     }
+    if (CL > 1) tc_cluster_sync();          // nobody leaves while the peer may still multicast / arrive into this CTA
 }
 
 // ---- host: tensor maps --------------------------------------------------------------------------------
@@ -291,15 +355,41 @@ static CUtensorMap make_map(const float* base, int rows, int cols, int box_cols,
     return m;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
+static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multicast clusters (A/B runs)
+    static int cl = -1;
+    if (cl < 0) { const char* e = getenv("PPO_B200_TC_CLUSTER"); cl = (e && e[0] == '1') ? 1 : 2; }
+    return cl;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
     const size_t smem = (size_t)kTcStages * (kTcBM + BN) * kTcBKBytes + 1024 /*align*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI>), grid, kTcThreads, smem, ta, tb, a);
+    if (CL == 1) {
+        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>), grid, kTcThreads, smem, ta, tb, a);
+        return;
+    }
+    grid.y = (grid.y + CL - 1) / CL * CL;     // a padding CTA runs the pipeline on zero-filled rows and stores nothing
+    if (g_profiling) profile_mark("(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)", true);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = CL; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>, ta, tb, a));
+    ++g_launches;
+    if (g_profiling) profile_mark("(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)", false);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
+    if (tc_cluster() == 2) launch_tc_cl<BN, A_MN, B_MN, EPI, 2>(ta, tb, a, grid);
+    else launch_tc_cl<BN, A_MN, B_MN, EPI, 1>(ta, tb, a, grid);
 }
 
 // Shapes the tensor path accepts: TMA needs 16-byte row pitches and aligned bases.
@@ -319,7 +409,7 @@ void tc_linear_forward(float* y, const float* x, const float* W, const float* b,
     TcArgs a{};
     a.C = y; a.M = m; a.N = l; a.K = n; a.ldc = l; a.bias = b; a.act = act;
     const CUtensorMap ta = make_map(x, m, n, kTcBK, kTcBM);        // A K-major
-    const CUtensorMap tb = make_map(W, l, n, kTcBK, kTcBN);        // B K-major
+    const CUtensorMap tb = make_map(W, l, n, kTcBK, kTcBN / tc_cluster());   // B K-major (half tile per CTA under multicast)
     launch_tc<kTcBN, false, false, kTcFwd>(ta, tb, a, dim3(div_up(l, kTcBN), div_up(m, kTcBM), 1));
 }
 
