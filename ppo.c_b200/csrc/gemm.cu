@@ -207,28 +207,37 @@ colsum_kernel(float* __restrict__ gb_part, size_t stride, const float* __restric
 }
 
 // Skinny dW (+db): one side of the layer is <= 32 wide (first layer of a low-dimensional env: n = S; value / action
-// heads: l <= 8).  gW[j][k] = sum_r g[r][j] * x[r][k].  The WIDE side is spread over threads (64 consecutive columns
-// per CTA, coalesced), the SMALL side lives in registers; rows are split over 4 row lanes per CTA and `splits` CTAs.
-// A 64x64 tile kernel would run these layers at a few percent utilisation (17 of 64 columns live).
+// heads: l <= 8).  gW[j][k] = sum_r g[r][j] * x[r][k].  The WIDE side is spread over threads (4 consecutive columns
+// per thread, 256 per CTA, 128-bit coalesced loads), the SMALL side is staged in shared memory and broadcast; each
+// broadcast LDS.128 feeds 16 FFMAs (4 columns x 4 small values) - with one column per thread the kernel was bound by
+// shared-memory wavefronts at 9% of the FFMA rate.  Rows are split over 4 row lanes per CTA, `splits` slabs and
+// gridDim.z extra row splits whose partials land in scratch and are folded in order by skinny_dw_fold_kernel.
 //   WIDE_IS_L = true : wide = g columns (l), small = x columns (n <= 32); also emits db (column sums of g)
 //   WIDE_IS_L = false: wide = x columns (n), small = g columns (l <= 32)
 template <int SP, bool WIDE_IS_L>     // SP = padded small width (multiple of 4)
 __global__ void __launch_bounds__(256)
-skinny_dw_kernel(float* __restrict__ gW_part, float* __restrict__ gb_part, size_t stride, const float* __restrict__ g,
-                 const float* __restrict__ x, int m, int n, int l, int rows_per_split) {
-    constexpr int CH = 64;                                   // rows staged per chunk
+skinny_dw_kernel(float* __restrict__ part, const float* __restrict__ g, const float* __restrict__ x, int m, int n, int l,
+                 int rows_per_split, float* __restrict__ gW_part, float* __restrict__ gb_part, size_t stride) {
+    constexpr int CH = 32;                                   // rows staged per chunk
     __shared__ __align__(16) float sm[CH][SP];
-    __shared__ float red[3][64][SP + 1];
+    __shared__ float red[64][4 * SP + 4];
     const int cx = threadIdx.x & 63, q = threadIdx.x >> 6;   // q = row lane 0..3
     const int wide_n = WIDE_IS_L ? l : n, small_n = WIDE_IS_L ? n : l;
     const float* wide = WIDE_IS_L ? g : x;
     const float* small = WIDE_IS_L ? x : g;
-    const int col = blockIdx.x * 64 + cx;
-    const bool live = col < wide_n;
-    const int r0 = blockIdx.y * rows_per_split, r1 = min(m, r0 + rows_per_split);
-    float acc[SP], bsum = 0.f;
+    const int col = blockIdx.x * 256 + 4 * cx;
+    const bool vec = (wide_n & 3) == 0 && col + 3 < wide_n && (((uintptr_t)wide) & 15) == 0;
+    const int R = gridDim.z;
+    const int sub = (rows_per_split + R - 1) / R;
+    const int s0 = blockIdx.y * rows_per_split;
+    const int r0 = s0 + blockIdx.z * sub, r1 = min(min(m, s0 + rows_per_split), r0 + sub);
+    float acc[4][SP], bsum[4];
 #pragma unroll
-    for (int k = 0; k < SP; k++) acc[k] = 0.f;
+    for (int c = 0; c < 4; c++) {
+        bsum[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < SP; k++) acc[c][k] = 0.f;
+    }
     for (int c0 = r0; c0 < r1; c0 += CH) {
         const int rows = min(CH, r1 - c0);
         __syncthreads();
@@ -237,44 +246,105 @@ skinny_dw_kernel(float* __restrict__ gW_part, float* __restrict__ gb_part, size_
             sm[r][k] = (r < rows && k < small_n) ? small[(size_t)(c0 + r) * small_n + k] : 0.f;
         }
         __syncthreads();
-        float wv[CH / 4];
+        float4 wv[CH / 4];
 #pragma unroll
         for (int i = 0; i < CH / 4; i++) {
             const int r = 4 * i + q;
-            wv[i] = (live && r < rows) ? __ldg(wide + (size_t)(c0 + r) * wide_n + col) : 0.f;
+            wv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) {
+                const float* wp = wide + (size_t)(c0 + r) * wide_n + col;
+                if (vec) wv[i] = __ldg(reinterpret_cast<const float4*>(wp));
+                else {
+                    if (col + 0 < wide_n) wv[i].x = wp[0];
+                    if (col + 1 < wide_n) wv[i].y = wp[1];
+                    if (col + 2 < wide_n) wv[i].z = wp[2];
+                    if (col + 3 < wide_n) wv[i].w = wp[3];
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < CH / 4; i++) {
             const int r = 4 * i + q;
-            bsum += wv[i];
+            const float w4[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) bsum[c] += w4[c];
 #pragma unroll
             for (int k4 = 0; k4 < SP / 4; k4++) {
                 const float4 sv = *reinterpret_cast<const float4*>(&sm[r][4 * k4]);
-                acc[4 * k4 + 0] = fmaf(wv[i], sv.x, acc[4 * k4 + 0]);
-                acc[4 * k4 + 1] = fmaf(wv[i], sv.y, acc[4 * k4 + 1]);
-                acc[4 * k4 + 2] = fmaf(wv[i], sv.z, acc[4 * k4 + 2]);
-                acc[4 * k4 + 3] = fmaf(wv[i], sv.w, acc[4 * k4 + 3]);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    acc[c][4 * k4 + 0] = fmaf(w4[c], sv.x, acc[c][4 * k4 + 0]);
+                    acc[c][4 * k4 + 1] = fmaf(w4[c], sv.y, acc[c][4 * k4 + 1]);
+                    acc[c][4 * k4 + 2] = fmaf(w4[c], sv.z, acc[c][4 * k4 + 2]);
+                    acc[c][4 * k4 + 3] = fmaf(w4[c], sv.w, acc[c][4 * k4 + 3]);
+                }
             }
         }
     }
-    __syncthreads();
-    if (q > 0) {
+    // row lanes 1..3 hand their partials to lane 0 one after the other (fixed order, one staging buffer)
+    for (int src = 1; src < 4; src++) {
+        __syncthreads();
+        if (q == src) {
 #pragma unroll
-        for (int k = 0; k < SP; k++) red[q - 1][cx][k] = acc[k];
-        red[q - 1][cx][SP] = bsum;
-    }
-    __syncthreads();
-    if (q == 0 && live) {
-        float* outW = gW_part + (size_t)blockIdx.y * stride;
+            for (int c = 0; c < 4; c++) {
 #pragma unroll
-        for (int k = 0; k < SP; k++) {
-            const float t = ((acc[k] + red[0][cx][k]) + red[1][cx][k]) + red[2][cx][k];
-            if (k < small_n) {
-                if (WIDE_IS_L) outW[(size_t)col * n + k] = t;      // gW[j = col][k]
-                else outW[(size_t)k * n + col] = t;                // gW[j = k][col]
+                for (int k = 0; k < SP; k++) red[cx][c * SP + k] = acc[c][k];
+                red[cx][4 * SP + c] = bsum[c];
             }
         }
-        if (WIDE_IS_L) gb_part[(size_t)blockIdx.y * stride + col] = ((bsum + red[0][cx][SP]) + red[1][cx][SP]) + red[2][cx][SP];
+        __syncthreads();
+        if (q == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+#pragma unroll
+                for (int k = 0; k < SP; k++) acc[c][k] += red[cx][c * SP + k];
+                bsum[c] += red[cx][4 * SP + c];
+            }
+        }
+    }
+    if (q == 0 && R == 1) {
+        // no extra row split: straight into the gradient slab
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (col + c >= wide_n) continue;
+#pragma unroll
+            for (int k = 0; k < SP; k++)
+                if (k < small_n) {
+                    if (WIDE_IS_L) gW_part[(size_t)blockIdx.y * stride + (size_t)(col + c) * n + k] = acc[c][k];
+                    else gW_part[(size_t)blockIdx.y * stride + (size_t)k * n + col + c] = acc[c][k];
+                }
+            if (WIDE_IS_L) gb_part[(size_t)blockIdx.y * stride + col + c] = bsum[c];
+        }
+    } else if (q == 0) {
+        // partial layout: [slab y][z][wide_n][SP + 1]  (last entry of a row = column sum of the wide array)
+        float* out = part + ((size_t)(blockIdx.y * R + blockIdx.z) * wide_n) * (SP + 1);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (col + c >= wide_n) continue;
+            float* o = out + (size_t)(col + c) * (SP + 1);
+#pragma unroll
+            for (int k = 0; k < SP; k++) o[k] = acc[c][k];
+            o[SP] = bsum[c];
+        }
+    }
+}
+
+// Fold the R row-split partials of every slab in order and scatter into the gradient slab layout.
+__global__ void __launch_bounds__(256)
+skinny_dw_fold_kernel(float* __restrict__ gW_part, float* __restrict__ gb_part, size_t stride, const float* __restrict__ part,
+                      int R, int wide_n, int small_n, int sp1, int n, int wide_is_l) {
+    const int slab = blockIdx.y;
+    const int total = wide_n * sp1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int col = e / sp1, k = e - col * sp1;
+        float t = 0.f;
+        for (int z = 0; z < R; z++) t += part[((size_t)(slab * R + z) * wide_n + col) * sp1 + k];
+        if (k < small_n) {
+            if (wide_is_l) gW_part[(size_t)slab * stride + (size_t)col * n + k] = t;    // gW[j = col][k]
+            else gW_part[(size_t)slab * stride + (size_t)k * n + col] = t;              // gW[j = k][col]
+        } else if (k == sp1 - 1 && wide_is_l) {
+            gb_part[(size_t)slab * stride + col] = t;
+        }
     }
 }
 
@@ -340,19 +410,29 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
         B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
         return;
     }
-    if (m >= 1024 && n <= 32 && l >= 64) {          // narrow input layer: wide side = l, also emits db
-        dim3 gs(div_up(l, 64), splits, 1);
-        if (n <= 8) B200_LAUNCH((skinny_dw_kernel<8, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
-        else if (n <= 16) B200_LAUNCH((skinny_dw_kernel<16, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
-        else if (n <= 24) B200_LAUNCH((skinny_dw_kernel<24, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
-        else B200_LAUNCH((skinny_dw_kernel<32, true>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
-        return;
-    }
-    if (m >= 1024 && l <= 8 && n >= 64) {           // value / action heads: wide side = n; db is a tiny column sum
-        dim3 gs(div_up(n, 64), splits, 1);
-        B200_LAUNCH((skinny_dw_kernel<8, false>), gs, 256, 0, gW_part, gb_part, stride, g, x, m, n, l, rows);
-        dim3 grid2(div_up(l, 32), splits, 1);
-        B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+    const bool narrow_in = m >= 1024 && n <= 32 && l >= 64;      // first layer of a low-dimensional env: wide side = l (+ db)
+    const bool narrow_out = m >= 1024 && l <= 8 && n >= 64;      // value / action heads: wide side = n
+    if (narrow_in || narrow_out) {
+        const int wide_n = narrow_in ? l : n, small_n = narrow_in ? n : l;
+        const int sp = narrow_in ? (n <= 8 ? 8 : n <= 16 ? 16 : n <= 24 ? 24 : 32) : 8;
+        const int gx = div_up(wide_n, 256);
+        const int R = m <= 16384 ? 1 : std::max(1, std::min(16, div_up(2 * num_sms(), gx * splits)));     // ~2 CTAs per SM
+        float* part = static_cast<float*>(scratch(kScratchPartials, (size_t)splits * R * wide_n * (sp + 1) * sizeof(float)));
+        dim3 gs(gx, splits, R);
+        if (narrow_in) {
+            if (sp == 8) B200_LAUNCH((skinny_dw_kernel<8, true>), gs, 256, 0, part, g, x, m, n, l, rows, gW_part, gb_part, stride);
+            else if (sp == 16) B200_LAUNCH((skinny_dw_kernel<16, true>), gs, 256, 0, part, g, x, m, n, l, rows, gW_part, gb_part, stride);
+            else if (sp == 24) B200_LAUNCH((skinny_dw_kernel<24, true>), gs, 256, 0, part, g, x, m, n, l, rows, gW_part, gb_part, stride);
+            else B200_LAUNCH((skinny_dw_kernel<32, true>), gs, 256, 0, part, g, x, m, n, l, rows, gW_part, gb_part, stride);
+        } else {
+            B200_LAUNCH((skinny_dw_kernel<8, false>), gs, 256, 0, part, g, x, m, n, l, rows, gW_part, gb_part, stride);
+        }
+        dim3 gf(std::max(1, std::min(32, div_up(wide_n * (sp + 1), 256))), splits, 1);
+        if (R > 1) B200_LAUNCH(skinny_dw_fold_kernel, gf, 256, 0, gW_part, gb_part, stride, part, R, wide_n, small_n, sp + 1, n, narrow_in ? 1 : 0);
+        if (narrow_out) {            // db of a <= 8 wide head: tiny column sum
+            dim3 grid2(div_up(l, 32), splits, 1);
+            B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+        }
         return;
     }
     GemmArgs a{};
