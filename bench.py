@@ -8,7 +8,8 @@ Workloads = BASELINE.json configs:
        one PPO iteration: fused device rollout (819 200 env-steps/GPU) + GAE + 10 value + 4 policy
        epochs of minibatch 16 384 (the reference schedule, src/main.c:33-43).  Unit: env-steps/s.
   c3 (configs[2])  HalfCheetah-shaped synthetic buffer (S=17, A=6), T=2048 x N=512 per GPU, 2x256 ReLU,
-       update only (GAE + 10 value + 4 policy epochs, minibatch 4096/GPU).  Unit: update samples/s.
+       update only (GAE + 10 value + 4 policy epochs, minibatch 65536/GPU; --mb 4096 for the small-minibatch line).
+       Unit: update samples/s.
   c4 (configs[3])  3x1024 actor-critic, minibatch 65 536/GPU, TF32 tcgen05 GEMMs, 262 144-sample
        synthetic buffer, update only.  Unit: update samples/s; roofline against tensor peak.
   c5 (configs[4])  GAE/returns sweep, T=2048 x N=65 536 per GPU, synthetic r/v/v'/flags.  Unit:
@@ -302,7 +303,7 @@ class UpdateOnly(Workload):
 class C3(UpdateOnly):
     name = "c3"
     SIZES, ACTS = [17, 256, 256, 6], ["relu", "relu", "none"]
-    T, N, MB = 2048, 512, 4096
+    T, N, MB = 2048, 512, 65536          # --mb 4096 gives the small-minibatch (launch-bound) line, profiles/r01_bench_c3_mb4096.json
 
     def config(self):
         return self.base_config("c3: HalfCheetah-shaped synthetic rollout buffer (S=17, A=6), T=2048 x N=512 per GPU, 2x256 ReLU "
@@ -713,7 +714,8 @@ def build_roofline(kernels, work, traffic_file=None):
             bound = "tensor"
         else:
             ach, peak, unit = amount / sec / 1e12, FP32_PEAK_TFLOPS, "TFLOP/s"
-            psrc = "nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)"
+            psrc = ("nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json); "
+                    "register-operand FFMA tiles measure 31 TFLOP/s on this part (profiles/NOTES.md)")
         out[prefix] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                        "launches": agg[prefix]["launches"], "avg_us": 1e3 * agg[prefix]["total_ms"] / agg[prefix]["launches"],
                        "peak_source": psrc}
