@@ -427,6 +427,12 @@ __device__ __forceinline__ void t64_stamp(const FusedArgs& p, int slot) {
     }
 }
 
+// Packed fp32 FMA (FFMA2): two lanes of a register pair per instruction.  Measured on B200 (profiles/NOTES.md): an 8x4
+// register tile of scalar 3-register FFMAs sustains 48 TFLOP/s, the same tile with FFMA2 65 TFLOP/s.  Each element is
+// still one fma.rn, so results are bit-identical to the scalar form.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
+
 __device__ __forceinline__ void t64_load8(const float* base, float (&a)[8]) {
     const float4 a0 = *reinterpret_cast<const float4*>(base);
     const float4 a1 = *reinterpret_cast<const float4*>(base + 32);
@@ -454,37 +460,39 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
     if (split) {
         const int kh = (n_in + 1) >> 1;
         const int k0 = g ? kh : 0, k1 = g ? n_in : kh;
-        float acc[8][4];
+        float2 acc[4][4];                   // [row pair][col]: rows (4tr, 4tr+1), (4tr+2, 4tr+3), (32+4tr, ..), (32+4tr+2, ..)
 #pragma unroll
-        for (int r = 0; r < 8; r++)
+        for (int r = 0; r < 4; r++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+            for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
         if (live) {
             const float* xp = Xt + 4 * tr;
             const float* wp = Wt + 4 * tc;
 #pragma unroll 2
             for (int k = k0; k < k1; k++) {
-                float a[8];
-                t64_load8(xp + k * kT64TMP, a);
+                const float4 a0 = *reinterpret_cast<const float4*>(xp + k * kT64TMP);
+                const float4 a1 = *reinterpret_cast<const float4*>(xp + k * kT64TMP + 32);
                 const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
+                const float2 ap[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
                 const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int r = 0; r < 8; r++)
+                for (int r = 0; r < 4; r++)
 #pragma unroll
-                    for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
+                    for (int c = 0; c < 4; c++) acc[r][c] = ffma2(ap[r], bcast2(wv[c]), acc[r][c]);
             }
-            // pass the other group's quad: group 0 sends rows 32+4tr.. (acc[4..7]), group 1 sends rows 4tr.. (acc[0..3])
+            // pass the other group's quad: group 0 sends rows 32+4tr.. (pairs 2,3), group 1 sends rows 4tr.. (pairs 0,1)
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 float* dst = xch + (4 * tc + c) * kT64TMP + 4 * tr + (g ? 0 : 32);
-                *reinterpret_cast<float4*>(dst) = g ? make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c])
-                                                    : make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+                *reinterpret_cast<float4*>(dst) = g ? make_float4(acc[0][c].x, acc[0][c].y, acc[1][c].x, acc[1][c].y)
+                                                    : make_float4(acc[2][c].x, acc[2][c].y, acc[3][c].x, acc[3][c].y);
             }
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) mine[r][c] = g ? acc[4 + r][c] : acc[r][c];
+        for (int c = 0; c < 4; c++) {
+            const float2 lo = g ? acc[2][c] : acc[0][c], hi = g ? acc[3][c] : acc[1][c];
+            mine[0][c] = lo.x; mine[1][c] = lo.y; mine[2][c] = hi.x; mine[3][c] = hi.y;
+        }
     } else {
 #pragma unroll
         for (int r = 0; r < 4; r++)
@@ -568,11 +576,11 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
                                                    int act_prev, int lt) {
     const int tr = lt & 7, tc = lt >> 3;
     if (tc >= pad4(n_in)) return;
-    float acc[8][4];
+    float2 acc[4][4];                       // [row pair][k column]
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+    for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+        for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
     const float* wrow[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) wrow[c] = Wt + (size_t)min(tc + 16 * c, n_in - 1) * ldw;
@@ -588,12 +596,13 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
         }
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
-            float g[8];
-            t64_load8(gp + (j0 + jj) * kT64TMP, g);
+            const float4 g0 = *reinterpret_cast<const float4*>(gp + (j0 + jj) * kT64TMP);
+            const float4 g1 = *reinterpret_cast<const float4*>(gp + (j0 + jj) * kT64TMP + 32);
+            const float2 gq[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int r = 0; r < 4; r++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[r][c] = fmaf(g[r], wv[c][jj], acc[r][c]);
+                for (int c = 0; c < 4; c++) acc[r][c] = ffma2(gq[r], bcast2(wv[c][jj]), acc[r][c]);
         }
     }
 #pragma unroll
@@ -602,8 +611,9 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
         if (k >= pad4(n_in)) continue;
         float h[8], o[8];
         t64_load8(Ht + k * kT64TMP + 4 * tr, h);
+        const float av[8] = {acc[0][c].x, acc[0][c].y, acc[1][c].x, acc[1][c].y, acc[2][c].x, acc[2][c].y, acc[3][c].x, acc[3][c].y};
 #pragma unroll
-        for (int r = 0; r < 8; r++) o[r] = (k < n_in) ? act_grad(h[r], acc[r][c], act_prev) : 0.f;
+        for (int r = 0; r < 8; r++) o[r] = (k < n_in) ? act_grad(h[r], av[r], act_prev) : 0.f;
         t64_store8(Gout + k * kT64TMP + 4 * tr, o);
     }
 }
@@ -615,11 +625,11 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
                                                      float* __restrict__ gW, int n_in, int n_out, int lt) {
     const int tk = lt & 7, tj = lt >> 3;
     if ((tj & ~3) >= n_out) return;          // warp-uniform: this warp owns no valid output row
-    float acc[JJ][KK];
+    float2 acc[JJ][KK];                     // (sum over even rows, sum over odd rows): both FFMA2 operands are natural pairs
 #pragma unroll
     for (int a = 0; a < JJ; a++)
 #pragma unroll
-        for (int b = 0; b < KK; b++) acc[a][b] = 0.f;
+        for (int b = 0; b < KK; b++) acc[a][b] = make_float2(0.f, 0.f);
     int jrow[JJ], krow[KK];
 #pragma unroll
     for (int a = 0; a < JJ; a++) jrow[a] = min(tj + 16 * a, n_out - 1) * kT64TMP;
@@ -636,10 +646,8 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
         for (int a = 0; a < JJ; a++)
 #pragma unroll
             for (int b = 0; b < KK; b++) {
-                acc[a][b] = fmaf(g[a].x, x[b].x, acc[a][b]);
-                acc[a][b] = fmaf(g[a].y, x[b].y, acc[a][b]);
-                acc[a][b] = fmaf(g[a].z, x[b].z, acc[a][b]);
-                acc[a][b] = fmaf(g[a].w, x[b].w, acc[a][b]);
+                acc[a][b] = ffma2(make_float2(g[a].x, g[a].y), make_float2(x[b].x, x[b].y), acc[a][b]);
+                acc[a][b] = ffma2(make_float2(g[a].z, g[a].w), make_float2(x[b].z, x[b].w), acc[a][b]);
             }
     }
 #pragma unroll
@@ -649,7 +657,7 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
 #pragma unroll
         for (int b = 0; b < KK; b++) {
             const int k = tk + 8 * b;
-            if (k < n_in) gW[(size_t)j * n_in + k] = acc[a][b];
+            if (k < n_in) gW[(size_t)j * n_in + k] = acc[a][b].x + acc[a][b].y;
         }
     }
 }
