@@ -134,6 +134,157 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs p) {
     }
 }
 
+// ---- 128x128x16 tile, 8x8 outputs per thread, 128-bit global loads, packed FFMA2 -------------------------------
+// The large-batch path of the fp32 layers (C3: 2x256 at minibatch 65536).  Same operand conventions and epilogues as
+// sgemm_kernel; requires 16-byte aligned operands with leading dimensions that are multiples of 4 (host-checked).
+// Per k each thread issues 4 LDS.128 (8 row values + 8 column values) for 32 FFMA2 = 64 FMAs: 4 FMAs per loaded
+// float, the ratio at which the 128 B/clk shared-memory pipe no longer bounds the FFMA pipe (see fused_mlp.cu).
+// Thread (tx, ty): columns {4tx..4tx+3} U {64+4tx..}, rows {4ty..4ty+3} U {64+4ty..}.
+constexpr int kTM = 128, kTN = 128, kTK = 16, kTPad = 4;
+__device__ __forceinline__ float2 ffma2g(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) sgemm128_kernel(const GemmArgs p) {
+    __shared__ __align__(16) float As[2][kTK][kTM + kTPad];
+    __shared__ __align__(16) float Bs[2][kTK][kTN + kTPad];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+    int kbeg = 0, kend = p.K;
+    if (MODE == kBwdParam) {
+        kbeg = blockIdx.z * p.k_per_split;
+        kend = min(p.K, kbeg + p.k_per_split);
+    }
+    constexpr bool A_KCONTIG = (MODE != kBwdParam);
+    constexpr bool B_KCONTIG = (MODE == kFwd);
+
+    float4 ra[2], rb[2];
+    // one operand tile = 512 float4 chunks, two per thread
+    auto load_op = [&](const float* base, int ld, int o0, int olim, bool kcontig, int k0, float4 (&r)[2]) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int e = tid + 256 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kcontig) {                       // [o][k]: chunk = (o = e >> 2, k offset 4 * (e & 3))
+                const int o = o0 + (e >> 2), gk = k0 + 4 * (e & 3);
+                if (o < olim) {
+                    const float* src = base + (size_t)o * ld + gk;
+                    if (gk + 3 < kend) v = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        if (gk + 0 < kend) v.x = src[0];
+                        if (gk + 1 < kend) v.y = src[1];
+                        if (gk + 2 < kend) v.z = src[2];
+                    }
+                }
+            } else {                             // [k][o]: chunk = (k = e >> 5, o offset 4 * (e & 31))
+                const int gk = k0 + (e >> 5), o = o0 + 4 * (e & 31);
+                if (gk < kend) {
+                    const float* src = base + (size_t)gk * ld + o;
+                    if (o + 3 < olim) v = __ldg(reinterpret_cast<const float4*>(src));
+                    else {
+                        if (o + 0 < olim) v.x = src[0];
+                        if (o + 1 < olim) v.y = src[1];
+                        if (o + 2 < olim) v.z = src[2];
+                    }
+                }
+            }
+            r[q] = v;
+        }
+    };
+    auto store_op = [&](float (*S)[kTM + kTPad], bool kcontig, const float4 (&r)[2]) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int e = tid + 256 * q;
+            if (kcontig) {
+                const int o = e >> 2, kk = 4 * (e & 3);
+                S[kk + 0][o] = r[q].x; S[kk + 1][o] = r[q].y; S[kk + 2][o] = r[q].z; S[kk + 3][o] = r[q].w;
+            } else {
+                *reinterpret_cast<float4*>(&S[e >> 5][4 * (e & 31)]) = r[q];
+            }
+        }
+    };
+
+    float2 acc[8][4];                            // [row][column pair]
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
+
+    const int ntiles = (kend - kbeg + kTK - 1) / kTK;
+    if (ntiles > 0) {
+        load_op(p.A, p.lda, m0, p.M, A_KCONTIG, kbeg, ra);
+        load_op(p.B, p.ldb, n0, p.N, B_KCONTIG, kbeg, rb);
+        store_op(As[0], A_KCONTIG, ra);
+        store_op(Bs[0], B_KCONTIG, rb);
+    }
+    __syncthreads();
+    for (int t = 0; t < ntiles; t++) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) {
+            load_op(p.A, p.lda, m0, p.M, A_KCONTIG, kbeg + (t + 1) * kTK, ra);
+            load_op(p.B, p.ldb, n0, p.N, B_KCONTIG, kbeg + (t + 1) * kTK, rb);
+        }
+#pragma unroll
+        for (int k = 0; k < kTK; k++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][4 * ty]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + 4 * ty]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][4 * tx]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + 4 * tx]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = ffma2g(make_float2(av[r], av[r]), bp[c], acc[r][c]);
+        }
+        if (t + 1 < ntiles) {
+            store_op(As[buf ^ 1], A_KCONTIG, ra);
+            store_op(Bs[buf ^ 1], B_KCONTIG, rb);
+        }
+        __syncthreads();
+    }
+
+    float* C = p.C + (MODE == kBwdParam ? (size_t)blockIdx.z * p.c_split_stride : 0);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int gi = m0 + (r < 4 ? 4 * ty + r : 64 + 4 * ty + (r - 4));
+        if (gi >= p.M) continue;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int gj = n0 + 64 * h + 4 * tx;
+            float v[4] = {acc[r][2 * h].x, acc[r][2 * h].y, acc[r][2 * h + 1].x, acc[r][2 * h + 1].y};
+            if (gj + 3 < p.N && (p.ldc & 3) == 0) {
+                if (MODE == kFwd) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gj));
+                    v[0] = act_apply(v[0] + b.x, p.act); v[1] = act_apply(v[1] + b.y, p.act);
+                    v[2] = act_apply(v[2] + b.z, p.act); v[3] = act_apply(v[3] + b.w, p.act);
+                } else if (MODE == kBwdInput && p.act != kActNone) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(p.xin + (size_t)gi * p.N + gj));
+                    v[0] = act_grad(x.x, v[0], p.act); v[1] = act_grad(x.y, v[1], p.act);
+                    v[2] = act_grad(x.z, v[2], p.act); v[3] = act_grad(x.w, v[3], p.act);
+                }
+                *reinterpret_cast<float4*>(C + (size_t)gi * p.ldc + gj) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (gj + c >= p.N) continue;
+                    float val = v[c];
+                    if (MODE == kFwd) val = act_apply(val + p.bias[gj + c], p.act);
+                    else if (MODE == kBwdInput && p.act != kActNone) val = act_grad(p.xin[(size_t)gi * p.N + gj + c], val, p.act);
+                    C[(size_t)gi * p.ldc + gj + c] = val;
+                }
+            }
+        }
+    }
+}
+
+static bool big_tile_ok(const GemmArgs& a, int splits = 1) {
+    auto al16 = [](const void* q) { return (((uintptr_t)q) & 15) == 0; };
+    // 128x128 tiles pay off only when they still fill the machine (at least one CTA per SM)
+    if ((long long)div_up(a.M, kTM) * div_up(a.N, kTN) * splits < num_sms()) return false;
+    return a.M >= 128 && a.N >= 128 && a.K >= 64 && (a.lda & 3) == 0 && (a.ldb & 3) == 0 && al16(a.A) && al16(a.B) &&
+           (a.xin == nullptr || (al16(a.xin) && (a.N & 3) == 0)) && (a.bias == nullptr || al16(a.bias));
+}
+
 // Skinny forward for l <= 8 outputs (value head l=1, action heads): one warp per row, lanes split k.
 __global__ void __launch_bounds__(256)
 linear_forward_skinny_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ W,
@@ -385,6 +536,11 @@ void linear_forward(float* y, const float* x, const float* W, const float* b, in
     GemmArgs a{};
     a.A = x; a.B = W; a.C = y; a.M = m; a.N = l; a.K = n; a.lda = n; a.ldb = n; a.ldc = l;
     a.bias = b; a.act = act;
+    if (big_tile_ok(a)) {
+        dim3 gridb(div_up(l, kTN), div_up(m, kTM), 1);
+        B200_LAUNCH(sgemm128_kernel<kFwd>, gridb, 256, 0, a);
+        return;
+    }
     dim3 grid(div_up(l, kBN), div_up(m, kBM), 1);
     B200_LAUNCH(sgemm_kernel<kFwd>, grid, 256, 0, a);
 }
@@ -395,6 +551,11 @@ void linear_backward_input(float* gx, const float* g, const float* W, const floa
     GemmArgs a{};
     a.A = g; a.B = W; a.C = gx; a.M = m; a.N = n; a.K = l; a.lda = l; a.ldb = n; a.ldc = n;
     a.xin = xin; a.act = act_prev;
+    if (big_tile_ok(a)) {
+        dim3 gridb(div_up(n, kTN), div_up(m, kTM), 1);
+        B200_LAUNCH(sgemm128_kernel<kBwdInput>, gridb, 256, 0, a);
+        return;
+    }
     dim3 grid(div_up(n, kBN), div_up(m, kBM), 1);
     B200_LAUNCH(sgemm_kernel<kBwdInput>, grid, 256, 0, a);
 }
@@ -438,8 +599,13 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
     GemmArgs a{};
     a.A = g; a.B = x; a.C = gW_part; a.M = l; a.N = n; a.K = m; a.lda = l; a.ldb = n; a.ldc = n;
     a.k_per_split = rows; a.c_split_stride = stride;
-    dim3 grid(div_up(n, kBN), div_up(l, kBM), splits);
-    B200_LAUNCH(sgemm_kernel<kBwdParam>, grid, 256, 0, a);
+    if (big_tile_ok(a, splits) && ((stride & 3) == 0) && ((((uintptr_t)gW_part) & 15) == 0)) {
+        dim3 gridb(div_up(n, kTN), div_up(l, kTM), splits);
+        B200_LAUNCH(sgemm128_kernel<kBwdParam>, gridb, 256, 0, a);
+    } else {
+        dim3 grid(div_up(n, kBN), div_up(l, kBM), splits);
+        B200_LAUNCH(sgemm_kernel<kBwdParam>, grid, 256, 0, a);
+    }
     dim3 grid2(div_up(l, 32), splits, 1);
     B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
 }
