@@ -315,9 +315,13 @@ class C3(UpdateOnly):
         w_mu, w_v = mlp_weights(self.SIZES), mlp_weights(sv)
         steps_v, steps_p = self.N_VAL * nb, self.N_POL * nb
         S, H = self.SIZES[0], self.SIZES[1]
-        return {"sgemm_kernel<kFwd>": ("fp32", 2 * self.MB * (steps_v * w_v + steps_p * w_mu) + 2 * 2 * self.cap * w_v),
-                "sgemm_kernel<kBwdInput>": ("fp32", 2 * self.MB * (steps_v * (w_v - S * H) + steps_p * (w_mu - S * H))),
-                "sgemm_kernel<kBwdParam>": ("fp32", 2 * self.MB * (steps_v * w_v + steps_p * w_mu)),
+        A = self.SIZES[-1]
+        # keys are substrings of kernel names: "kernel<kFwd>" covers sgemm_kernel<kFwd> and sgemm128_kernel<kFwd>; the
+        # <= 8-wide heads run in linear_forward_skinny_kernel / skinny_dw_kernel and are left out of these FLOP counts
+        return {"kernel<kFwd>": ("fp32", 2 * self.MB * (steps_v * (w_v - H) + steps_p * (w_mu - H * A)) + 2 * 2 * self.cap * (w_v - H)),
+                "kernel<kBwdInput>": ("fp32", 2 * self.MB * (steps_v * (w_v - S * H) + steps_p * (w_mu - S * H))),
+                "kernel<kBwdParam>": ("fp32", 2 * self.MB * (steps_v * (w_v - H - S * H) + steps_p * (w_mu - H * A - S * H))),
+                "skinny_dw_kernel": ("fp32", 2 * self.MB * (steps_v * (H + S * H) + steps_p * (H * A + S * H))),
                 "gather_kernel": ("hbm", (steps_v + steps_p) * self.MB * (4 + 2 * 4 * (self.SIZES[0] + self.SIZES[-1] + 3))),
                 "adam_flat_kernel": ("hbm", 28.0 * (steps_v * mlp_params(sv) + steps_p * (mlp_params(self.SIZES) + self.SIZES[-1]))),
                 "gae_scan_kernel": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}

@@ -374,23 +374,26 @@ __global__ void __launch_bounds__(kR64Threads) rollout64_kernel(const Rollout64A
                 const float* wp = img + net.wt_off[l] + 4 * ug;
                 const int ldw = net.ldw[l];
                 const float4 b = *reinterpret_cast<const float4*>(img + net.bs_off[l] + 4 * ug);
-                float acc[4][4];
+                float2 acc2[4][2];               // [unit][env pair]: packed FFMA2
                 const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) acc[c][e] = bv[c];
+                for (int c = 0; c < 4; c++) { acc2[c][0] = make_float2(bv[c], bv[c]); acc2[c][1] = make_float2(bv[c], bv[c]); }
                 const float* xp = hin + 4 * eg;
 #pragma unroll 4
                 for (int k = 0; k < n_in; k++) {
                     const float4 a = *reinterpret_cast<const float4*>(xp + k * E);
                     const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
-                    const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+                    const float2 ap[2] = {make_float2(a.x, a.y), make_float2(a.z, a.w)};
+                    const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                    for (int c = 0; c < 4; c++)
-#pragma unroll
-                        for (int e = 0; e < 4; e++) acc[c][e] = fmaf(av[e], wv[c], acc[c][e]);
+                    for (int c = 0; c < 4; c++) {
+                        acc2[c][0] = __ffma2_rn(ap[0], make_float2(wv[c], wv[c]), acc2[c][0]);
+                        acc2[c][1] = __ffma2_rn(ap[1], make_float2(wv[c], wv[c]), acc2[c][1]);
+                    }
                 }
+                float acc[4][4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) { acc[c][0] = acc2[c][0].x; acc[c][1] = acc2[c][0].y; acc[c][2] = acc2[c][1].x; acc[c][3] = acc2[c][1].y; }
                 const int act = net.acts[l];
 #pragma unroll
                 for (int c = 0; c < 4; c++)

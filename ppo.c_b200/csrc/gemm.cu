@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs p) {
         }
     };
 
-    float acc[4][4];
+    float2 acc2[4][2];                       // [row][column pair]: packed FFMA2 (bit-identical to scalar fma.rn per element)
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+        for (int c = 0; c < 2; c++) acc2[r][c] = make_float2(0.f, 0.f);
 
     const int ntiles = (kend - kbeg + kBK - 1) / kBK;
     if (ntiles > 0) {
@@ -104,15 +104,19 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs p) {
         for (int k = 0; k < kBK; k++) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float2 bp[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
 #pragma unroll
             for (int r = 0; r < 4; r++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+                for (int c = 0; c < 2; c++) acc2[r][c] = __ffma2_rn(make_float2(av[r], av[r]), bp[c], acc2[r][c]);
         }
         if (t + 1 < ntiles) store_tiles(buf ^ 1);
         __syncthreads();
     }
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { acc[r][0] = acc2[r][0].x; acc[r][1] = acc2[r][0].y; acc[r][2] = acc2[r][1].x; acc[r][3] = acc2[r][1].y; }
 
     float* C = p.C + (MODE == kBwdParam ? (size_t)blockIdx.z * p.c_split_stride : 0);
 #pragma unroll
