@@ -45,7 +45,8 @@ struct TcArgs {
     const float* bias;      // kTcFwd
     const float* xin;       // kTcDx: post-activation input of the layer [M][N]
     int act;
-    int k_per_split;        // kTcDw: reduction rows per blockIdx.z
+    int k_per_split;        // kTcDw: reduction rows per split
+    int splits;             // kTcDw: number of split-K slabs
     size_t c_split_stride;
 };
 
@@ -154,163 +155,208 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTcStages * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + kTcStages;
-    uint64_t* tmem_full_bar = empty_bar + kTcStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + kTcStages;      // [2] accumulator buffer b holds a finished tile
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2] the epilogue warps have drained buffer b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
-    int kbeg = 0, kend = p.K;
-    if (EPI == kTcDw) { kbeg = blockIdx.z * p.k_per_split; kend = min(p.K, kbeg + p.k_per_split); }
-    const int num_kb = max(0, (kend - kbeg + kTcBK - 1) / kTcBK);
+    const uint32_t crank = CL > 1 ? tc_cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+
+    // ---- persistent tile schedule.  Work item w = (split z, M-tile group mg, N tile nt), nt fastest so that the N tiles of
+    // one A row block run back to back (L2 reuse of A).  A cluster walks items c, c + #clusters, ...; CTA `crank` of the
+    // cluster owns M tile mg * CL + crank of the item.
+    const int tiles_n = (p.N + BN - 1) / BN;
+    const int groups_m = ((p.M + kTcBM - 1) / kTcBM + CL - 1) / CL;
+    const int splits = (EPI == kTcDw) ? p.splits : 1;
+    const int n_items = tiles_n * groups_m * splits;
+    const int n_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
         for (int s = 0; s < kTcStages; s++) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], CL); }
-        tc_mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; b++) { tc_mbar_init(&tmem_full_bar[b], 1); tc_mbar_init(&tmem_empty_bar[b], kTcEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM allocation is warp-wide; BN fp32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    if (warp == 1) {   // TMEM allocation is warp-wide: two accumulator buffers of BN fp32 columns each (2 * 256 = all of TMEM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t crank = CL > 1 ? tc_cluster_ctarank() : 0u;
-    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     if (CL > 1) tc_cluster_sync();          // the peer's barriers are initialised before anything is multicast into them
+
+    auto item_coords = [&](int w, int& m0, int& n0, int& kbeg, int& kend, int& z) {
+        const int nt = w % tiles_n, rest = w / tiles_n;
+        const int mg = rest % groups_m;
+        z = rest / groups_m;
+        m0 = (mg * CL + (int)crank) * kTcBM;
+        n0 = nt * BN;
+        kbeg = 0; kend = p.K;
+        if (EPI == kTcDw) { kbeg = z * p.k_per_split; kend = min(p.K, kbeg + p.k_per_split); }
+    };
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % kTcStages;
-                const uint32_t phase = (kb / kTcStages) & 1;
-                tc_mbar_wait(&empty_bar[s], phase ^ 1);
-                uint8_t* sa = smem + s * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                tc_mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                const int k0 = kbeg + kb * kTcBK;
-                if (!A_MN) {
-                    tc_tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                         // box {32 k, 128 rows}
-                } else {
-#pragma unroll
-                    for (int i = 0; i < kTcBM / 32; i++)                                        // box {32 mn, 32 k-rows}
-                        tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + 32 * i, k0, &full_bar[s]);
-                }
-                if (CL == 1) {
-                    if (!B_MN) {
-                        tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
+            uint32_t it = 0;                                     // ring position, runs across tiles
+            for (int w = cluster_id; w < n_items; w += n_clusters) {
+                int m0, n0, kbeg, kend, z;
+                item_coords(w, m0, n0, kbeg, kend, z);
+                const int num_kb = max(0, (kend - kbeg + kTcBK - 1) / kTcBK);
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % kTcStages;
+                    const uint32_t phase = (it / kTcStages) & 1;
+                    tc_mbar_wait(&empty_bar[s], phase ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    tc_mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    const int k0 = kbeg + kb * kTcBK;
+                    if (!A_MN) {
+                        tc_tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                         // box {32 k, 128 rows}
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BN / 32; i++)
-                            tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * i, k0, &full_bar[s]);
+                        for (int i = 0; i < kTcBM / 32; i++)                                        // box {32 mn, 32 k-rows}
+                            tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + 32 * i, k0, &full_bar[s]);
                     }
-                } else {                     // my half of the shared B tile, multicast to both CTAs of the cluster
-                    if (!B_MN) {             // box {32 k, BN/CL rows}
-                        constexpr int HR = BN / CL;
-                        tc_tma_load_2d_mc(sb + crank * (HR * kTcBKBytes), &tmB, k0, n0 + (int)crank * HR, &full_bar[s], kMask);
-                    } else {
-                        constexpr int HB = BN / 32 / CL;
+                    if (CL == 1) {
+                        if (!B_MN) {
+                            tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < HB; i++) {
-                            const int bi = (int)crank * HB + i;
-                            tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * bi, k0, &full_bar[s], kMask);
+                            for (int i = 0; i < BN / 32; i++)
+                                tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * i, k0, &full_bar[s]);
+                        }
+                    } else {                     // my half of the shared B tile, multicast to both CTAs of the cluster
+                        if (!B_MN) {             // box {32 k, BN/CL rows}
+                            constexpr int HR = BN / CL;
+                            tc_tma_load_2d_mc(sb + crank * (HR * kTcBKBytes), &tmB, k0, n0 + (int)crank * HR, &full_bar[s], kMask);
+                        } else {
+                            constexpr int HB = BN / 32 / CL;
+#pragma unroll
+                            for (int i = 0; i < HB; i++) {
+                                const int bi = (int)crank * HB + i;
+                                tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * bi, k0, &full_bar[s], kMask);
+                            }
                         }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (single thread) =====
+        // ===== MMA issuer (single thread): tile i accumulates into TMEM buffer i & 1 while the epilogue drains the other =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % kTcStages;
-                const uint32_t phase = (kb / kTcStages) & 1;
-                tc_mbar_wait(&full_bar[s], phase);
+            uint32_t it = 0, tile = 0;
+            for (int w = cluster_id; w < n_items; w += n_clusters, tile++) {
+                int m0, n0, kbeg, kend, z;
+                item_coords(w, m0, n0, kbeg, kend, z);
+                const int num_kb = max(0, (kend - kbeg + kTcBK - 1) / kTcBK);
+                const uint32_t buf = tile & 1;
+                tc_mbar_wait(&tmem_empty_bar[buf], ((tile >> 1) & 1) ^ 1);      // first use of each buffer passes immediately
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = s_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                const uint32_t tmem_acc = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % kTcStages;
+                    const uint32_t phase = (it / kTcStages) & 1;
+                    tc_mbar_wait(&full_bar[s], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = s_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < kTcBK / kTcUmmaK; k++) {
-                    // K-major: 8 rows x 128 B swizzle atoms, 1024 B apart; a k-step is 32 B inside the row.
-                    // MN-major: 32-element (128 B) MN chunks kTcBK*128 B apart (LBO), 4 k-rows = 512 B atoms (SBO);
-                    //           a k-step (8 k-rows) spans two atoms = 1024 B.
-                    const uint64_t da = A_MN ? tc_make_desc(sa + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sa + k * 32, 16, 1024, 2);
-                    const uint64_t db = B_MN ? tc_make_desc(sb + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sb + k * 32, 16, 1024, 2);
-                    tc_umma_tf32(tmem_base, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kTcBK / kTcUmmaK; k++) {
+                        // K-major: 8 rows x 128 B swizzle atoms, 1024 B apart; a k-step is 32 B inside the row.
+                        // MN-major: 32-element (128 B) MN chunks kTcBK*128 B apart (LBO), 4 k-rows = 512 B atoms (SBO);
+                        //           a k-step (8 k-rows) spans two atoms = 1024 B.
+                        const uint64_t da = A_MN ? tc_make_desc(sa + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sa + k * 32, 16, 1024, 2);
+                        const uint64_t db = B_MN ? tc_make_desc(sb + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sb + k * 32, 16, 1024, 2);
+                        tc_umma_tf32(tmem_acc, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (CL == 1) tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
+                    else tc_umma_commit_mc(&empty_bar[s], kMask);        // ... in both CTAs (each writes into the other's slot)
                 }
-                if (CL == 1) tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
-                else tc_umma_commit_mc(&empty_bar[s], kMask);        // ... in both CTAs (each writes into the other's slot)
+                tc_umma_commit(&tmem_full_bar[buf]);      // accumulator of this tile complete
             }
-            tc_umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
         // ===== epilogue warps: TMEM lane quadrant = warp % 4; warps 2..5 take columns [0, BN/2), warps 6..9 the rest =====
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        const int row = m0 + q * 32 + lane;
-        tc_mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* Crow = p.C + (EPI == kTcDw ? (size_t)blockIdx.z * p.c_split_stride : 0) + (size_t)row * p.ldc;
-        const bool rows_ok = row < p.M;
-        constexpr int CPW = BN / (kTcEpiWarps / 4);          // columns per warp
+        uint32_t tile = 0;
+        for (int w = cluster_id; w < n_items; w += n_clusters, tile++) {
+            int m0, n0, kbeg, kend, z;
+            item_coords(w, m0, n0, kbeg, kend, z);
+            const int num_kb = max(0, (kend - kbeg + kTcBK - 1) / kTcBK);
+            const uint32_t buf = tile & 1;
+            const int row = m0 + q * 32 + lane;
+            tc_mbar_wait(&tmem_full_bar[buf], (tile >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_acc = tmem_base + buf * BN;
+            float* Crow = p.C + (EPI == kTcDw ? (size_t)z * p.c_split_stride : 0) + (size_t)row * p.ldc;
+            const bool rows_ok = row < p.M;
+            constexpr int CPW = BN / (kTcEpiWarps / 4);          // columns per warp
 #pragma unroll 1
-        for (int c0 = half * CPW; c0 < (half + 1) * CPW; c0 += 32) {
-            const int nb = n0 + c0;
-            // the activation-derivative operand is fetched while the TMEM load is in flight
-            float4 hv[8];
-            const bool full32 = nb + 32 <= p.N;
-            const bool need_h = EPI == kTcDx && p.act != kActNone && rows_ok;
-            if (need_h && full32 && (p.N & 3) == 0) {
-                const float4* hrow4 = reinterpret_cast<const float4*>(p.xin + (size_t)row * p.N + nb);
+            for (int c0 = half * CPW; c0 < (half + 1) * CPW; c0 += 32) {
+                const int nb = n0 + c0;
+                // the activation-derivative operand is fetched while the TMEM load is in flight
+                float4 hv[8];
+                const bool full32 = nb + 32 <= p.N;
+                const bool need_h = EPI == kTcDx && p.act != kActNone && rows_ok;
+                if (need_h && full32 && (p.N & 3) == 0) {
+                    const float4* hrow4 = reinterpret_cast<const float4*>(p.xin + (size_t)row * p.N + nb);
 #pragma unroll
-                for (int j = 0; j < 8; j++) hv[j] = __ldg(hrow4 + j);
-            }
-            uint32_t r[32];
-            if (num_kb > 0) {
-                tc_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; j++) r[j] = 0u;
-            }
-            if (rows_ok) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-                if (EPI == kTcFwd) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (nb + j < p.N) v[j] = round_tf32(act_apply(v[j] + __ldg(p.bias + nb + j), p.act));
-                } else if (EPI == kTcDx) {
-                    if (need_h) {
-                        if (full32 && (p.N & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                v[4 * j + 0] = act_grad(hv[j].x, v[4 * j + 0], p.act);
-                                v[4 * j + 1] = act_grad(hv[j].y, v[4 * j + 1], p.act);
-                                v[4 * j + 2] = act_grad(hv[j].z, v[4 * j + 2], p.act);
-                                v[4 * j + 3] = act_grad(hv[j].w, v[4 * j + 3], p.act);
-                            }
-                        } else {
-                            const float* hrow = p.xin + (size_t)row * p.N + nb;
-#pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
+                    for (int j = 0; j < 8; j++) hv[j] = __ldg(hrow4 + j);
                 }
-                if (full32 && (p.ldc & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(Crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                uint32_t r[32];
+                if (num_kb > 0) {
+                    tc_tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (nb + j < p.N) Crow[nb + j] = v[j];
+                    for (int j = 0; j < 32; j++) r[j] = 0u;
+                }
+                if (c0 + 32 >= (half + 1) * CPW) {            // last TMEM read of this tile: hand the buffer back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_u32(&tmem_empty_bar[buf])) : "memory");
+                }
+                if (rows_ok) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                    if (EPI == kTcFwd) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (nb + j < p.N) v[j] = round_tf32(act_apply(v[j] + __ldg(p.bias + nb + j), p.act));
+                    } else if (EPI == kTcDx) {
+                        if (need_h) {
+                            if (full32 && (p.N & 3) == 0) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    v[4 * j + 0] = act_grad(hv[j].x, v[4 * j + 0], p.act);
+                                    v[4 * j + 1] = act_grad(hv[j].y, v[4 * j + 1], p.act);
+                                    v[4 * j + 2] = act_grad(hv[j].z, v[4 * j + 2], p.act);
+                                    v[4 * j + 3] = act_grad(hv[j].w, v[4 * j + 3], p.act);
+                                }
+                            } else {
+                                const float* hrow = p.xin + (size_t)row * p.N + nb;
+#pragma unroll
+                                for (int j = 0; j < 32; j++)
+                                    if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
+                    }
+                    if (full32 && (p.ldc & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(Crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (nb + j < p.N) Crow[nb + j] = v[j];
+                    }
                 }
             }
         }
@@ -319,7 +365,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
     }
     if (CL > 1) tc_cluster_sync();          // nobody leaves while the peer may still multicast / arrive into this CTA
 }
@@ -362,24 +408,27 @@ static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multi
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
-static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
+static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 tiles /* (N tiles, M tiles, splits) */) {
     const size_t smem = (size_t)kTcStages * (kTcBM + BN) * kTcBKBytes + 1024 /*align*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    // persistent: one CTA per SM (190 KB of shared memory each), clusters of CL CTAs walk the work items
+    const long long items = (long long)tiles.x * div_up(tiles.y, CL) * tiles.z;
+    const int clusters = (int)std::min<long long>(items, num_sms() / CL);
+    const dim3 grid(clusters * CL, 1, 1);
     if (CL == 1) {
         B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>), grid, kTcThreads, smem, ta, tb, a);
         return;
     }
-    grid.y = (grid.y + CL - 1) / CL * CL;     // a padding CTA runs the pipeline on zero-filled rows and stores nothing
     if (g_profiling) profile_mark("(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)", true);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = CL; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>, ta, tb, a));
     ++g_launches;
@@ -425,7 +474,7 @@ void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const
     TcArgs a{};
     int rows = div_up(m, splits);
     rows = div_up(rows, kTcBK) * kTcBK;
-    a.C = gW_part; a.M = l; a.N = n; a.K = m; a.ldc = n; a.k_per_split = rows; a.c_split_stride = stride;
+    a.C = gW_part; a.M = l; a.N = n; a.K = m; a.ldc = n; a.k_per_split = rows; a.c_split_stride = stride; a.splits = splits;
     const CUtensorMap ta = make_map(g, m, l, 32, kTcBK, true);     // A MN-major: g[k=batch][m'=out]
     const CUtensorMap tb = make_map(x, m, n, 32, kTcBK, true);     // B MN-major: x[k=batch][n=in]
     launch_tc<kTcBN, true, true, kTcDw>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
