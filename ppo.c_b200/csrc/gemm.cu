@@ -289,6 +289,81 @@ static bool big_tile_ok(const GemmArgs& a, int splits = 1) {
            (a.xin == nullptr || (al16(a.xin) && (a.N & 3) == 0)) && (a.bias == nullptr || al16(a.bias));
 }
 
+// Small-K dense layer: out[m][N] = epi(sum_{k < K} in[m][k] * Wk[k][N]), K <= 32 (first layer of a low-dimensional
+// env: K = S; dX of a <= 8 wide head: K = l).  Output-bandwidth bound (the 64x64 tile kernel spends its time on a
+// K padded to 16/32 and scalar stores).  CTA = 32 rows x 256 columns; thread = 8 rows x 4 columns; the K x 256 weight
+// slice is staged in shared memory (k-major), the 32 x K input block too (broadcast reads), stores are 128-bit.
+//   TRANS_W = true : Wk[k][j] = W[j * K + k]   (forward, W is [N][K] row-major)      epilogue: bias + activation
+//   TRANS_W = false: Wk[k][j] = W[k * N + j]   (dX, W is [K = l][N = n] row-major)   epilogue: activation' of xin
+template <bool TRANS_W>
+__global__ void __launch_bounds__(256)
+smallk_linear_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ W,
+                     const float* __restrict__ bias, const float* __restrict__ xin, int m, int K, int N, int act) {
+    __shared__ __align__(16) float Ws[32][256 + 4];
+    __shared__ float Xs[32][33];
+    const int tid = threadIdx.x;
+    constexpr int kRowsPerCta = 256;                 // 8 blocks of 32 rows share one staged weight slice
+    const int n0 = blockIdx.x * 256;
+    for (int e = tid; e < K * 256; e += 256) {
+        const int k = TRANS_W ? (e % K) : (e >> 8), j = TRANS_W ? (e / K) : (e & 255);
+        const int gj = n0 + j;
+        Ws[k][j] = gj < N ? (TRANS_W ? W[(size_t)gj * K + k] : W[(size_t)k * N + gj]) : 0.f;
+    }
+    const int tc = tid & 63, tr = tid >> 6;          // columns 4tc..4tc+3, rows tr*8..tr*8+7
+    const int gj = n0 + 4 * tc;
+    const bool vec = gj + 3 < N && (N & 3) == 0;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TRANS_W && vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + gj));
+    for (int m0 = blockIdx.y * kRowsPerCta; m0 < min(m, (int)(blockIdx.y + 1) * kRowsPerCta); m0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * K; e += 256) {
+            const int r = e / K, k = e - r * K;
+            Xs[r][k] = (m0 + r < m) ? in[(size_t)(m0 + r) * K + k] : 0.f;
+        }
+        __syncthreads();
+        float2 acc[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; r++) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
+        for (int k = 0; k < K; k++) {
+            const float4 w = *reinterpret_cast<const float4*>(&Ws[k][4 * tc]);
+            const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float x = Xs[tr * 8 + r][k];
+                acc[r][0] = __ffma2_rn(make_float2(x, x), w01, acc[r][0]);
+                acc[r][1] = __ffma2_rn(make_float2(x, x), w23, acc[r][1]);
+            }
+        }
+        if (gj >= N) continue;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int gi = m0 + tr * 8 + r;
+            if (gi >= m) continue;
+            float v[4] = {acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y};
+            if (vec) {
+                if (TRANS_W) {
+                    v[0] = act_apply(v[0] + b4.x, act); v[1] = act_apply(v[1] + b4.y, act);
+                    v[2] = act_apply(v[2] + b4.z, act); v[3] = act_apply(v[3] + b4.w, act);
+                } else if (act != kActNone) {
+                    const float4 h = __ldg(reinterpret_cast<const float4*>(xin + (size_t)gi * N + gj));
+                    v[0] = act_grad(h.x, v[0], act); v[1] = act_grad(h.y, v[1], act);
+                    v[2] = act_grad(h.z, v[2], act); v[3] = act_grad(h.w, v[3], act);
+                }
+                *reinterpret_cast<float4*>(out + (size_t)gi * N + gj) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (gj + c >= N) continue;
+                    float val = v[c];
+                    if (TRANS_W) val = act_apply(val + bias[gj + c], act);
+                    else if (act != kActNone) val = act_grad(xin[(size_t)gi * N + gj + c], val, act);
+                    out[(size_t)gi * N + gj + c] = val;
+                }
+            }
+        }
+    }
+}
+
 // Skinny forward for l <= 8 outputs (value head l=1, action heads): one warp per row, lanes split k.
 __global__ void __launch_bounds__(256)
 linear_forward_skinny_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ W,
@@ -537,6 +612,11 @@ void linear_forward(float* y, const float* x, const float* W, const float* b, in
         B200_LAUNCH(linear_forward_skinny_kernel, blocks, 256, 0, y, x, W, b, m, n, l, act);
         return;
     }
+    if (n <= 32 && l >= 64 && m >= 256) {
+        dim3 gk(div_up(l, 256), div_up(m, 256), 1);
+        B200_LAUNCH(smallk_linear_kernel<true>, gk, 256, 0, y, x, W, b, (const float*)nullptr, m, n, l, act);
+        return;
+    }
     GemmArgs a{};
     a.A = x; a.B = W; a.C = y; a.M = m; a.N = l; a.K = n; a.lda = n; a.ldb = n; a.ldc = l;
     a.bias = b; a.act = act;
@@ -552,6 +632,11 @@ void linear_forward(float* y, const float* x, const float* W, const float* b, in
 void linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev) {
     if (m <= 0) return;
     if (use_tc(m, n, l, g, W, l, n)) { tc_linear_backward_input(gx, g, W, xin, m, n, l, act_prev); return; }
+    if (l <= 32 && n >= 64 && m >= 256) {
+        dim3 gk(div_up(n, 256), div_up(m, 256), 1);
+        B200_LAUNCH(smallk_linear_kernel<false>, gk, 256, 0, gx, g, W, (const float*)nullptr, xin, m, l, n, act_prev);
+        return;
+    }
     GemmArgs a{};
     a.A = g; a.B = W; a.C = gx; a.M = m; a.N = n; a.K = l; a.lda = l; a.ldb = n; a.ldc = n;
     a.xin = xin; a.act = act_prev;
