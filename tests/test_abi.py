@@ -87,3 +87,28 @@ def test_reference_main_compiles_and_links_unmodified():
                            "-L", os.path.join(ROOT, "ppo.c_b200"), "-lppo_b200", "-lm",
                            "-Wl,-rpath," + os.path.join(ROOT, "ppo.c_b200")])
     assert os.path.exists(out)
+
+
+def _build_example():
+    b200.package().build()
+    out = os.path.join(ROOT, "build", "abi_probe", "pendulum_b200")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "pendulum_b200.c"), "-o", out,
+                           "-L", os.path.join(ROOT, "ppo.c_b200"), "-lppo_b200", "-lm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "ppo.c_b200")])
+    return out
+
+
+def test_c_example_compiles_against_the_boundary_headers():
+    """A plain-C caller (gcc, no nvcc, no CUDA headers) builds against include/ and links the C-ABI library."""
+    assert os.path.exists(_build_example())
+
+
+@pytest.mark.gpu
+def test_c_example_solves_pendulum():
+    """The C caller trains Pendulum-v1 through train_ppo_epoch on the device env and exits 0 iff the mean return of
+    some iteration exceeded -200 (the north star's "solved" threshold)."""
+    res = subprocess.run([_build_example(), "40", "4096"], capture_output=True, text=True, timeout=300)
+    print(res.stdout[-1500:])
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]

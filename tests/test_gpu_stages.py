@@ -259,6 +259,32 @@ def test_gather_vs_oracle(L, S, A, n, mb):
             assert np.array_equal(got.numpy(), want)
 
 
+@pytest.mark.parametrize("S,A,n,mb", [(40, 8, 300, 37), (3, 1, 9, 1), (64, 2, 1000, 1000)])
+def test_gather_wide_rows_and_odd_batches(L, S, A, n, mb):
+    """Packed rows wider than one warp (S + A + 3 > 32), minibatches that are not a multiple of the 8 rows a warp
+    takes per iteration, and the wrap-around of (offset + i) % limit (src/trajectory_buffer.cu:171-173)."""
+    rng = np.random.default_rng(n + mb)
+    st, ac = rng.standard_normal((n, S)).astype(f32), rng.standard_normal((n, A)).astype(f32)
+    lp, ad, at = (rng.standard_normal(n).astype(f32) for _ in range(3))
+    idx = rng.permutation(n).astype(i32)
+    d = [b200.dev(x) for x in (idx, st, ac, lp, ad, at)]
+    for offset in [0, n - mb // 2 - 1]:                 # the second one wraps
+        o = [b200.dev_empty((mb, S)), b200.dev_empty((mb, A)), b200.dev_empty(mb), b200.dev_empty(mb), b200.dev_empty(mb)]
+        L.ppo_b200_gather(d[0].ptr, offset, n, mb, S, A, *[x.ptr for x in d[1:]], *[x.ptr for x in o])
+        rows = idx[(offset + np.arange(mb)) % n]
+        for got, want in zip(o, (st[rows], ac[rows], lp[rows], ad[rows], at[rows])):
+            assert np.array_equal(got.numpy(), want)
+
+
+def test_empty_inputs_are_noops(L):
+    """n = 0 / batch 0 calls must return without launching on garbage (the reference would index out of bounds)."""
+    z = b200.dev_empty(4)
+    L.ppo_b200_gae(z.ptr, z.ptr, z.ptr, z.ptr, z.ptr, 0, 0.99, 0.95, z.ptr, z.ptr, 1, z.ptr)
+    L.ppo_b200_gather(z.ptr, 0, 1, 0, 3, 1, *[z.ptr] * 10)
+    L.ppo_b200_adam_flat(z.ptr, z.ptr, z.ptr, z.ptr, 0, 3e-4, 0.9, 0.999, 1)
+    L.ppo_b200_sync()
+
+
 @pytest.mark.parametrize("n", [1, 2, 1000, 819200])
 def test_device_permutation_is_a_permutation(L, n):
     d = b200.dev_empty(n, i32)
