@@ -112,3 +112,24 @@ def test_c_example_solves_pendulum():
     res = subprocess.run([_build_example(), "40", "4096"], capture_output=True, text=True, timeout=300)
     print(res.stdout[-1500:])
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+
+
+REF_MAIN = os.path.join(ROOT, "build", "abi_probe", "ref_main")
+
+
+@pytest.mark.gpu
+def test_reference_main_runs_unmodified_on_the_drop_in():
+    """The reference's own src/main.c, compiled UNMODIFIED against include/ and linked against libppo_b200.so by
+    test_reference_main_compiles_and_links_unmodified (in the build container, where /root/reference is mounted; the
+    binary travels with the snapshot), trains Pendulum for its 10 epochs x 30000 steps at minibatch 64 through the
+    reference call sequence (create_gym_env -> create_ppo -> eval_ppo / train_ppo_epoch -> save_ppo).  The mean
+    episode return printed by eval_ppo ("R:") must improve clearly."""
+    if not os.path.exists(REF_MAIN):
+        pytest.skip("build/abi_probe/ref_main not prebuilt (needs /root/reference at build time)")
+    res = subprocess.run([REF_MAIN, "64"], capture_output=True, text=True, timeout=600, cwd=os.path.join(ROOT, "build", "abi_probe"))
+    print(res.stdout[-3000:])
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    rs = [float(m.group(1)) for m in re.finditer(r"R: (-?[0-9.]+)", res.stdout)]
+    assert len(rs) >= 11, res.stdout[-2000:]
+    assert max(rs[1:]) > rs[0] + 300, rs
+    assert os.path.exists(os.path.join(ROOT, "build", "abi_probe", "ppo_model.bin"))
