@@ -99,6 +99,124 @@ __device__ __forceinline__ void gae_load_chunk(GaeRaw<kGaeTiles>& raw, long long
     }
 }
 
+// Scan one chunk held in registers: local suffix scan, look-back for the carry-in, outputs, Welford partial.
+template <int kGaeTiles, bool HINT>
+__device__ __forceinline__ void gae_process_chunk(const GaeRaw<kGaeTiles>& cur, int wc, int nchunks, int lane, int n, int vec_ok,
+                                                  float gamma, float gl, float cfull, float* __restrict__ adv_out,
+                                                  float* __restrict__ target_out, GaeDesc* desc, unsigned epoch,
+                                                  float4* __restrict__ wstats) {
+    constexpr int kGaeChunk = kGaeTile * kGaeTiles;
+    const long long base = (long long)wc * kGaeChunk;
+    float dl[kGaeTiles][4], cc[kGaeTiles][4];
+#pragma unroll
+    for (int t = 0; t < kGaeTiles; t++) {
+        const float r4[4] = {cur.r[t].x, cur.r[t].y, cur.r[t].z, cur.r[t].w};
+        const float v4[4] = {cur.v[t].x, cur.v[t].y, cur.v[t].z, cur.v[t].w};
+        const float n4[4] = {cur.vn[t].x, cur.vn[t].y, cur.vn[t].z, cur.vn[t].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const bool te = (cur.ft[t] >> (8 * e)) & 0xff, tr = (cur.fr[t] >> (8 * e)) & 0xff;
+            dl[t][e] = r4[e] + gamma * n4[e] * (te ? 0.f : 1.f) - v4[e];
+            cc[t][e] = (te || tr) ? 0.f : gl;
+        }
+    }
+    // ---- local scan (zero carry-in): loc = advantage, cend = product of c from element to chunk end
+    float loc[kGaeTiles][4], cend[kGaeTiles][4];
+    float X = 0.f, Cx = 1.f;   // head of the already-scanned suffix (tiles behind this one)
+#pragma unroll
+    for (int t = kGaeTiles - 1; t >= 0; t--) {
+        float A = 0.f, C = 1.f;
+#pragma unroll
+        for (int e = 3; e >= 0; e--) { A = dl[t][e] + cc[t][e] * A; C = cc[t][e] * C; }
+        float Ai = A, Ci = C;  // inclusive suffix over lanes lane..31
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float Ao = __shfl_down_sync(kFull, Ai, off), Co = __shfl_down_sync(kFull, Ci, off);
+            if (lane + off < 32) { Ai = Ai + Ci * Ao; Ci = Ci * Co; }
+        }
+        const float An = __shfl_down_sync(kFull, Ai, 1), Cn = __shfl_down_sync(kFull, Ci, 1);
+        float a = (lane == 31) ? X : An + Cn * X;
+        float ce = (lane == 31) ? Cx : Cn * Cx;
+#pragma unroll
+        for (int e = 3; e >= 0; e--) {
+            a = dl[t][e] + cc[t][e] * a;
+            ce = cc[t][e] * ce;
+            loc[t][e] = a;
+            cend[t][e] = ce;
+        }
+        X = __shfl_sync(kFull, loc[t][0], 0);
+        Cx = __shfl_sync(kFull, cend[t][0], 0);
+    }
+    // ---- publish the chunk aggregate, then resolve the carry-in by looking at later chunks.
+    // Cx is exactly 0 when the chunk holds a done step, else (gamma*lambda)^512 up to rounding.
+    if (lane == 0) st_relaxed_u64(&desc[wc], pack(epoch, Cx == 0.f ? kGaeAggDone : kGaeAggOpen, X));
+    const float c_last = __shfl_sync(kFull, cend[kGaeTiles - 1][3], 31);
+    float carry = 0.f;
+    if (c_last != 0.f && wc + 1 < nchunks) {   // warp-uniform
+        if (lane == 0) {
+            float mult = 1.f;
+            int j = wc + 1;
+            while (j < nchunks) {
+                const unsigned long long w = ld_relaxed_u64(&desc[j]);
+                if ((unsigned)(w >> 34) != epoch) { __nanosleep(20); continue; }
+                const unsigned state = (unsigned)(w >> 32) & 3u;
+                carry += mult * __uint_as_float((unsigned)w);
+                if (state != kGaeAggOpen) break;            // inclusive value, or the chunk cuts the chain
+                mult *= cfull;
+                if (mult == 0.f) break;
+                j++;
+            }
+        }
+        carry = __shfl_sync(kFull, carry, 0);
+    }
+    if (lane == 0 && Cx != 0.f) st_relaxed_u64(&desc[wc], pack(epoch, kGaeInclusive, X + Cx * carry));
+
+    // ---- final values, stores, Welford partial
+    float sum = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < kGaeTiles; t++) {
+        const long long i0 = base + t * kGaeTile + lane * 4;
+        const float v4[4] = {cur.v[t].x, cur.v[t].y, cur.v[t].z, cur.v[t].w};
+        float a4[4], t4[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            a4[e] = loc[t][e] + cend[t][e] * carry;
+            t4[e] = v4[e] + a4[e];
+            loc[t][e] = a4[e];
+            if (i0 + e < n) { sum += a4[e]; cnt++; }
+        }
+        if (vec_ok && i0 + 3 < n) {
+            if (HINT) {
+                st_stream4(adv_out + i0, make_float4(a4[0], a4[1], a4[2], a4[3]));
+                st_stream4(target_out + i0, make_float4(t4[0], t4[1], t4[2], t4[3]));
+            } else {
+                *reinterpret_cast<float4*>(adv_out + i0) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                *reinterpret_cast<float4*>(target_out + i0) = make_float4(t4[0], t4[1], t4[2], t4[3]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (i0 + e < n) { adv_out[i0 + e] = a4[e]; target_out[i0 + e] = t4[e]; }
+        }
+    }
+    sum = warp_sum(sum);
+    int total = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+    const float mean = sum / (float)total;
+    float m2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < kGaeTiles; t++) {
+        const long long i0 = base + t * kGaeTile + lane * 4;
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (i0 + e < n) { const float d = loc[t][e] - mean; m2 += d * d; }
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) wstats[wc] = make_float4(mean, m2, (float)total, 0.f);
+}
+
 // Persistent kernel: global warp g handles chunks nchunks-1-(i*W+g), i = 0,1,...  (descending order, so a
 // chunk's successor is handled in the same or an earlier iteration by a resident warp -> the look-back
 // cannot deadlock as long as the whole grid is co-resident, which the host guarantees through the
@@ -125,120 +243,98 @@ gae_scan_kernel(const float* __restrict__ reward, const float* __restrict__ v,
     GaeRaw<kGaeTiles> cur;
     gae_load_chunk<kGaeTiles, HINT>(cur, (long long)wc * kGaeChunk, lane, n, vec_ok, reward, v, v_next, terminated, truncated);
     for (; wc >= 0; wc -= W) {
-        const long long base = (long long)wc * kGaeChunk;
         GaeRaw<kGaeTiles> nxt;
         const bool has_next = wc - W >= 0;
         if (has_next) gae_load_chunk<kGaeTiles, HINT>(nxt, (long long)(wc - W) * kGaeChunk, lane, n, vec_ok, reward, v, v_next, terminated, truncated);
-
-        float dl[kGaeTiles][4], cc[kGaeTiles][4];
-#pragma unroll
-        for (int t = 0; t < kGaeTiles; t++) {
-            const float r4[4] = {cur.r[t].x, cur.r[t].y, cur.r[t].z, cur.r[t].w};
-            const float v4[4] = {cur.v[t].x, cur.v[t].y, cur.v[t].z, cur.v[t].w};
-            const float n4[4] = {cur.vn[t].x, cur.vn[t].y, cur.vn[t].z, cur.vn[t].w};
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const bool te = (cur.ft[t] >> (8 * e)) & 0xff, tr = (cur.fr[t] >> (8 * e)) & 0xff;
-                dl[t][e] = r4[e] + gamma * n4[e] * (te ? 0.f : 1.f) - v4[e];
-                cc[t][e] = (te || tr) ? 0.f : gl;
-            }
-        }
-        // ---- local scan (zero carry-in): loc = advantage, cend = product of c from element to chunk end
-        float loc[kGaeTiles][4], cend[kGaeTiles][4];
-        float X = 0.f, Cx = 1.f;   // head of the already-scanned suffix (tiles behind this one)
-#pragma unroll
-        for (int t = kGaeTiles - 1; t >= 0; t--) {
-            float A = 0.f, C = 1.f;
-#pragma unroll
-            for (int e = 3; e >= 0; e--) { A = dl[t][e] + cc[t][e] * A; C = cc[t][e] * C; }
-            float Ai = A, Ci = C;  // inclusive suffix over lanes lane..31
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const float Ao = __shfl_down_sync(kFull, Ai, off), Co = __shfl_down_sync(kFull, Ci, off);
-                if (lane + off < 32) { Ai = Ai + Ci * Ao; Ci = Ci * Co; }
-            }
-            const float An = __shfl_down_sync(kFull, Ai, 1), Cn = __shfl_down_sync(kFull, Ci, 1);
-            float a = (lane == 31) ? X : An + Cn * X;
-            float ce = (lane == 31) ? Cx : Cn * Cx;
-#pragma unroll
-            for (int e = 3; e >= 0; e--) {
-                a = dl[t][e] + cc[t][e] * a;
-                ce = cc[t][e] * ce;
-                loc[t][e] = a;
-                cend[t][e] = ce;
-            }
-            X = __shfl_sync(kFull, loc[t][0], 0);
-            Cx = __shfl_sync(kFull, cend[t][0], 0);
-        }
-        // ---- publish the chunk aggregate, then resolve the carry-in by looking at later chunks.
-        // Cx is exactly 0 when the chunk holds a done step, else (gamma*lambda)^512 up to rounding.
-        if (lane == 0) st_relaxed_u64(&desc[wc], pack(epoch, Cx == 0.f ? kGaeAggDone : kGaeAggOpen, X));
-        const float c_last = __shfl_sync(kFull, cend[kGaeTiles - 1][3], 31);
-        float carry = 0.f;
-        if (c_last != 0.f && wc + 1 < nchunks) {   // warp-uniform
-            if (lane == 0) {
-                float mult = 1.f;
-                int j = wc + 1;
-                while (j < nchunks) {
-                    const unsigned long long w = ld_relaxed_u64(&desc[j]);
-                    if ((unsigned)(w >> 34) != epoch) { __nanosleep(20); continue; }
-                    const unsigned state = (unsigned)(w >> 32) & 3u;
-                    carry += mult * __uint_as_float((unsigned)w);
-                    if (state != kGaeAggOpen) break;            // inclusive value, or the chunk cuts the chain
-                    mult *= cfull;
-                    if (mult == 0.f) break;
-                    j++;
-                }
-            }
-            carry = __shfl_sync(kFull, carry, 0);
-        }
-        if (lane == 0 && Cx != 0.f) st_relaxed_u64(&desc[wc], pack(epoch, kGaeInclusive, X + Cx * carry));
-
-        // ---- final values, stores, Welford partial
-        float sum = 0.f;
-        int cnt = 0;
-#pragma unroll
-        for (int t = 0; t < kGaeTiles; t++) {
-            const long long i0 = base + t * kGaeTile + lane * 4;
-            const float v4[4] = {cur.v[t].x, cur.v[t].y, cur.v[t].z, cur.v[t].w};
-            float a4[4], t4[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                a4[e] = loc[t][e] + cend[t][e] * carry;
-                t4[e] = v4[e] + a4[e];
-                loc[t][e] = a4[e];
-                if (i0 + e < n) { sum += a4[e]; cnt++; }
-            }
-            if (vec_ok && i0 + 3 < n) {
-                if (HINT) {
-                    st_stream4(adv_out + i0, make_float4(a4[0], a4[1], a4[2], a4[3]));
-                    st_stream4(target_out + i0, make_float4(t4[0], t4[1], t4[2], t4[3]));
-                } else {
-                    *reinterpret_cast<float4*>(adv_out + i0) = make_float4(a4[0], a4[1], a4[2], a4[3]);
-                    *reinterpret_cast<float4*>(target_out + i0) = make_float4(t4[0], t4[1], t4[2], t4[3]);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (i0 + e < n) { adv_out[i0 + e] = a4[e]; target_out[i0 + e] = t4[e]; }
-            }
-        }
-        sum = warp_sum(sum);
-        int total = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
-        const float mean = sum / (float)total;
-        float m2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < kGaeTiles; t++) {
-            const long long i0 = base + t * kGaeTile + lane * 4;
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-                if (i0 + e < n) { const float d = loc[t][e] - mean; m2 += d * d; }
-        }
-        m2 = warp_sum(m2);
-        if (lane == 0) wstats[wc] = make_float4(mean, m2, (float)total, 0.f);
+        gae_process_chunk<kGaeTiles, HINT>(cur, wc, nchunks, lane, n, vec_ok, gamma, gl, cfull, adv_out, target_out, desc, epoch, wstats);
         if (has_next) cur = nxt;
+    }
+}
+
+// ---- TMA-staged variant (n a multiple of 512, 16-byte aligned arrays) ---------------------------------------------------
+// Same schedule, but the inputs of the next kGaeStages chunks of every warp are in flight as 1-D bulk copies
+// (cp.async.bulk global -> shared, one mbarrier per stage and warp: SASS UBLKCP + SYNCS) instead of one register-buffered
+// chunk: 16 warps x 2 stages x 7 KB = 224 KB of requests outstanding per SM.  The register version is bound by bytes in
+// flight (an ncu pass attributed 48 % of its stall samples to the first use of the prefetched chunk).
+constexpr int kGaeStages = 2;
+constexpr int kGaeTmaWarps = 16;              // 16 warps x 2 stages x 7 KB = 224 KB in flight per SM, 4 warps per scheduler
+constexpr int kGaeStageBytes = 3 * 512 * 4 + 2 * 512;          // r, v, v' (2 KB each) + two flag arrays (512 B each)
+
+__device__ __forceinline__ uint32_t gae_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kGaeTmaWarps * 32, 1)
+gae_scan_tma_kernel(const float* __restrict__ reward, const float* __restrict__ v,
+                    const float* __restrict__ v_next, const unsigned char* __restrict__ terminated,
+                    const unsigned char* __restrict__ truncated, int n, float gamma, float gl,
+                    float* __restrict__ adv_out, float* __restrict__ target_out, GaeDesc* desc,
+                    unsigned epoch, float4* __restrict__ wstats) {
+    constexpr int kTiles = 4, kChunk = kGaeTile * kTiles;      // 512 elements
+    extern __shared__ __align__(128) unsigned char gsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* stage0 = gsm + (size_t)warp * kGaeStages * kGaeStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)kGaeTmaWarps * kGaeStages * kGaeStageBytes) + warp * kGaeStages;
+    const int nchunks = n / kChunk;
+    const int W = gridDim.x * kGaeTmaWarps;
+    const int g = blockIdx.x * kGaeTmaWarps + warp;
+    const int wc0 = nchunks - 1 - g;
+    if (wc0 < 0) return;
+    float cfull = gl;
+#pragma unroll
+    for (int q = 1; q < kChunk; q <<= 1) cfull *= cfull;
+
+    auto issue = [&](int wc, int s) {                          // lane 0 only
+        unsigned char* dst = stage0 + (size_t)s * kGaeStageBytes;
+        const uint32_t bar = gae_smem_u32(&bars[s]);
+        const size_t e0 = (size_t)wc * kChunk;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)kGaeStageBytes) : "memory");
+        const void* src[5] = {reward + e0, v + e0, v_next + e0, terminated + e0, truncated + e0};
+        const uint32_t off[5] = {0u, 2048u, 4096u, 6144u, 6656u}, bytes[5] = {2048u, 2048u, 2048u, 512u, 512u};
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(gae_smem_u32(dst + off[q])), "l"(src[q]), "r"(bytes[q]), "r"(bar) : "memory");
+    };
+    if (lane == 0) {
+        for (int s = 0; s < kGaeStages; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(gae_smem_u32(&bars[s])), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < kGaeStages; s++)
+            if (wc0 - s * W >= 0) issue(wc0 - s * W, s);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int wc = wc0; wc >= 0; wc -= W, it++) {
+        const int s = it % kGaeStages;
+        const uint32_t parity = (uint32_t)(it / kGaeStages) & 1u;
+        {
+            const uint32_t bar = gae_smem_u32(&bars[s]);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "GW_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra GD_%=;\n\t"
+                "bra GW_%=;\n\t"
+                "GD_%=:\n\t}"
+                :: "r"(bar), "r"(parity) : "memory");
+        }
+        const unsigned char* sb = stage0 + (size_t)s * kGaeStageBytes;
+        GaeRaw<kTiles> cur;
+#pragma unroll
+        for (int t = 0; t < kTiles; t++) {
+            const int o = t * kGaeTile + lane * 4;
+            cur.r[t] = *reinterpret_cast<const float4*>(sb + 4 * o);
+            cur.v[t] = *reinterpret_cast<const float4*>(sb + 2048 + 4 * o);
+            cur.vn[t] = *reinterpret_cast<const float4*>(sb + 4096 + 4 * o);
+            cur.ft[t] = *reinterpret_cast<const uint32_t*>(sb + 6144 + o);
+            cur.fr[t] = *reinterpret_cast<const uint32_t*>(sb + 6656 + o);
+        }
+        __syncwarp();                                           // every lane has its copy: the stage can be refilled
+        if (lane == 0 && wc - kGaeStages * W >= 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(wc - kGaeStages * W, s);
+        }
+        gae_process_chunk<kTiles, true>(cur, wc, nchunks, lane, n, 1, gamma, gl, cfull, adv_out, target_out, desc, epoch, wstats);
     }
 }
 
@@ -393,7 +489,19 @@ GaeWork gae_scan(const float* reward, const float* v, const float* v_next, const
                     reinterpret_cast<const unsigned char*>(terminated), reinterpret_cast<const unsigned char*>(truncated), \
                     n, gamma, gl, advantage, adv_target, desc, g_gae_epoch & 0x3FFFFFFFu, wstats, vec_ok);          \
     } while (0)
-    if (variant == 0) B200_GAE_LAUNCH(4, true, 2);
+    static int tma_cfg = -1;
+    const size_t tma_smem = (size_t)kGaeTmaWarps * kGaeStages * kGaeStageBytes + kGaeTmaWarps * kGaeStages * sizeof(uint64_t);
+    if (tma_cfg < 0) {
+        const char* e = getenv("PPO_B200_GAE_TMA");
+        tma_cfg = (e && e[0] == '0') ? 0 : 1;
+        if (tma_cfg) CUDA_CHECK(cudaFuncSetAttribute(gae_scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+    }
+    if (tma_cfg && vec_ok && tiles == 4 && (n % 512) == 0 && n >= 512 * kGaeTmaWarps * 4) {
+        const int grid = std::min(div_up(nchunks, kGaeTmaWarps), num_sms());            // 224 KB of shared memory: one CTA per SM, all co-resident
+        B200_LAUNCH(gae_scan_tma_kernel, grid, kGaeTmaWarps * 32, tma_smem, reward, v, v_next,
+                    reinterpret_cast<const unsigned char*>(terminated), reinterpret_cast<const unsigned char*>(truncated),
+                    n, gamma, gl, advantage, adv_target, desc, g_gae_epoch & 0x3FFFFFFFu, wstats);
+    } else if (variant == 0) B200_GAE_LAUNCH(4, true, 2);
     else if (variant == 1) B200_GAE_LAUNCH(2, true, 4);
     else if (variant == 2) B200_GAE_LAUNCH(4, false, 2);
     else if (variant == 3) B200_GAE_LAUNCH(2, false, 4);
