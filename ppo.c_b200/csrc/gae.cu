@@ -438,7 +438,19 @@ gae_normalize_kernel(float* __restrict__ adv, int n, const float* __restrict__ s
     const float denom = (float)((double)stats[1] + 1e-8);
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n4 = vec_ok ? n / 4 : 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {          // four independent 128-bit loads in flight per thread
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) a[u] = ld_stream4(adv + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u].x = (a[u].x - mean) / denom; a[u].y = (a[u].y - mean) / denom;
+            a[u].z = (a[u].z - mean) / denom; a[u].w = (a[u].w - mean) / denom;
+            st_stream4(adv + 4 * (i + u * stride), a[u]);
+        }
+    }
+    for (; i < n4; i += stride) {
         float4 a = ld_stream4(adv + 4 * i);
         a.x = (a.x - mean) / denom; a.y = (a.y - mean) / denom;
         a.z = (a.z - mean) / denom; a.w = (a.w - mean) / denom;
