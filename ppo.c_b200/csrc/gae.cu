@@ -100,7 +100,7 @@ __device__ __forceinline__ void gae_load_chunk(GaeRaw<kGaeTiles>& raw, long long
 }
 
 // Scan one chunk held in registers: local suffix scan, look-back for the carry-in, outputs, Welford partial.
-template <int kGaeTiles, bool HINT>
+template <int kGaeTiles, bool HINT, bool FULL>      // FULL: the chunk lies entirely inside [0, n) and the arrays are 16-byte aligned
 __device__ __forceinline__ void gae_process_chunk(const GaeRaw<kGaeTiles>& cur, int wc, int nchunks, int lane, int n, int vec_ok,
                                                   float gamma, float gl, float cfull, float* __restrict__ adv_out,
                                                   float* __restrict__ target_out, GaeDesc* desc, unsigned epoch,
@@ -186,7 +186,7 @@ __device__ __forceinline__ void gae_process_chunk(const GaeRaw<kGaeTiles>& cur, 
             loc[t][e] = a4[e];
             if (i0 + e < n) { sum += a4[e]; cnt++; }
         }
-        if (vec_ok && i0 + 3 < n) {
+        if (FULL || (vec_ok && i0 + 3 < n)) {
             if (HINT) {
                 st_stream4(adv_out + i0, make_float4(a4[0], a4[1], a4[2], a4[3]));
                 st_stream4(target_out + i0, make_float4(t4[0], t4[1], t4[2], t4[3]));
@@ -202,8 +202,11 @@ __device__ __forceinline__ void gae_process_chunk(const GaeRaw<kGaeTiles>& cur, 
     }
     sum = warp_sum(sum);
     int total = cnt;
+    if (FULL) total = kGaeChunk;
+    else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+    }
     const float mean = sum / (float)total;
     float m2 = 0.f;
 #pragma unroll
@@ -211,7 +214,7 @@ __device__ __forceinline__ void gae_process_chunk(const GaeRaw<kGaeTiles>& cur, 
         const long long i0 = base + t * kGaeTile + lane * 4;
 #pragma unroll
         for (int e = 0; e < 4; e++)
-            if (i0 + e < n) { const float d = loc[t][e] - mean; m2 += d * d; }
+            if (FULL || i0 + e < n) { const float d = loc[t][e] - mean; m2 += d * d; }
     }
     m2 = warp_sum(m2);
     if (lane == 0) wstats[wc] = make_float4(mean, m2, (float)total, 0.f);
@@ -246,7 +249,7 @@ gae_scan_kernel(const float* __restrict__ reward, const float* __restrict__ v,
         GaeRaw<kGaeTiles> nxt;
         const bool has_next = wc - W >= 0;
         if (has_next) gae_load_chunk<kGaeTiles, HINT>(nxt, (long long)(wc - W) * kGaeChunk, lane, n, vec_ok, reward, v, v_next, terminated, truncated);
-        gae_process_chunk<kGaeTiles, HINT>(cur, wc, nchunks, lane, n, vec_ok, gamma, gl, cfull, adv_out, target_out, desc, epoch, wstats);
+        gae_process_chunk<kGaeTiles, HINT, false>(cur, wc, nchunks, lane, n, vec_ok, gamma, gl, cfull, adv_out, target_out, desc, epoch, wstats);
         if (has_next) cur = nxt;
     }
 }
@@ -334,7 +337,7 @@ gae_scan_tma_kernel(const float* __restrict__ reward, const float* __restrict__ 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(wc - kGaeStages * W, s);
         }
-        gae_process_chunk<kTiles, true>(cur, wc, nchunks, lane, n, 1, gamma, gl, cfull, adv_out, target_out, desc, epoch, wstats);
+        gae_process_chunk<kTiles, true, true>(cur, wc, nchunks, lane, n, 1, gamma, gl, cfull, adv_out, target_out, desc, epoch, wstats);
     }
 }
 
