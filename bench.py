@@ -186,7 +186,7 @@ class C2(Workload):
         return {"fused_tile64_kernel": ("fp32", upd_flops), "fused_update_kernel": ("fp32", upd_flops),
                 "fused_reduce_adam_kernel": ("hbm", red_bytes),      # slab reads + 28 B/param Adam + 4 B/param image
                 "rollout64_kernel": ("fp32", roll_flops), "rollout_kernel": ("fp32", roll_flops),
-                "gae_scan_kernel": ("hbm", 22.0 * B), "gae_normalize_kernel": ("hbm", 8.0 * B)}
+                "gae_scan": ("hbm", 22.0 * B), "gae_normalize_kernel": ("hbm", 8.0 * B)}
 
     def teardown(self):
         self.L.free_ppo(self.ppo)
@@ -324,7 +324,7 @@ class C3(UpdateOnly):
                 "skinny_dw_kernel": ("fp32", 2 * self.MB * (steps_v * (H + S * H) + steps_p * (H * A + S * H))),
                 "gather_kernel": ("hbm", (steps_v + steps_p) * self.MB * (4 + 2 * 4 * (self.SIZES[0] + self.SIZES[-1] + 3))),
                 "adam_flat_kernel": ("hbm", 28.0 * (steps_v * mlp_params(sv) + steps_p * (mlp_params(self.SIZES) + self.SIZES[-1]))),
-                "gae_scan_kernel": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
+                "gae_scan": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
 
 
 class C4(UpdateOnly):
@@ -352,7 +352,7 @@ class C4(UpdateOnly):
         return {"tc_gemm_kernel": ("tensor_tf32", tc),
                 "adam_flat_kernel": ("hbm", 28.0 * (steps_v * mlp_params(sv) + steps_p * (mlp_params(self.SIZES) + self.SIZES[-1]))),
                 "gather_kernel": ("hbm", (steps_v + steps_p) * self.MB * (4 + 2 * 4 * (self.SIZES[0] + self.SIZES[-1] + 3))),
-                "gae_scan_kernel": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
+                "gae_scan": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
 
 
 class C5(Workload):
@@ -430,7 +430,7 @@ class C5(Workload):
                             "normalise + 2 D2H copies (8 B/element)"}
 
     def roofline_work(self, kernels):
-        return {"gae_scan_kernel": ("hbm", 22.0 * self.n), "gae_normalize_kernel": ("hbm", 8.0 * self.n)}
+        return {"gae_scan": ("hbm", 22.0 * self.n), "gae_normalize_kernel": ("hbm", 8.0 * self.n)}
 
     def teardown(self):
         for d in self.dev + [self.adv, self.tgt, self.st]:
@@ -729,9 +729,12 @@ def build_roofline(kernels, work, traffic_file=None):
     dom = max(out, key=lambda p: agg[p]["total_ms"])
     r = dict(out[dom])
     traffic = None
-    try:
+    try:      # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        ran = [name.replace(" ", "") for name in kernels if dom in name.replace(" ", "")]
+        for key, val in tj.items():
+            if dom in key and any(key in name for name in ran):
+                traffic = val.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     r.update({"kernel": dom, "share_of_step": agg[dom]["total_ms"] / total if total > 0 else None, "traffic": traffic,
