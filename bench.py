@@ -183,7 +183,7 @@ class C2(Workload):
         red_bytes = (self.N_VAL * nb * (ctas * slab_v * 4 + 32 * mlp_params(sv))
                      + self.N_POL * nb * (ctas * slab_p * 4 + 32 * mlp_params(self.SIZES)))
         roll_flops = 2 * B * mlp_weights(self.SIZES)
-        return {"fused_tile64_kernel": ("fp32", upd_flops), "fused_update_kernel": ("fp32", upd_flops),
+        return {"fused_tile64_kernel": ("fp32", upd_flops),
                 "fused_reduce_adam_kernel": ("hbm", red_bytes),      # slab reads + 28 B/param Adam + 4 B/param image
                 "rollout64_kernel": ("fp32", roll_flops), "rollout_kernel": ("fp32", roll_flops),
                 "gae_scan": ("hbm", 22.0 * B), "gae_normalize_kernel": ("hbm", 8.0 * B)}

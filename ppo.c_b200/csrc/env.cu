@@ -526,7 +526,12 @@ void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buff
     static int use64 = -1;
     if (use64 < 0) { const char* v = getenv("PPO_B200_ROLLOUT"); use64 = (v && strcmp(v, "old") == 0) ? 0 : 1; }
     Rollout64Args r{};
-    if (use64 && fused_image64(policy->mu, &r.net, &r.image)) {
+    bool narrow = true;                       // rollout64_kernel tiles at most 64 units per layer
+    {
+        NetDev* ndp = net_dev(policy->mu);
+        for (int w : ndp->sizes) narrow = narrow && w <= 64;
+    }
+    if (use64 && narrow && fused_image64(policy->mu, &r.net, &r.image)) {
         const int blocks = div_up(e->n_envs, kR64E);
         if (e->obs_norm && blocks > e->obs_partial_cap) {
             CUDA_CHECK(cudaStreamSynchronize(stream()));

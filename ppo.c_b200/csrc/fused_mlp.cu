@@ -1,38 +1,34 @@
 // fused_mlp.cu — the small-net fast path (SURVEY.md §8 rows a7+a9..a14 in two launches per minibatch).
 //
-// For the reference-width actor/critic nets (every layer width <= 128: 2x64, 2x128) one minibatch
-// update is
-//   fused_update_kernel   gather rows by permutation index -> forward through ALL layers -> fused loss
+// For the reference-width actor/critic nets (every layer width <= 128: 2x64, the reference's default 2x128) one
+// minibatch update is
+//   fused_tile64_kernel   gather rows by permutation index -> forward through ALL layers -> fused loss
 //                         head (MSE, or Gaussian log-prob + PPO-clip surrogate) -> backward through
 //                         all layers -> this CTA's partial gradient slab.  Weights are staged ONCE per
 //                         CTA in shared memory, activations never leave shared memory, nothing but
 //                         the slab is written to HBM.
-//   fused_reduce_adam_kernel  fixed-order sum of the slabs + Adam on the flat parameter vector (+ the
-//                         log_std vector for the policy) + loss accumulation; also refreshes the
-//                         pre-transposed weight image the next fused_update_kernel will stage.
+//   fused_reduce_adam_kernel  fixed-order sum of the slabs (+ the cross-GPU sum over NVLink peer memory under data
+//                         parallelism) + Adam on the flat parameter vector (+ the log_std vector for the policy) +
+//                         loss accumulation; also refreshes the pre-transposed weight image the next
+//                         fused_tile64_kernel will stage.
 // versus ~14 launches through the layer-wise kernels of gemm.cu/policy.cu/adam.cu (which remain the
 // generic path for wider nets).  The reference does this with ~25 launches, 1-3 blocking D2H reads
-// and 1-2 cudaMallocs per minibatch (src/ppo.cu:495-532).
+// and 1-2 cudaMallocs per minibatch (src/ppo.cu:495-532).  The two kernels are chained with programmatic
+// dependent launch: the gather prologue of minibatch k+1 overlaps the Adam kernel of minibatch k.
 //
-// Shared-memory layouts (TM = rows per CTA, TMP = TM + 4 so that TMP % 32 == 4):
+// Shared-memory layouts (64 rows per CTA, row stride TMP = 68 floats so that TMP % 32 == 4):
 //   activations / gradients  At[feature][TMP]   feature-major: a thread reads 4 consecutive ROWS with
 //                            one conflict-free LDS.128
-//   weights                  Wt[in][out_pad]    k-major transpose of the reference's W[out][in]; the whole
+//   weights                  Wt[in][ldw]        k-major transpose of the reference's W[out][in]; the whole
 //                            "image" [Wt_0|Wt_1|..|biases] is kept pre-transposed in global memory by the
 //                            Adam kernel and lands in shared memory with ONE TMA bulk copy
-//                            (cp.async.bulk + mbarrier complete_tx) that overlaps the row gather
-// Thread mappings (256 threads):
-//   forward / dX : thread = (row lane tr, column group tc): RT rows x 4 columns
-//   dW (+db)     : thread = (tj, tk) in 16x16, owns j = tj+16*jj, k = tk+16*kk (interleaved so the 16
-//                  lanes of a half-warp read 16 consecutive feature rows: stride TMP -> conflict-free)
-// Tile configs: <TM=64,RT=4> two CTAs per SM (widths <= 64), <TM=64,RT=8> one CTA per SM (widths <= 128).
-// All arithmetic is fp32 FFMA (tolerance 1e-5).
+//                            (cp.async.bulk + mbarrier complete_tx)
+// All arithmetic is fp32 (packed FFMA2 = two fma.rn per instruction; tolerance 1e-5).
 #include "common.cuh"
 #include "internal.h"
 
 namespace b200 {
 
-constexpr int kFusedThreads = 256;
 constexpr double kPiF = 3.14159265358979323846;
 
 enum FusedMode { kFusedForward = 0, kFusedValue = 1, kFusedPolicy = 2 };
@@ -82,163 +78,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// rows owned by a thread: RT=4 -> {4tr..4tr+3}; RT=8 -> {4tr..4tr+3, TM/2+4tr..TM/2+4tr+3}
-template <int TM, int RT>
-__device__ __forceinline__ void load_rows(const float* base, float (&a)[RT]) {
-    const float4 a0 = *reinterpret_cast<const float4*>(base);
-    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-    if (RT == 8) {
-        const float4 a1 = *reinterpret_cast<const float4*>(base + TM / 2);
-        a[RT - 4] = a1.x; a[RT - 3] = a1.y; a[RT - 2] = a1.z; a[RT - 1] = a1.w;
-    }
-}
-template <int TM, int RT>
-__device__ __forceinline__ void store_rows(float* base, const float (&a)[RT]) {
-    *reinterpret_cast<float4*>(base) = make_float4(a[0], a[1], a[2], a[3]);
-    if (RT == 8) *reinterpret_cast<float4*>(base + TM / 2) = make_float4(a[RT - 4], a[RT - 3], a[RT - 2], a[RT - 1]);
-}
-
-template <int TM, int RT>
-__device__ __forceinline__ void fused_forward_layer(const float* __restrict__ Xt, const float* __restrict__ Wt,
-                                                    const float* __restrict__ bias, float* __restrict__ Yt,
-                                                    int n_in, int n_out, int act, int ldw) {
-    constexpr int TMP = TM + 4, RL = TM / RT;
-    const int tr = threadIdx.x % RL, tc = threadIdx.x / RL;
-    const int out_pad = pad4(n_out);
-    if (4 * tc >= out_pad) return;
-    float acc[RT][4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const float b = (4 * tc + c < n_out) ? bias[4 * tc + c] : 0.f;
-#pragma unroll
-        for (int r = 0; r < RT; r++) acc[r][c] = b;
-    }
-    const float* xp = Xt + 4 * tr;
-    const float* wp = Wt + 4 * tc;
-#pragma unroll 4
-    for (int k = 0; k < n_in; k++) {
-        float a[RT];
-        load_rows<TM, RT>(xp + k * TMP, a);
-        const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
-        const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int r = 0; r < RT; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        float o[RT];
-#pragma unroll
-        for (int r = 0; r < RT; r++) o[r] = act_apply(acc[r][c], act);
-        store_rows<TM, RT>(Yt + (4 * tc + c) * TMP + 4 * tr, o);
-    }
-}
-
-// GXt[k][r] = (sum_j Gt[j][r] * W[j][k]) * act'(Ht[k][r])   (Wt is [k][out_pad])
-template <int TM, int RT>
-__device__ __forceinline__ void fused_backward_input(const float* __restrict__ Gt, const float* __restrict__ Wt,
-                                                     const float* __restrict__ Ht, float* __restrict__ GXt,
-                                                     int n_in, int n_out, int act_prev, int ldw) {
-    constexpr int TMP = TM + 4, RL = TM / RT;
-    const int tr = threadIdx.x % RL, tc = threadIdx.x / RL;
-    const int out_pad = ldw;
-    if (4 * tc >= pad4(n_in)) return;
-    float acc[RT][4];
-#pragma unroll
-    for (int r = 0; r < RT; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
-    const float* gp = Gt + 4 * tr;
-    // rows of Wt owned by this thread; out-of-range columns alias row 0 and are discarded below
-    const float* wp[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) wp[c] = Wt + (size_t)((4 * tc + c < n_in) ? 4 * tc + c : 0) * out_pad;
-#pragma unroll 4
-    for (int j = 0; j < n_out; j++) {
-        float g[RT];
-        load_rows<TM, RT>(gp + j * TMP, g);
-        float wv[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) wv[c] = wp[c][j];
-#pragma unroll
-        for (int r = 0; r < RT; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = fmaf(g[r], wv[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        if (4 * tc + c >= n_in) continue;
-        float h[RT], o[RT];
-        load_rows<TM, RT>(Ht + (4 * tc + c) * TMP + 4 * tr, h);
-#pragma unroll
-        for (int r = 0; r < RT; r++) o[r] = act_grad(h[r], acc[r][c], act_prev);
-        store_rows<TM, RT>(GXt + (4 * tc + c) * TMP + 4 * tr, o);
-    }
-}
-
-// gW[j][k] = sum_r Gt[j][r] * Xt[k][r]  and  gb[j] = sum_r Gt[j][r]  -> global slab
-// (row-major [out][in], the reference layout; src/mat_mul.cu:195-208 + src/neural_network.cu:108-118)
-template <int TM, int JJ, int KK>
-__device__ __forceinline__ void fused_backward_weights(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                       float* __restrict__ gW, float* __restrict__ gb, int n_in, int n_out) {
-    constexpr int TMP = TM + 4;
-    const int tk = threadIdx.x & 15, tj = threadIdx.x >> 4;
-    float acc[JJ][KK], bsum[JJ];
-#pragma unroll
-    for (int a = 0; a < JJ; a++) {
-        bsum[a] = 0.f;
-#pragma unroll
-        for (int b = 0; b < KK; b++) acc[a][b] = 0.f;
-    }
-    // clamp out-of-range rows to a valid one (results discarded) so loads stay in bounds
-    int jrow[JJ], krow[KK];
-#pragma unroll
-    for (int a = 0; a < JJ; a++) jrow[a] = min(tj + 16 * a, n_out - 1) * TMP;
-#pragma unroll
-    for (int b = 0; b < KK; b++) krow[b] = min(tk + 16 * b, n_in - 1) * TMP;
-#pragma unroll 2
-    for (int r = 0; r < TM; r += 4) {
-        float4 g[JJ], x[KK];
-#pragma unroll
-        for (int a = 0; a < JJ; a++) g[a] = *reinterpret_cast<const float4*>(Gt + jrow[a] + r);
-#pragma unroll
-        for (int b = 0; b < KK; b++) x[b] = *reinterpret_cast<const float4*>(Xt + krow[b] + r);
-#pragma unroll
-        for (int a = 0; a < JJ; a++) {
-            if (tk == 0) bsum[a] += (g[a].x + g[a].y) + (g[a].z + g[a].w);
-#pragma unroll
-            for (int b = 0; b < KK; b++) {
-                acc[a][b] = fmaf(g[a].x, x[b].x, acc[a][b]);
-                acc[a][b] = fmaf(g[a].y, x[b].y, acc[a][b]);
-                acc[a][b] = fmaf(g[a].z, x[b].z, acc[a][b]);
-                acc[a][b] = fmaf(g[a].w, x[b].w, acc[a][b]);
-            }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < JJ; a++) {
-        const int j = tj + 16 * a;
-        if (j >= n_out) continue;
-        if (tk == 0) gb[j] = bsum[a];
-#pragma unroll
-        for (int b = 0; b < KK; b++) {
-            const int k = tk + 16 * b;
-            if (k < n_in) gW[(size_t)j * n_in + k] = acc[a][b];
-        }
-    }
-}
-
-template <int TM>
-__device__ __forceinline__ void fused_weights_dispatch(const float* Gt, const float* Xt, float* gW, float* gb, int n_in, int n_out) {
-    const int jj = (n_out + 15) / 16, kk = (n_in + 15) / 16;
-#define B200_DW(J, K) fused_backward_weights<TM, J, K>(Gt, Xt, gW, gb, n_in, n_out)
-    if (jj <= 1) { if (kk <= 2) B200_DW(1, 2); else if (kk <= 4) B200_DW(1, 4); else B200_DW(1, 8); }
-    else if (jj <= 4) { if (kk <= 2) B200_DW(4, 2); else if (kk <= 4) B200_DW(4, 4); else B200_DW(4, 8); }
-    else { if (kk <= 2) B200_DW(8, 2); else if (kk <= 4) B200_DW(8, 4); else B200_DW(8, 8); }
-#undef B200_DW
-}
-
 __device__ __forceinline__ float fused_log_prob(const float* mu, const float* log_std, const float* action, int A) {
     float logprob = (float)(-0.5 * A * (double)logf((float)(2 * kPiF)));   // src/policy.cu:67-74
     for (int j = 0; j < A; j++) {
@@ -248,163 +87,13 @@ __device__ __forceinline__ float fused_log_prob(const float* mu, const float* lo
     return logprob;
 }
 
-template <int TM, int RT>
-__global__ void __launch_bounds__(kFusedThreads, (TM == 64 && RT == 4) ? 2 : 1) fused_update_kernel(const FusedArgs p) {
-    constexpr int TMP = TM + 4;
-    extern __shared__ __align__(128) float smem[];
-    const FusedNet& net = p.net;
-    const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * TM;
-    const int S = net.sizes[0], OUT = net.sizes[net.L];
-    float* img = smem;                                   // [Wt_0 | Wt_1 | ... | biases]
-    float* act0 = smem + net.img_floats;                 // activation buffers
-    float* red = smem + p.smem_red_off;                  // 64 floats
-    int* src_rows = reinterpret_cast<int*>(red + 64);    // TM ints
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64 + TM);
-
-    // ---- one elected thread launches the TMA bulk copy of the weight image; everybody else gathers
-    if (tid == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
-        tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
-    }
-    // per-row head inputs are fetched now so their latency hides behind the forward pass
-    float h_target = 0.f, h_adv = 0.f, h_lp_old = 0.f, h_act[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) h_act[j] = 0.f;
-    int my_src = -1;
-    if (tid < TM) {
-        const int r = row0 + tid;
-        if (r < p.m) my_src = p.idx ? p.idx[(p.offset + r) % p.limit] : p.offset + r;
-        src_rows[tid] = my_src;
-    }
-    __syncthreads();
-    {   // gather the input tile: Xt[k][r] = state[src][k]
-        float* Xt = act0 + net.a_off[0];
-        for (int e = tid; e < TM * S; e += kFusedThreads) {
-            const int r = e / S, k = e - r * S;
-            const int src = src_rows[r];
-            Xt[k * TMP + r] = src >= 0 ? p.state[(size_t)src * S + k] : 0.f;
-        }
-    }
-    if (my_src >= 0) {
-        if (p.mode == kFusedValue) {
-            h_target = p.adv_target[my_src];
-        } else if (p.mode == kFusedPolicy) {
-            h_adv = p.advantage[my_src];
-            h_lp_old = p.logprob[my_src];
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (j < OUT) h_act[j] = p.action[(size_t)my_src * OUT + j];
-        }
-    }
-    mbar_wait(mbar, 0);
-    __syncthreads();
-    // ---- forward
-    for (int l = 0; l < net.L; l++) {
-        fused_forward_layer<TM, RT>(act0 + net.a_off[l], img + net.wt_off[l], img + net.bs_off[l], act0 + net.a_off[l + 1],
-                                    net.sizes[l], net.sizes[l + 1], net.acts[l], net.ldw[l]);
-        __syncthreads();
-    }
-    const float* Yt = act0 + net.a_off[net.L];
-    if (p.mode == kFusedForward) {
-        for (int e = tid; e < TM * OUT; e += kFusedThreads) {
-            const int r = e / OUT, j = e - r * OUT;
-            if (row0 + r < p.m) p.y_out[(size_t)(row0 + r) * OUT + j] = Yt[j * TMP + r];
-        }
-        return;
-    }
-    float* slab = p.partials + (size_t)blockIdx.x * p.slab;
-    float* Ga = smem + p.smem_g_off;
-    float* Gb = Ga + net.max_width_pad * TMP;
-    // ---- fused loss head: writes Ga[j][r] = dLoss/dy[r][j] (already through the output activation)
-    {
-        float loss_term = 0.f;
-        float gls[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) gls[j] = 0.f;
-        if (tid < TM) {
-            float gout[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) gout[j] = 0.f;
-            if (my_src >= 0) {
-                if (p.mode == kFusedValue) {            // src/loss.cu:5-23
-                    const float y = Yt[tid];
-                    gout[0] = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(y, h_target)), (float)p.m_total);
-                    const float d = __fsub_rn(h_target, y);
-                    loss_term = __fmul_rn(d, d);
-                } else {                                // src/policy.cu:67-111 + src/ppo.cu:89-98
-                    float mu[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) mu[j] = (j < OUT) ? Yt[j * TMP + tid] : 0.f;
-                    const float lp = fused_log_prob(mu, p.log_std, h_act, OUT);
-                    const float ratio = expf(__fsub_rn(lp, h_lp_old));
-                    const bool adv_pos = h_adv > 0.f;
-                    const bool hi = ratio > 1.f + p.epsilon, lo = ratio < 1.f - p.epsilon;
-                    const float sel = adv_pos ? (hi ? 1.f + p.epsilon : ratio) : (lo ? 1.f - p.epsilon : ratio);
-                    loss_term = __fmul_rn(h_adv, sel);
-                    const int keep = adv_pos ? !hi : !lo;
-                    const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)p.m_total);
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        if (j < OUT) {
-                            const float e2 = expf(-2.f * p.log_std[j]);
-                            const float diff = __fsub_rn(h_act[j], mu[j]);
-                            gout[j] = __fmul_rn(__fmul_rn(diff, e2), g);
-                            gls[j] = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), g);
-                        }
-                }
-            }
-            const int out_act = net.acts[net.L - 1];
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (j < OUT) Ga[j * TMP + tid] = act_grad(Yt[j * TMP + tid], gout[j], out_act);
-        }
-        // block reductions of the loss term and the log_std gradient (warps 0..TM/32-1 hold data)
-        const int warp = tid >> 5, lane = tid & 31;
-        float v = warp_sum(loss_term);
-        if (lane == 0) red[warp] = v;
-        if (p.mode == kFusedPolicy) {
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (j < OUT) { const float s = warp_sum(gls[j]); if (lane == 0) red[8 + j * 8 + warp] = s; }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float t = 0.f;
-            for (int w = 0; w < kFusedThreads / 32; w++) t += red[w];
-            slab[net.P + OUT] = t;
-        }
-        if (p.mode == kFusedPolicy && tid < OUT) {
-            float t = 0.f;
-            for (int w = 0; w < kFusedThreads / 32; w++) t += red[8 + tid * 8 + w];
-            slab[net.P + tid] = t;
-        }
-    }
-    // ---- backward
-    float* G = Ga;
-    float* Gn = Gb;
-    for (int l = net.L - 1; l >= 0; l--) {
-        const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
-        const float* Xt = act0 + net.a_off[l];
-        fused_weights_dispatch<TM>(G, Xt, slab + net.w_off[l], slab + net.b_off[l], n_in, n_out);
-        if (l > 0) {
-            fused_backward_input<TM, RT>(G, img + net.wt_off[l], Xt, Gn, n_in, n_out, net.acts[l - 1], net.ldw[l]);
-            __syncthreads();
-            float* tmp = G; G = Gn; Gn = tmp;
-        }
-    }
-}
-
-
 // ===================================================================================================
-// 64-wide tile kernel (every layer width <= 64: the reference's Pendulum / 2x64 nets).
+// Tile kernel (every layer width <= 128: the reference's Pendulum nets, 2x64 and the default 2x128).
 //
-// 256 threads = two groups of four warps working on one 64-row tile, two CTAs per SM (16 warps per SM).
-// Compared with fused_update_kernel above:
-//   * 8 rows x 4 columns per thread in forward and dX: 3 LDS.128 feed 32 FFMAs (the 4x4 tile needed 2 per 16;
-//     shared memory delivers 128 B/clk/SM, so floats-loaded-per-FFMA is what bounds an fp32 tile kernel);
+// 256 threads = two groups of four warps working on one 64-row tile, two CTAs per SM (16 warps per SM) for 64-wide
+// nets, one for 128-wide nets (layers wider than 64 are processed in 64-column / 64x64 blocks).
+//   * 8 rows x 4 columns per thread in forward and dX: 3 LDS.128 feed 32 FMAs (a 4x4 tile needs 2 per 16;
+//     shared memory delivers 128 B/clk/SM, so floats-loaded-per-FMA is what bounds an fp32 tile kernel);
 //   * the two groups split the WORK, not the tile: forward = split-K halves that meet through one
 //     exchange buffer; backward = group 0 computes dW_l/db_l while group 1 computes dX_l (independent given
 //     G_{l+1} and A_l), so the backward critical path is max(dW, dX) instead of their sum;
@@ -417,7 +106,6 @@ __global__ void __launch_bounds__(kFusedThreads, (TM == 64 && RT == 4) ? 2 : 1) 
 constexpr int kT64Threads = 256;
 constexpr int kT64TM = 64;
 constexpr int kT64TMP = 68;      // feature row stride in floats; 68 % 32 == 4 keeps feature-strided LDS.128 conflict-free
-constexpr int kT64Ebuf = 64 * kT64TMP;
 
 __device__ __forceinline__ void t64_stamp(const FusedArgs& p, int slot) {
     if (p.dbg && threadIdx.x == 0) {
@@ -452,9 +140,10 @@ __device__ __forceinline__ void t64_store8(float* base, const float (&a)[8]) {
 // Contains one __syncthreads.
 __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
                                             const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ xch,
-                                            int n_in, int n_out, int act, int lt, int g) {
+                                            int n_in, int n_out, int act, int lt, int g, int cb) {
+    // cb = first column of the 64-column block this call computes (layers wider than 64 are done block by block)
     const int tr = lt & 7, tc = lt >> 3;
-    const bool live = 4 * tc < pad4(n_out);
+    const bool live = cb + 4 * tc < pad4(n_out);
     const bool split = n_in >= 16;
     float mine[4][4];                       // [row of my quad][col]
     if (split) {
@@ -467,7 +156,7 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
             for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
         if (live) {
             const float* xp = Xt + 4 * tr;
-            const float* wp = Wt + 4 * tc;
+            const float* wp = Wt + cb + 4 * tc;
 #pragma unroll 2
             for (int k = k0; k < k1; k++) {
                 const float4 a0 = *reinterpret_cast<const float4*>(xp + k * kT64TMP);
@@ -500,7 +189,7 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
             for (int c = 0; c < 4; c++) mine[r][c] = 0.f;
         if (live) {
             const float* xp = Xt + 4 * tr + 32 * g;
-            const float* wp = Wt + 4 * tc;
+            const float* wp = Wt + cb + 4 * tc;
             for (int k = 0; k < n_in; k++) {
                 const float4 a = *reinterpret_cast<const float4*>(xp + k * kT64TMP);
                 const float4 w = *reinterpret_cast<const float4*>(wp + k * ldw);
@@ -514,7 +203,7 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
     }
     __syncthreads();
     if (live) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + 4 * tc);     // bias block is zero-padded to pad4
+        const float4 b = *reinterpret_cast<const float4*>(bias + cb + 4 * tc);     // bias block is zero-padded to pad4
         const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -527,7 +216,7 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
             }
 #pragma unroll
             for (int r = 0; r < 4; r++) o[r] = act_apply(o[r] + bv[c], act);
-            *reinterpret_cast<float4*>(Yt + (4 * tc + c) * kT64TMP + 4 * tr + 32 * g) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(Yt + (cb + 4 * tc + c) * kT64TMP + 4 * tr + 32 * g) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -573,9 +262,10 @@ __device__ __forceinline__ void t64_forward_skinny(const float* __restrict__ Xt,
 // Rows [n_in, pad4(n_in)) of Gout are zero-filled (they are read as padding by the next dX).
 __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt, const float* __restrict__ Wt, int ldw,
                                                    const float* __restrict__ Ht, float* __restrict__ Gout, int n_in, int n_out,
-                                                   int act_prev, int lt) {
+                                                   int act_prev, int lt, int kb) {
+    // kb = first of the 64 input features (output rows of Gout) this call produces
     const int tr = lt & 7, tc = lt >> 3;
-    if (tc >= pad4(n_in)) return;
+    if (kb + tc >= pad4(n_in)) return;
     float2 acc[4][4];                       // [row pair][k column]
 #pragma unroll
     for (int r = 0; r < 4; r++)
@@ -583,7 +273,7 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
         for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
     const float* wrow[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) wrow[c] = Wt + (size_t)min(tc + 16 * c, n_in - 1) * ldw;
+    for (int c = 0; c < 4; c++) wrow[c] = Wt + (size_t)min(kb + tc + 16 * c, n_in - 1) * ldw;
     const float* gp = Gt + 4 * tr;
     const int jpad = pad4(n_out);
 #pragma unroll 1
@@ -607,7 +297,7 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        const int k = tc + 16 * c;
+        const int k = kb + tc + 16 * c;
         if (k >= pad4(n_in)) continue;
         float h[8], o[8];
         t64_load8(Ht + k * kT64TMP + 4 * tr, h);
@@ -622,9 +312,10 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
 // and 8 X rows a warp loads per instruction are consecutive features.
 template <int JJ, int KK>
 __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                     float* __restrict__ gW, int n_in, int n_out, int lt) {
+                                                     float* __restrict__ gW, int n_in, int n_out, int lt, int jb, int kb) {
+    // (jb, kb) = first output row / input column of the 64x64 block of gW this call produces
     const int tk = lt & 7, tj = lt >> 3;
-    if ((tj & ~3) >= n_out) return;          // warp-uniform: this warp owns no valid output row
+    if (jb + (tj & ~3) >= n_out) return;     // warp-uniform: this warp owns no valid output row
     float2 acc[JJ][KK];                     // (sum over even rows, sum over odd rows): both FFMA2 operands are natural pairs
 #pragma unroll
     for (int a = 0; a < JJ; a++)
@@ -632,9 +323,9 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
         for (int b = 0; b < KK; b++) acc[a][b] = make_float2(0.f, 0.f);
     int jrow[JJ], krow[KK];
 #pragma unroll
-    for (int a = 0; a < JJ; a++) jrow[a] = min(tj + 16 * a, n_out - 1) * kT64TMP;
+    for (int a = 0; a < JJ; a++) jrow[a] = min(jb + tj + 16 * a, n_out - 1) * kT64TMP;
 #pragma unroll
-    for (int b = 0; b < KK; b++) krow[b] = min(tk + 8 * b, n_in - 1) * kT64TMP;
+    for (int b = 0; b < KK; b++) krow[b] = min(kb + tk + 8 * b, n_in - 1) * kT64TMP;
 #pragma unroll 1
     for (int r = 0; r < kT64TM; r += 4) {
         float4 g[JJ], x[KK];
@@ -652,11 +343,11 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
     }
 #pragma unroll
     for (int a = 0; a < JJ; a++) {
-        const int j = tj + 16 * a;
+        const int j = jb + tj + 16 * a;
         if (j >= n_out) continue;
 #pragma unroll
         for (int b = 0; b < KK; b++) {
-            const int k = tk + 8 * b;
+            const int k = kb + tk + 8 * b;
             if (k < n_in) gW[(size_t)j * n_in + k] = acc[a][b].x + acc[a][b].y;
         }
     }
@@ -667,8 +358,8 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
 // The two row halves meet through one shuffle; sums run in a fixed order.
 template <bool WIDE_IS_K>
 __device__ __forceinline__ void t64_backward_weights_skinny(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                            float* __restrict__ gW, int n_in, int n_out, int lt) {
-    const int wide = lt >> 1, h = lt & 1;
+                                                            float* __restrict__ gW, int n_in, int n_out, int lt, int wb) {
+    const int wide = wb + (lt >> 1), h = lt & 1;       // wb = first of the 64 wide-side features of this call
     const int n_wide = WIDE_IS_K ? n_in : n_out, n_small = WIDE_IS_K ? n_out : n_in;
     const float* wide_base = (WIDE_IS_K ? Xt : Gt) + min(wide, n_wide - 1) * kT64TMP + 32 * h;
     const float* small_base = (WIDE_IS_K ? Gt : Xt) + 32 * h;
@@ -699,27 +390,36 @@ __device__ __forceinline__ void t64_backward_weights_skinny(const float* __restr
 }
 
 __device__ __forceinline__ void t64_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out, int lt) {
-    // few tile shapes only (instruction-cache footprint)
-    if (n_out <= 8) t64_backward_weights_skinny<true>(Gt, Xt, gW, n_in, n_out, lt);
-    else if (n_in <= 8) t64_backward_weights_skinny<false>(Gt, Xt, gW, n_in, n_out, lt);
-    else if (n_out <= 16) t64_backward_weights<1, 8>(Gt, Xt, gW, n_in, n_out, lt);
-    else t64_backward_weights<4, 8>(Gt, Xt, gW, n_in, n_out, lt);
+    // few tile shapes only (instruction-cache footprint); layers wider than 64 go 64x64 block by block
+    if (n_out <= 8) {
+        for (int wb = 0; wb < n_in; wb += 64) t64_backward_weights_skinny<true>(Gt, Xt, gW, n_in, n_out, lt, wb);
+    } else if (n_in <= 8) {
+        for (int wb = 0; wb < n_out; wb += 64) t64_backward_weights_skinny<false>(Gt, Xt, gW, n_in, n_out, lt, wb);
+    } else {
+        for (int jb = 0; jb < n_out; jb += 64)
+            for (int kb = 0; kb < n_in; kb += 64) {
+                if (n_out - jb <= 16) t64_backward_weights<1, 8>(Gt, Xt, gW, n_in, n_out, lt, jb, kb);
+                else t64_backward_weights<4, 8>(Gt, Xt, gW, n_in, n_out, lt, jb, kb);
+            }
+    }
 }
 
 // gb[j] = sum_r Gt[j][r]: thread = (j, row half), fixed-order sums
 __device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out, int lt) {
-    const int j = lt >> 1, h = lt & 1;
-    float s = 0.f;
-    if (j < n_out) {
-        const float* gp = Gt + j * kT64TMP + 32 * h;
+    for (int jb = 0; jb < n_out; jb += 64) {
+        const int j = jb + (lt >> 1), h = lt & 1;
+        float s = 0.f;
+        if (j < n_out) {
+            const float* gp = Gt + j * kT64TMP + 32 * h;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float4 g = *reinterpret_cast<const float4*>(gp + 4 * i);
-            s += (g.x + g.y) + (g.z + g.w);
+            for (int i = 0; i < 8; i++) {
+                const float4 g = *reinterpret_cast<const float4*>(gp + 4 * i);
+                s += (g.x + g.y) + (g.z + g.w);
+            }
         }
+        s += __shfl_xor_sync(kFull, s, 1);
+        if (h == 0 && j < n_out) gb[j] = s;
     }
-    s += __shfl_xor_sync(kFull, s, 1);
-    if (h == 0 && j < n_out) gb[j] = s;
 }
 
 __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const FusedArgs p) {
@@ -792,7 +492,10 @@ __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const Fuse
         if (net.sizes[l + 1] <= 8)
             t64_forward_skinny(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, scratch, net.sizes[l], net.sizes[l + 1], net.acts[l]);
         else
-            t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp);
+            for (int cb = 0; cb < pad4(net.sizes[l + 1]); cb += 64) {
+                if (cb) __syncthreads();           // the previous block's finalisation has read the exchange buffer
+                t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp, cb);
+            }
         __syncthreads();
         t64_stamp(p, 4 + l);
     }
@@ -867,12 +570,13 @@ __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const Fuse
     for (int l = net.L - 1; l >= 0; l--) {
         const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
         const float* Xt = act0 + net.a_off[l];
-        float* Gout = ebuf + ((net.L - 1 - l) & 1) * kT64Ebuf;
+        float* Gout = ebuf + ((net.L - 1 - l) & 1) * (net.max_width_pad * TMP);
         if (grp == 0) {
             t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt);
             t64_bias_grad(G, slab + net.b_off[l], n_out, lt);
         } else if (l > 0) {
-            t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt);
+            for (int kb = 0; kb < pad4(n_in); kb += 64)
+                t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt, kb);
         }
         if (l > 0) __syncthreads();
         t64_stamp(p, 10 + l);
@@ -1029,56 +733,9 @@ __global__ void __launch_bounds__(256) build_image_kernel(const float* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-struct FusedPlan { bool ok; int tm, rt; size_t smem_bytes; FusedNet net; int g_off, red_off; int kind; };   // kind 1: 64-wide tile kernel
+struct FusedPlan { bool ok; int tm, rt; size_t smem_bytes; FusedNet net; int g_off, red_off; int kind; };
 
-static FusedPlan make_plan(NetDev* nd, int tm, int rt) {
-    FusedPlan pl{};
-    pl.ok = false;
-    pl.kind = 0;
-    const int L = nd->num_layers - 1;
-    if (L < 1 || L > kFusedMaxLayers) return pl;
-    const int tmp = tm + 4;
-    const int cg = kFusedThreads / (tm / rt);        // column groups of 4
-    FusedNet& n = pl.net;
-    n.L = L;
-    int off = 0, maxw = 4;
-    for (int l = 0; l <= L; l++) n.sizes[l] = nd->sizes[l];
-    for (int l = 0; l < L; l++) {
-        n.acts[l] = nd->acts[l];
-        n.w_off[l] = (int)nd->w_off[l];
-        n.b_off[l] = (int)nd->b_off[l];
-        if (pad4(n.sizes[l + 1]) > 4 * cg || n.sizes[l + 1] > 128) return pl;       // forward column coverage / dW tiles
-        if (l > 0 && (pad4(n.sizes[l]) > 4 * cg || n.sizes[l] > 128)) return pl;   // dX column coverage
-        if (n.sizes[l] > 128) return pl;
-        n.wt_off[l] = off;
-        n.ldw[l] = pad4(n.sizes[l + 1]);
-        off += n.sizes[l] * n.ldw[l];
-    }
-    for (int l = 0; l < L; l++) { n.bs_off[l] = off; off += pad4(n.sizes[l + 1]); }
-    n.img_floats = (off + 31) & ~31;                 // 128-byte multiple
-    if (n.sizes[L] > 8) return pl;                   // loss heads keep <= 8 outputs in registers
-    n.P = (int)nd->param_count;
-    off = 0;
-    for (int l = 0; l <= L; l++) {
-        n.a_off[l] = off;
-        off += pad4(n.sizes[l]) * tmp;
-        if (l > 0) maxw = std::max(maxw, pad4(n.sizes[l]));
-    }
-    n.max_width_pad = maxw;
-    off += n.img_floats;
-    pl.g_off = off;
-    off += 2 * maxw * tmp;
-    pl.red_off = off;
-    off += 64 + tm + 4;
-    pl.smem_bytes = (size_t)off * sizeof(float);
-    pl.tm = tm;
-    pl.rt = rt;
-    const size_t limit = (tm == 64 && rt == 4) ? 110 * 1024 : 220 * 1024;   // two CTAs per SM in the <64,4> config
-    pl.ok = pl.smem_bytes <= limit;
-    return pl;
-}
-
-// Plan for fused_tile64_kernel: every width <= 64, <= 8 outputs.
+// Plan for fused_tile64_kernel: every width <= 128 (64-column blocks), <= 8 outputs, everything in <= 220 KB of shared memory.
 static FusedPlan make_plan64(NetDev* nd) {
     FusedPlan pl{};
     pl.ok = false;
@@ -1087,7 +744,7 @@ static FusedPlan make_plan64(NetDev* nd) {
     if (L < 1 || L > kFusedMaxLayers) return pl;
     FusedNet& n = pl.net;
     n.L = L;
-    for (int l = 0; l <= L; l++) { n.sizes[l] = nd->sizes[l]; if (n.sizes[l] > 64 || n.sizes[l] < 1) return pl; }
+    for (int l = 0; l <= L; l++) { n.sizes[l] = nd->sizes[l]; if (n.sizes[l] > 128 || n.sizes[l] < 1) return pl; }
     if (n.sizes[L] > 8) return pl;
     int off = 0, maxw = 4;
     for (int l = 0; l < L; l++) {
@@ -1110,8 +767,10 @@ static FusedPlan make_plan64(NetDev* nd) {
     }
     n.max_width_pad = maxw;
     off += n.img_floats;
-    pl.g_off = off;            // E0 | E1: forward split-K exchange, out-of-place dX ping-pong, skinny-forward scratch
-    off += 2 * kT64Ebuf;
+    maxw = std::max(maxw, 64);  // the forward exchange uses 64 feature rows, the skinny forward 24
+    n.max_width_pad = maxw;
+    pl.g_off = off;            // E0 | E1 (maxw rows each): forward split-K exchange, out-of-place dX ping-pong, skinny scratch
+    off += 2 * maxw * kT64TMP;
     pl.red_off = off;
     off += 64 + kT64TM + 4;
     pl.smem_bytes = (size_t)off * sizeof(float);
@@ -1121,17 +780,7 @@ static FusedPlan make_plan64(NetDev* nd) {
     return pl;
 }
 
-static int g_fused_variant = -1;     // PPO_B200_FUSED_KERNEL=old forces the 256-thread kernel (A/B runs)
-static FusedPlan choose_plan(NetDev* nd) {
-    if (g_fused_variant < 0) { const char* e = getenv("PPO_B200_FUSED_KERNEL"); g_fused_variant = (e && strcmp(e, "old") == 0) ? 0 : 1; }
-    if (g_fused_variant == 1) {
-        FusedPlan q = make_plan64(nd);
-        if (q.ok) return q;
-    }
-    FusedPlan p = make_plan(nd, 64, 4);
-    if (p.ok) return p;
-    return make_plan(nd, 64, 8);
-}
+static FusedPlan choose_plan(NetDev* nd) { return make_plan64(nd); }
 
 bool fused_supported(NeuralNetwork* nn) { return choose_plan(net_dev(nn)).ok; }
 
@@ -1177,26 +826,12 @@ static void launch_fused(NetDev* nd, const FusedPlan& pl, FusedArgs& a, bool pdl
     a.smem_g_off = pl.g_off;
     a.smem_red_off = pl.red_off;
     const int blocks = div_up(a.m, pl.tm);
-    static size_t configured[3] = {0, 0, 0};
-    if (pl.kind == 1) {
-        if (pl.smem_bytes > configured[2]) {
-            CUDA_CHECK(cudaFuncSetAttribute(fused_tile64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-            configured[2] = pl.smem_bytes;
-        }
-        B200_LAUNCH_PDL(fused_tile64_kernel, blocks, kT64Threads, pl.smem_bytes, pdl, a);
-    } else if (pl.rt == 4) {
-        if (pl.smem_bytes > configured[0]) {
-            CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-            configured[0] = pl.smem_bytes;
-        }
-        B200_LAUNCH((fused_update_kernel<64, 4>), blocks, kFusedThreads, pl.smem_bytes, a);
-    } else {
-        if (pl.smem_bytes > configured[1]) {
-            CUDA_CHECK(cudaFuncSetAttribute(fused_update_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-            configured[1] = pl.smem_bytes;
-        }
-        B200_LAUNCH((fused_update_kernel<64, 8>), blocks, kFusedThreads, pl.smem_bytes, a);
+    static size_t configured = 0;
+    if (pl.smem_bytes > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(fused_tile64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        configured = pl.smem_bytes;
     }
+    B200_LAUNCH_PDL(fused_tile64_kernel, blocks, kT64Threads, pl.smem_bytes, pdl, a);
 }
 
 void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out) {
