@@ -316,9 +316,10 @@ __global__ void __launch_bounds__(kR64Threads) rollout64_kernel(const Rollout64A
     const FusedNet& net = p.net;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* img = smem;
-    float* hA = img + net.img_floats;       // [64][E]: feature-major, one column per env
-    float* hB = hA + 64 * E;
-    float* part = hB + 64 * E;              // [4][8][E] partial action means
+    const int HW = net.max_width_pad;       // rows of the activation tiles (64 or 128)
+    float* hA = img + net.img_floats;       // [HW][E]: feature-major, one column per env
+    float* hB = hA + HW * E;
+    float* part = hB + HW * E;              // [4][8][E] partial action means
     for (int i = tid * 4; i < net.img_floats; i += kR64Threads * 4)
         *reinterpret_cast<float4*>(img + i) = *reinterpret_cast<const float4*>(p.image + i);
     const int L = net.L, A = net.sizes[L];
@@ -370,10 +371,11 @@ __global__ void __launch_bounds__(kR64Threads) rollout64_kernel(const Rollout64A
         float* hout = hB;
         for (int l = 0; l < L - 1; l++) {
             const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
-            if (4 * ug < pad4(n_out)) {
-                const float* wp = img + net.wt_off[l] + 4 * ug;
+            for (int ub = 0; ub < pad4(n_out); ub += 64)        // layers wider than 64 units: 64-unit blocks
+            if (ub + 4 * ug < pad4(n_out)) {
+                const float* wp = img + net.wt_off[l] + ub + 4 * ug;
                 const int ldw = net.ldw[l];
-                const float4 b = *reinterpret_cast<const float4*>(img + net.bs_off[l] + 4 * ug);
+                const float4 b = *reinterpret_cast<const float4*>(img + net.bs_off[l] + ub + 4 * ug);
                 float2 acc2[4][2];               // [unit][env pair]: packed FFMA2
                 const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(kR64Threads) rollout64_kernel(const Rollout64A
                 const int act = net.acts[l];
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    *reinterpret_cast<float4*>(hout + (4 * ug + c) * E + 4 * eg) =
+                    *reinterpret_cast<float4*>(hout + (ub + 4 * ug + c) * E + 4 * eg) =
                         make_float4(act_apply(acc[c][0], act), act_apply(acc[c][1], act), act_apply(acc[c][2], act), act_apply(acc[c][3], act));
             }
             __syncthreads();
@@ -526,10 +528,10 @@ void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buff
     static int use64 = -1;
     if (use64 < 0) { const char* v = getenv("PPO_B200_ROLLOUT"); use64 = (v && strcmp(v, "old") == 0) ? 0 : 1; }
     Rollout64Args r{};
-    bool narrow = true;                       // rollout64_kernel tiles at most 64 units per layer
+    bool narrow = true;                       // rollout64_kernel handles layers of up to 128 units (64-unit blocks)
     {
         NetDev* ndp = net_dev(policy->mu);
-        for (int w : ndp->sizes) narrow = narrow && w <= 64;
+        for (int w : ndp->sizes) narrow = narrow && w <= 128;
     }
     if (use64 && narrow && fused_image64(policy->mu, &r.net, &r.image)) {
         const int blocks = div_up(e->n_envs, kR64E);
@@ -551,7 +553,7 @@ void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buff
         r.ret_sum = e->d_ret_sum; r.ret_cnt = e->d_ret_cnt;
         r.obs_partial = e->obs_norm ? e->d_obs_partial : nullptr;
         r.horizon = e->base.horizon;
-        const size_t smem = ((size_t)r.net.img_floats + 2 * 64 * kR64E + 4 * 8 * kR64E) * sizeof(float);
+        const size_t smem = ((size_t)r.net.img_floats + 2 * r.net.max_width_pad * kR64E + 4 * 8 * kR64E) * sizeof(float);
         static size_t configured64 = 0;
         if (smem > configured64) {
             CUDA_CHECK(cudaFuncSetAttribute(rollout64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -156,15 +156,16 @@ def test_host_pendulum_env_semantics(L):
         assert not term.value and trunc.value == (t == 199)
 
 
-def test_device_rollout_is_self_consistent(L):
-    """Fused device rollout (4096 envs x 16 steps): every stored row must be reproducible by the
+@pytest.mark.parametrize("H", [64, 128, 32])
+def test_device_rollout_is_self_consistent(L, H):
+    """Fused device rollout (4096 envs x 16 steps; hidden widths 64 / 128 (two 64-unit blocks) / 32): every stored row must be reproducible by the
     oracle from the stored state/action: log-prob under the policy, reward and next state from the
     Pendulum definition, reference bookkeeping of next_state -> state and the forced last-step flag."""
     n_envs, T = 4096, 16
     cabi.srand(5)
     env = L.create_pendulum_env_cuda(n_envs, 7)
     assert L.ppo_b200_env_is_device(env) == 1 and L.ppo_b200_env_num_envs(env) == n_envs
-    sizes = [3, 64, 64, 1]
+    sizes = [3, H, H, 1]
     ppo = make_ppo(L, sizes, RELU3, n_envs * T)
     L.collect_trajectories(ppo.contents.buffer, env, ppo.contents.policy, n_envs * T)
     L.ppo_b200_sync_host(ppo)
