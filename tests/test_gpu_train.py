@@ -111,6 +111,34 @@ def test_update_phase_matches_oracle(L, sizes, acts, n, mb, npol, nval, path):
     L.free_ppo(ppo)
 
 
+@pytest.mark.parametrize("sizes,acts,n,mb", [([3, 64, 64, 1], ["tanh", "tanh", "none"], 4096, 1024),
+                                             ([17, 32, 32, 6], RELU3, 2048, 512),
+                                             ([3, 128, 128, 1], RELU3, 2048, 512),
+                                             ([17, 256, 256, 6], RELU3, 4096, 2048)])
+def test_update_is_bitwise_reproducible(L, sizes, acts, n, mb):
+    """Every reduction in the update path runs in a fixed order (slab sums, split-K, loss heads; the reference uses float
+    atomics, src/policy.cu:157), so two runs from the same state must agree BIT FOR BIT.  This doubles as the race
+    detector for the hand-synchronised shared-memory kernels (compute-sanitizer is not available on the GPU pool)."""
+    outs = []
+    for _ in range(3):
+        cabi.srand(31)
+        ppo = make_ppo(L, sizes, acts, n)
+        T = oracle.Trainer(sizes, acts, batch_size=mb, n_epochs_policy=2, n_epochs_value=2, init=False)
+        T.mu[:] = b200.nn_get_params(L, ppo.contents.policy.contents.mu)
+        b = synthetic_buffer(T, np.random.default_rng(5), sizes, acts, n)
+        fill_host_buffer(ppo, b)
+        cabi.srand(32)
+        L.ppo_b200_update(ppo, 0.99, mb, 2, 2)
+        outs.append((b200.nn_get_params(L, ppo.contents.V, sync=False).copy(),
+                     b200.nn_get_params(L, ppo.contents.policy.contents.mu, sync=False).copy(),
+                     host_field(ppo, "advantage", (n,)).copy(), L.ppo_b200_last_policy_loss(ppo), L.ppo_b200_last_value_loss(ppo)))
+        L.free_ppo(ppo)
+    for o in outs[1:]:
+        for a, ref in zip(o[:3], outs[0][:3]):
+            assert np.array_equal(a, ref)
+        assert o[3] == outs[0][3] and o[4] == outs[0][4]
+
+
 def test_train_ppo_epoch_toy_env_matches_oracle(L):
     """Reference entry point, opaque host env (toy env of src/env.c): rollout on the GPU one step at a
     time from the reference's rand() stream, then the update.  One iteration, so GPU-vs-libm ulps in
