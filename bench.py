@@ -139,12 +139,22 @@ class C2(Workload):
         self.env = L.create_pendulum_env_cuda(self.N_ENVS, 100 + self.rank)
         self.ppo = L.create_ppo(cabi.cstr_array(self.ACTS), cabi.int_array(self.SIZES), len(self.SIZES), self.cap,
                                 3e-4, 3e-4, 0.95, 0.2, 0.0, 1.0, True)
-        L.ppo_b200_set_permutation_mode(self.ppo, -1, 7 + self.rank)
+        L.ppo_b200_set_permutation_mode(self.ppo, 1, 7 + self.rank)
 
     def step_device(self, k):
         self.L.ppo_b200_train_iterations(self.ppo, self.env, k, self.MB, self.N_POL, self.N_VAL)
 
     def step_e2e(self, k):
+        """The reference's data flow with HOST buffers (src/ppo.cu:482-538): the rollout lands in the host buffer, every
+        iteration uploads it (buffer_to_device), updates, and mirrors buffer + weights back to the host."""
+        L, ppo = self.L, self.ppo
+        for _ in range(k):
+            L.collect_trajectories(ppo.contents.buffer, self.env, ppo.contents.policy, self.cap)   # fused device rollout
+            L.buffer_to_host(ppo.contents.buffer)                                                   # D2H: rollout -> pinned host arrays
+            L.ppo_b200_update(ppo, 0.99, self.MB, self.N_POL, self.N_VAL)                           # H2D + GAE + epochs + D2H mirrors
+
+    def step_api(self, k):
+        """train_ppo_epoch, the one call a ppo.c user makes: device rollout + update + host mirrors (no host input exists)."""
         self.L.train_ppo_epoch(self.ppo, self.env, self.cap * k, self.MB, self.N_POL, self.N_VAL)
 
     def units_per_step(self):
@@ -154,7 +164,8 @@ class C2(Workload):
         S, A = self.SIZES[0], self.SIZES[-1]
         p_mu = mlp_params(self.SIZES)
         p_v = mlp_params(self.SIZES[:-1] + [1])
-        return 0, self.cap * (4 * (2 * S + A + 4) + 2) + 4 * (p_mu + p_v + A)
+        buf = self.cap * (4 * (2 * S + A + 4) + 2)
+        return buf, 2 * buf + 4 * (p_mu + p_v + A)
 
     def config(self):
         return {"workload": "c2: Pendulum-v1 PPO, %d device envs/GPU x T=%d, 2x64 tanh MLP, fp32, minibatch %d/GPU, "
@@ -162,10 +173,11 @@ class C2(Workload):
                 "env_steps_per_step_per_gpu": self.cap, "parallelism": "dp%d" % self.world,
                 "l2": "inputs larger than L2: every step streams the 819200-row buffer (38 MB of rows + 14 permutations) "
                       "through 700 minibatch launches and rewrites it in the rollout; no explicit flush",
-                "permutation": "device generator (auto mode after a device rollout)",
-                "e2e_call": "train_ppo_epoch (reference API): device rollout + update + buffer_to_host/policy_to_host/"
-                            "nn_write_weights_to_host every iteration (src/ppo.cu:536-538); the envs live on the device, "
-                            "so there is no per-step host input: h2d_bytes_per_step is 0 by construction"}
+                "permutation": "device generator (mode 1); the reference's host rand() chain is the bit-exact mode of the parity tests",
+                "e2e_call": "reference data flow with HOST buffers (src/ppo.cu:482-538): collect_trajectories (device rollout) -> "
+                            "buffer_to_host (D2H, pinned) -> ppo_b200_update = buffer_to_device (H2D of all nine arrays) + GAE + epochs + "
+                            "buffer_to_host/policy_to_host/nn_write_weights_to_host (D2H); `api` = train_ppo_epoch, the single call a "
+                            "user makes (device rollout, no host input, host mirrors refreshed every iteration)"}
 
     def extra(self, ms):
         nb = self.cap // self.MB
@@ -816,7 +828,19 @@ def run_gpu_arm(args):
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     e2e_ms = max(f0.elapsed_time(f1), 0.0)
+    api_ms = None
+    if hasattr(wl, "step_api"):
+        wl.step_api(1)
+        barrier()
+        ta = time.perf_counter()
+        wl.step_api(e2e_steps)
+        barrier()
+        api_ms = 1e3 * (time.perf_counter() - ta)
     if world > 1:
+        if api_ms is not None:
+            ta_t = torch.tensor([api_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(ta_t, op=dist.ReduceOp.MAX)
+            api_ms = float(ta_t.cpu()[0])
         tt = torch.tensor([ms, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms, wall_ms = (float(x) for x in tt.cpu())
@@ -846,6 +870,8 @@ def run_gpu_arm(args):
             "config": wl.config(),
             "e2e": {"value": units * e2e_steps / (e2e_ms * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+            "api": None if api_ms is None else {"value": units * e2e_steps / (api_ms * 1e-3), "unit": wl.unit,
+                                                 "ms_per_step": api_ms / e2e_steps, "call": "train_ppo_epoch"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
