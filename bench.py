@@ -164,8 +164,9 @@ class C2(Workload):
         S, A = self.SIZES[0], self.SIZES[-1]
         p_mu = mlp_params(self.SIZES)
         p_v = mlp_params(self.SIZES[:-1] + [1])
-        buf = self.cap * (4 * (2 * S + A + 4) + 2)
-        return buf, 2 * buf + 4 * (p_mu + p_v + A)
+        buf = self.cap * (4 * (2 * S + A + 4) + 2)            # all nine arrays (buffer_to_host after the rollout)
+        # ppo_b200_update moves the seven input arrays up and only advantage / adv_target (+ weights) down
+        return buf - 8 * self.cap, buf + 8 * self.cap + 4 * (p_mu + p_v + A)
 
     def config(self):
         return {"workload": "c2: Pendulum-v1 PPO, %d device envs/GPU x T=%d, 2x64 tanh MLP, fp32, minibatch %d/GPU, "
@@ -175,8 +176,8 @@ class C2(Workload):
                       "through 700 minibatch launches and rewrites it in the rollout; no explicit flush",
                 "permutation": "device generator (mode 1); the reference's host rand() chain is the bit-exact mode of the parity tests",
                 "e2e_call": "reference data flow with HOST buffers (src/ppo.cu:482-538): collect_trajectories (device rollout) -> "
-                            "buffer_to_host (D2H, pinned) -> ppo_b200_update = buffer_to_device (H2D of all nine arrays) + GAE + epochs + "
-                            "buffer_to_host/policy_to_host/nn_write_weights_to_host (D2H); `api` = train_ppo_epoch, the single call a "
+                            "buffer_to_host (D2H of all nine arrays, pinned) -> ppo_b200_update = H2D of the seven input arrays + GAE + epochs + "
+                            "D2H of advantage / adv_target + policy_to_host / nn_write_weights_to_host; `api` = train_ppo_epoch, the single call a "
                             "user makes (device rollout, no host input, host mirrors refreshed every iteration)"}
 
     def extra(self, ms):
@@ -273,7 +274,8 @@ class UpdateOnly(Workload):
         S, A = self.SIZES[0], self.SIZES[-1]
         per_row = 4 * (2 * S + A + 4) + 2
         p = mlp_params(self.SIZES) + mlp_params(self.SIZES[:-1] + [1]) + A
-        return self.cap * per_row, self.cap * per_row + 4 * p
+        # ppo_b200_update: seven input arrays up, advantage / adv_target + weights down
+        return self.cap * (per_row - 8), self.cap * 8 + 4 * p
 
     def base_config(self, label):
         return {"workload": label, "buffer_rows_per_gpu": self.cap, "minibatch_per_gpu": self.MB,
@@ -282,8 +284,8 @@ class UpdateOnly(Workload):
                       % (self.cap, self.cap * 4 * (self.SIZES[0] + self.SIZES[-1] + 3) / 1e6),
                 "permutation": "device generator (mode 1); the reference's host rand() chain is the bit-exact mode "
                                "used by the parity tests",
-                "e2e_call": "ppo_b200_update: buffer_to_device (all 9 arrays, pinned host) + GAE + epochs + "
-                            "buffer_to_host/policy_to_host/nn_write_weights_to_host"}
+                "e2e_call": "ppo_b200_update on a HOST-filled buffer: upload of the seven input arrays (pinned host) + GAE + epochs + "
+                            "download of advantage / adv_target + policy_to_host / nn_write_weights_to_host"}
 
     def teardown(self):
         self.L.free_ppo(self.ppo)

@@ -315,6 +315,36 @@ static void copy_all(TrajectoryBuffer* b, bool to_device) {
     CUDA_CHECK(cudaStreamSynchronize(stream()));
 }
 
+}  // extern "C"
+
+namespace b200 {
+// Update phase on a host-filled buffer (ppo_b200_update): GAE overwrites advantage / adv_target and nothing else in the
+// buffer changes, so the mirrors move only what is needed - the seven input arrays up, the two output arrays down -
+// instead of the reference's nine blocking copies each way (src/trajectory_buffer.cu:227-273).  The post-condition is the
+// reference's: on return the host set is active and holds exactly what the device holds.
+void buffer_upload_inputs(TrajectoryBuffer* b) {
+    const size_t n = b->capacity, S = b->state_size, A = b->action_size;
+    auto up = [&](void* d, const void* h, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream())); };
+    up(b->d_state_p, b->h_state_p, n * S * 4);
+    up(b->d_next_state_p, b->h_next_state_p, n * S * 4);
+    up(b->d_reward_p, b->h_reward_p, n * 4);
+    up(b->d_terminated_p, b->h_terminated_p, n);
+    up(b->d_truncated_p, b->h_truncated_p, n);
+    up(b->d_action_p, b->h_action_p, n * A * 4);
+    up(b->d_logprob_p, b->h_logprob_p, n * 4);
+    activate(b, true);
+}
+void buffer_download_outputs(TrajectoryBuffer* b) {
+    const size_t n = b->capacity;
+    CUDA_CHECK(cudaMemcpyAsync(b->h_advantage_p, b->d_advantage_p, n * 4, cudaMemcpyDeviceToHost, stream()));
+    CUDA_CHECK(cudaMemcpyAsync(b->h_adv_target_p, b->d_adv_target_p, n * 4, cudaMemcpyDeviceToHost, stream()));
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    activate(b, false);
+}
+}  // namespace b200
+
+extern "C" {
+
 void buffer_to_device(TrajectoryBuffer* b) {    // src/trajectory_buffer.cu:227-249
     copy_all(b, true);
     activate(b, true);

@@ -151,7 +151,9 @@ void launch_policy_head(const float* mu, const float* log_std, const float* acti
 void launch_gather(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* state,
                    const float* action, const float* logprob, const float* advantage, const float* adv_target,
                    float* states, float* actions, float* logprobs, float* advantages, float* adv_targets);
-void host_shuffle(int* idx, int limit);   // the reference's rand() swap chain, trajectory_buffer.cu:132-141
+void host_shuffle(int* idx, int limit);
+void buffer_upload_inputs(TrajectoryBuffer* b);      // 7 input arrays host -> device (async), device set active
+void buffer_download_outputs(TrajectoryBuffer* b);   // advantage, adv_target device -> host, host set active   // the reference's rand() swap chain, trajectory_buffer.cu:132-141
 
 // ---- env.cu -----------------------------------------------------------------------------------
 struct DeviceEnv;

@@ -398,9 +398,13 @@ void ppo_b200_update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_
 
 void ppo_b200_update(PPO* ppo, float gamma, int batch_size, int n_epochs_policy, int n_epochs_value) {
     trainer(ppo)->last_rollout_on_device = false;
-    ppo_b200_buffer_upload(ppo);
+    buffer_upload_inputs(ppo->buffer);            // the GAE outputs need no upload, the kernels run behind the copies
+    ppo->buffer->idx = 0;
+    ppo->buffer->full = true;
     update_device(ppo, gamma, batch_size, n_epochs_policy, n_epochs_value);
-    ppo_b200_sync_host(ppo);
+    buffer_download_outputs(ppo->buffer);         // only advantage / adv_target changed on the device
+    policy_to_host(ppo->policy);
+    nn_write_weights_to_host(ppo->V);
 }
 
 void ppo_b200_train_iterations(PPO* ppo, Env* env, int n_iters, int batch_size, int n_epochs_policy, int n_epochs_value) {
