@@ -6,7 +6,7 @@
 Workloads = BASELINE.json configs:
   c2 (default, configs[1])  Pendulum-v1 PPO, 4096 device envs/GPU x T=200, 2x64 tanh, fp32.  One step =
        one PPO iteration: fused device rollout (819 200 env-steps/GPU) + GAE + 10 value + 4 policy
-       epochs of minibatch 16 384 (the reference schedule, src/main.c:33-43).  Unit: env-steps/s.
+       epochs of minibatch 18 944 = 148 SMs x 2 CTAs x 64 rows (the reference schedule, src/main.c:33-43).  Unit: env-steps/s.
   c3 (configs[2])  HalfCheetah-shaped synthetic buffer (S=17, A=6), T=2048 x N=512 per GPU, 2x256 ReLU,
        update only (GAE + 10 value + 4 policy epochs, minibatch 65536/GPU; --mb 4096 for the small-minibatch line).
        Unit: update samples/s.
@@ -126,7 +126,10 @@ class C2(Workload):
     """Pendulum-v1 PPO, vectorised device envs (BASELINE.json configs[1])."""
     name = "c2"
     SIZES, ACTS = [3, 64, 64, 1], ["tanh", "tanh", "none"]
-    N_ENVS, T, MB, N_POL, N_VAL = 4096, 200, 16384, 4, 10
+    # minibatch = 148 SMs x 2 resident CTAs x 64 rows: every SM holds exactly two tiles of each minibatch (at 16384 rows
+    # 40 of the 148 SMs hold one).  43 minibatches per epoch; like the reference (src/ppo.cu:387: limit / batch_size) the
+    # remainder of the shuffled buffer (0.56 %) is not visited in that epoch.
+    N_ENVS, T, MB, N_POL, N_VAL = 4096, 200, 18944, 4, 10
     CPU_STEPS, CPU_MB = 8200, 2050           # 41 episodes of 200 steps, 4 minibatches per epoch
 
     def init_sizes(self):
@@ -172,8 +175,10 @@ class C2(Workload):
         return {"workload": "c2: Pendulum-v1 PPO, %d device envs/GPU x T=%d, 2x64 tanh MLP, fp32, minibatch %d/GPU, "
                             "%d value + %d policy epochs (BASELINE.json configs[1])" % (self.N_ENVS, self.T, self.MB, self.N_VAL, self.N_POL),
                 "env_steps_per_step_per_gpu": self.cap, "parallelism": "dp%d" % self.world,
+                "minibatch": "%d = 148 SMs x 2 resident CTAs x 64 rows; %d minibatches per epoch, the last %d shuffled rows of an epoch are "
+                             "not visited (reference semantics, src/ppo.cu:387)" % (self.MB, self.cap // self.MB, self.cap % self.MB),
                 "l2": "inputs larger than L2: every step streams the 819200-row buffer (38 MB of rows + 14 permutations) "
-                      "through 700 minibatch launches and rewrites it in the rollout; no explicit flush",
+                      "through 602 minibatch launches and rewrites it in the rollout; no explicit flush",
                 "permutation": "device generator (mode 1); the reference's host rand() chain is the bit-exact mode of the parity tests",
                 "e2e_call": "reference data flow with HOST buffers (src/ppo.cu:482-538): collect_trajectories (device rollout) -> "
                             "buffer_to_host (D2H of all nine arrays, pinned) -> ppo_b200_update = H2D of the seven input arrays + GAE + epochs + "

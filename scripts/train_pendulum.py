@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Learning-curve run of the c2 configuration (BASELINE.json configs[1]): Pendulum-v1, 4096 device envs x T=200,
 2x64 MLP, the reference's hyper-parameters (src/main.c:33-43: lr 3e-4 both, lambda 0.95, eps 0.2, ent 0, init std 1,
-4 policy / 10 value epochs, gamma 0.99) at minibatch 16384.  Prints / writes the mean undiscounted episode return
+4 policy / 10 value epochs, gamma 0.99) at minibatch 18944 (= 148 SMs x 2 CTAs x 64 rows).  Prints / writes the mean undiscounted episode return
 per iteration (eval_ppo's "R", src/ppo.cu:581, over the 4096 training episodes of that iteration).
 
     python scripts/train_pendulum.py [--iters 80] [--act tanh|relu] [--obs-norm] [--mb 16384] [--out gpurun_out/learning_curve.json]
@@ -16,7 +16,7 @@ ap.add_argument("--iters", type=int, default=80)
 ap.add_argument("--act", default="tanh")
 ap.add_argument("--envs", type=int, default=4096)
 ap.add_argument("--T", type=int, default=200)
-ap.add_argument("--mb", type=int, default=16384)
+ap.add_argument("--mb", type=int, default=18944)
 ap.add_argument("--lr", type=float, default=3e-4)
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--obs-norm", action="store_true")
