@@ -1,3 +1,4 @@
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o scratch/ubench/ffma scratch/ubench/ffma.cu ; run: ./scratch/ubench/ffma
 // FFMA throughput by operand form (sm_100a).  All loops are pure FFMA streams (checked in SASS).
 #include <cstdio>
 #include <cuda_runtime.h>
