@@ -358,6 +358,9 @@ const char* ppo_b200_version(void);
  * bracketed by a CUDA-event pair on the launching stream.  end() writes "name count total_ms" lines. */
 void ppo_b200_profile_begin(void);
 int  ppo_b200_profile_end(char* out, int out_bytes);
+/* Debug aid (env PPO_B200_PHASE_DEBUG=1): %globaltimer stamps of the phases of the last fused minibatch kernel,
+ * [blocks][16] 64-bit values (scratch/phase_debug.py prints the timeline).  No-op when the env var is not set. */
+void ppo_b200_debug_phase_stamps(unsigned long long* out, int blocks);
 
 /* ---- stage-level kernels on plain DEVICE arrays ------------------------------------------------ */
 /* GAE + returns (src/ppo.cu:338-353) as one segmented reverse scan; optional normalisation

@@ -51,6 +51,7 @@ EXTENSION_API = {
     "ppo_b200_version": (C.c_char_p, []),
     "ppo_b200_profile_begin": (None, []),
     "ppo_b200_profile_end": (C.c_int, [C.c_char_p, C.c_int]),
+    "ppo_b200_debug_phase_stamps": (None, [vp, C.c_int]),
     "ppo_b200_gae": (None, [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, vp]),
     "ppo_b200_adam_flat": (None, [vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
     "ppo_b200_gather": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 10),

@@ -36,6 +36,10 @@ def test_library_loads_and_exports_every_declared_symbol():
     for n in cabi.REFERENCE_API:
         assert n in names, n
     assert b"sm_100a" in lib.ppo_b200_version()
+    # ... and nothing else: every unmangled (C ABI) function the library exports is declared in the boundary header
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "ppo.c_b200", "libppo_b200.so")], text=True)
+    exported = {ln.split()[2] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] == "T" and not ln.split()[2].startswith("_Z")}
+    assert exported - names == set(), sorted(exported - names)
 
 
 def test_struct_layouts_match_reference_abi():
@@ -133,3 +137,16 @@ def test_reference_main_runs_unmodified_on_the_drop_in():
     assert len(rs) >= 11, res.stdout[-2000:]
     assert max(rs[1:]) > rs[0] + 300, rs
     assert os.path.exists(os.path.join(ROOT, "build", "abi_probe", "ppo_model.bin"))
+
+
+def test_boundary_header_compiles_as_c_and_cxx():
+    """include/ppo_b200.h (and every thin compatibility header) is valid C11 and C++17 on its own, warnings as errors."""
+    tmp = os.path.join(ROOT, "build", "abi_probe")
+    os.makedirs(tmp, exist_ok=True)
+    heads = ["ppo.h", "policy.h", "neural_network.h", "trajectory_buffer.h", "adam.h", "loss.h", "mat_mul.h",
+             "activation_function.h", "env.h", "gym_env.h", "ppo_b200.h"]
+    src = "".join('#include "%s"\n' % h for h in heads) + "int main(void) { return (int)sizeof(PPO) == 0; }\n"
+    for name, cc, std in (("hdr.c", "gcc", "-std=c11"), ("hdr.cpp", "g++", "-std=c++17")):
+        path = os.path.join(tmp, name)
+        open(path, "w").write(src)
+        subprocess.check_call([cc, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), path])
