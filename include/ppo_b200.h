@@ -422,6 +422,8 @@ void ppo_b200_set_obs_norm(PPO* ppo, int enabled);
 void ppo_b200_get_obs_norm(const Env* env, float* mean3, float* std3, double* count);
 /* mean undiscounted return per episode of the last device rollout (eval_ppo's "R", src/ppo.cu:581) */
 float ppo_b200_last_mean_return(PPO* ppo);
+/* the three numbers the last eval_ppo call printed ("J: %f R: %f Episodes: %d", src/ppo.cu:581) */
+void ppo_b200_last_eval(PPO* ppo, float* J, float* R, int* episodes);
 float ppo_b200_last_value_loss(PPO* ppo);
 float ppo_b200_last_policy_loss(PPO* ppo);
 

@@ -526,3 +526,28 @@ int orc_collect(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int
     free(cache);
     return idx;
 }
+
+/* eval_ppo, ppo.cu:560-583: reset_buffer, collect `steps` transitions from index 0, then the reverse walk that
+ * accumulates the undiscounted reward sum and the per-episode discounted return J (float arithmetic, in the
+ * reference's order; the episode that ends at steps-1 is counted in n_episodes but its J is only added when an
+ * earlier done flag is met, exactly as the reference does). */
+void orc_eval(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int capacity, int steps, int env_id,
+              float gamma, float* J_out, float* R_out, int* episodes_out) {
+    orc_collect(cfg, model, buf, capacity, 0, steps, env_id);
+    float rewards = buf->reward[steps - 1];
+    float episode_J = buf->reward[steps - 1];
+    int n_episodes = 1;
+    float sum_J = 0;
+    for (int i = steps - 2; i >= 0; i--) {
+        rewards += buf->reward[i];
+        episode_J = buf->reward[i] + gamma * episode_J;
+        if (buf->terminated[i] || buf->truncated[i]) {
+            n_episodes++;
+            sum_J += episode_J;
+            episode_J = 0;
+        }
+    }
+    *J_out = sum_J / n_episodes;
+    *R_out = rewards / n_episodes;
+    *episodes_out = n_episodes;
+}

@@ -116,6 +116,10 @@ float orc_update(const OrcConfig* cfg, OrcModel* model, OrcBuffer* buf, int* per
 int orc_collect(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int capacity,
                 int start_idx, int steps, int env_id);
 
+/* eval_ppo (ppo.cu:560-583): rollout of `steps` transitions from index 0 + the J / R / Episodes statistics it prints. */
+void orc_eval(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int capacity, int steps, int env_id,
+              float gamma, float* J_out, float* R_out, int* episodes_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -667,7 +667,8 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
         const int sp = narrow_in ? (n <= 8 ? 8 : n <= 16 ? 16 : n <= 24 ? 24 : 32) : 8;
         const int gx = div_up(wide_n, 256);
         const int R = m <= 16384 ? 1 : std::max(1, std::min(16, div_up(2 * num_sms(), gx * splits)));     // ~2 CTAs per SM
-        float* part = static_cast<float*>(scratch(kScratchPartials, (size_t)splits * R * wide_n * (sp + 1) * sizeof(float)));
+        // own slot: callers (mat_mul_backwards_cuda) keep their split-K slabs in kScratchPartials across this call
+        float* part = static_cast<float*>(scratch(kScratchSkinny, (size_t)splits * R * wide_n * (sp + 1) * sizeof(float)));
         dim3 gs(gx, splits, R);
         if (narrow_in) {
             if (sp == 8) B200_LAUNCH((skinny_dw_kernel<8, true>), gs, 256, 0, part, g, x, m, n, l, rows, gW_part, gb_part, stride);

@@ -35,6 +35,8 @@ struct Trainer {
     int n_v_steps = 0, n_p_steps = 0;
     bool obs_norm = false;
     double* d_dist_triples = nullptr;
+    float eval_J = 0.f, eval_R = 0.f;   // what the last eval_ppo printed (src/ppo.cu:581)
+    int eval_episodes = 0;
 };
 static std::unordered_map<PPO*, Trainer*> g_trainers;
 
@@ -449,7 +451,18 @@ void eval_ppo(PPO* ppo, Env* env, int steps) {                     // src/ppo.cu
         }
     }
     printf("J: %f R: %f Episodes: %d\n", sum_J / n_episodes, rewards / n_episodes, n_episodes);
+    Trainer* t = trainer(ppo);
+    t->eval_J = sum_J / n_episodes;
+    t->eval_R = rewards / n_episodes;
+    t->eval_episodes = n_episodes;
     reset_buffer(ppo->buffer);
+}
+
+void ppo_b200_last_eval(PPO* ppo, float* J, float* R, int* episodes) {
+    Trainer* t = trainer(ppo);
+    if (J) *J = t->eval_J;
+    if (R) *R = t->eval_R;
+    if (episodes) *episodes = t->eval_episodes;
 }
 
 void save_ppo(PPO* ppo, const char* filename) {                    // src/ppo.cu:585-607, same byte format

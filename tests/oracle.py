@@ -279,3 +279,11 @@ class Trainer:
         cb = self._cbuf(b)
         return lib().orc_collect(C.byref(self.cfg), C.byref(self.model), C.byref(cb), b["reward"].shape[0],
                                  start_idx, steps, env_id)
+
+    def eval(self, b, steps, env_id, gamma=0.99):
+        """eval_ppo (src/ppo.cu:560-583): returns (J, R, episodes) as float32 / int."""
+        cb = self._cbuf(b)
+        J, R, n = C.c_float(), C.c_float(), C.c_int()
+        lib().orc_eval(C.byref(self.cfg), C.byref(self.model), C.byref(cb), b["reward"].shape[0], steps, env_id,
+                       C.c_float(gamma), C.byref(J), C.byref(R), C.byref(n))
+        return f32(J.value), f32(R.value), n.value

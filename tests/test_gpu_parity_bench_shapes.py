@@ -1,0 +1,234 @@
+"""Parity at the shapes bench.py measures, and the arguments behind the stated tolerances (-m gpu).
+
+Round-1 review items: the benched minibatch sizes (c2: 18 944 rows = 296 tiles; c3: 65 536 rows through the skinny-dW
+row splits) had no whole-update oracle comparison; the post-Adam tolerance was asserted, not justified; the TF32 update was
+never compared with the fp32 oracle; eval_ppo and the device mean-return had no oracle check.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import b200
+import cabi
+import f64ref
+import oracle
+from conftest import nerr
+from test_gpu_train import RELU3, fill_host_buffer, host_field, make_ppo, synthetic_buffer
+
+pytestmark = pytest.mark.gpu
+f32, u8 = np.float32, np.uint8
+TANH3 = ["tanh", "tanh", "none"]
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = b200.lib()
+    assert lib.ppo_b200_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return lib
+
+
+def _oracle_value_grads(T, b, rows):
+    """Gradient of ONE value minibatch at T's current weights (stage functions of the oracle)."""
+    y, cache = oracle.mlp_forward(T.v, T.sizes_v, T.acts, b["state"][rows])
+    return oracle.mlp_backward(T.v, T.sizes_v, T.acts, cache, oracle.mse_derivative(y.ravel(), b["adv_target"][rows]).reshape(-1, 1))
+
+
+def _oracle_policy_grads(T, b, rows, eps=0.2, ent=0.0):
+    mu, cache = oracle.mlp_forward(T.mu, T.sizes_mu, T.acts, b["state"][rows])
+    lp = oracle.log_prob(mu, T.log_std, b["action"][rows])
+    _, g, ge = oracle.policy_loss_and_grad(b["advantage"][rows], lp, b["logprob"][rows], oracle.entropy(T.log_std), ent, eps)
+    gmu, gls = oracle.log_prob_backwards(mu, T.log_std, b["action"][rows], g, ref_index=False)
+    return oracle.mlp_backward(T.mu, T.sizes_mu, T.acts, cache, gmu), gls + ge
+
+
+@pytest.mark.parametrize("sizes,acts,n,mb,path", [
+    ([3, 64, 64, 1], TANH3, 2 * 18944 + 77, 18944, 1),      # c2: the benched minibatch (296 tiles of 64 rows)
+    ([3, 64, 64, 1], RELU3, 3000, 64, 1),                    # the reference default (one tile)
+    ([3, 128, 128, 1], RELU3, 4096 + 5, 2048, 1),            # reference default width
+    ([17, 32, 32, 6], RELU3, 8192, 4096, 1),
+    ([17, 256, 256, 6], RELU3, 2 * 4096 + 9, 4096, 0),       # c3 widths, layer-wise kernels
+])
+def test_pre_adam_gradients_match_oracle(L, sizes, acts, n, mb, path):
+    """Gradients BEFORE Adam, inside the whole update call, at 1e-5: with both learning rates 0 the weights never move
+    (w - 0*m/denom == w exactly), so after the call the device gradient arenas hold the gradient of the LAST minibatch of
+    the last value / policy epoch at the initial weights, which the oracle's stage functions reproduce from the logged
+    permutation."""
+    L.ppo_b200_set_kernel_path(path)
+    seed = 7 + n
+    cabi.srand(seed)
+    ppo = L.create_ppo(cabi.cstr_array(acts), cabi.int_array(sizes), len(sizes), n, 0.0, 0.0, 0.95, 0.2, 0.0, 1.0, True)
+    cabi.srand(seed)
+    T = oracle.Trainer(sizes, acts, lr_policy=0.0, lr_v=0.0, batch_size=mb, n_epochs_policy=1, n_epochs_value=1, ref_index=False)
+    b = synthetic_buffer(T, np.random.default_rng(seed), sizes, acts, n)
+    fill_host_buffer(ppo, b)
+    cabi.srand(seed + 1)
+    L.ppo_b200_update(ppo, 0.99, mb, 1, 1)
+    cabi.srand(seed + 1)
+    mu0, v0 = T.mu.copy(), T.v.copy()
+    perms, _ = T.update(b, log_perms=True)
+    assert np.array_equal(T.mu, mu0) and np.array_equal(T.v, v0)
+    assert np.array_equal(b200.nn_get_params(L, ppo.contents.V, sync=False), v0)
+    nb = n // mb
+    gv = _oracle_value_grads(T, b, perms[0][(nb - 1) * mb:nb * mb])
+    gp_last, gls_last = _oracle_policy_grads(T, b, perms[1][(nb - 1) * mb:nb * mb])
+    dv = b200.nn_get_device_grads(L, ppo.contents.V)
+    dp = b200.nn_get_device_grads(L, ppo.contents.policy.contents.mu)
+    dls = b200.d2h(L, ppo.contents.policy.contents.d_log_std_grad, (sizes[-1],))
+    errs = (nerr(dv, gv), nerr(dp, gp_last), nerr(dls, gls_last))
+    print("pre-Adam gradient errors (V, mu, log_std):", errs)
+    assert max(errs) < 1e-5
+    L.ppo_b200_set_kernel_path(-1)
+    L.free_ppo(ppo)
+
+
+def _run_update_three_ways(L, sizes, acts, n, mb, npol, nval, seed, precision=0):
+    cabi.srand(seed)
+    ppo = make_ppo(L, sizes, acts, n)
+    cabi.srand(seed)
+    T = oracle.Trainer(sizes, acts, batch_size=mb, n_epochs_policy=npol, n_epochs_value=nval, ref_index=False)
+    b = synthetic_buffer(T, np.random.default_rng(seed), sizes, acts, n)
+    fill_host_buffer(ppo, b)
+    mu0, v0, ls0 = T.mu.copy(), T.v.copy(), T.log_std.copy()
+    L.ppo_b200_set_matmul_precision(precision)
+    cabi.srand(seed + 1)
+    L.ppo_b200_update(ppo, 0.99, mb, npol, nval)
+    after = cabi.rand()
+    L.ppo_b200_set_matmul_precision(0)
+    cabi.srand(seed + 1)
+    perms, losses = T.update(b, log_perms=True, log_losses=True)
+    assert cabi.rand() == after
+    gpu = dict(v=b200.nn_get_params(L, ppo.contents.V, sync=False), mu=b200.nn_get_params(L, ppo.contents.policy.contents.mu, sync=False),
+               log_std=np.ctypeslib.as_array(ppo.contents.policy.contents.log_std, shape=(sizes[-1],)).copy(),
+               advantage=host_field(ppo, "advantage", (n,)), adv_target=host_field(ppo, "adv_target", (n,)),
+               v_loss=L.ppo_b200_last_value_loss(ppo), p_loss=L.ppo_b200_last_policy_loss(ppo))
+    L.free_ppo(ppo)
+    return gpu, T, b, perms, losses, (mu0, v0, ls0)
+
+
+def _report(tag, gpu, T, ref64):
+    m64, v64 = ref64[0], ref64[1]
+    rows = []
+    for name, got, orc, r64 in (("V", gpu["v"], T.v, v64), ("mu", gpu["mu"], T.mu, m64)):
+        scale = np.max(np.abs(r64))
+        rows.append(dict(net=name, gpu_vs_oracle=nerr(got, orc), gpu_vs_f64=nerr(got, r64), oracle_vs_f64=nerr(orc, r64),
+                         frac_gpu_vs_oracle_gt_1e5=float(np.mean(np.abs(got - orc) > 1e-5 * scale))))
+    print(tag, json.dumps(rows))
+    return rows
+
+
+@pytest.mark.parametrize("sizes,acts,n,mb,npol,nval", [
+    ([3, 64, 64, 1], TANH3, 2 * 18944 + 77, 18944, 2, 2),         # c2 shape: minibatch 18 944, 296 tiles, tail rows unvisited
+    ([3, 64, 64, 1], TANH3, 4096, 256, 2, 3),
+    ([17, 32, 32, 6], RELU3, 8192, 1024, 2, 2),
+])
+def test_update_at_bench_minibatch_matches_oracle_and_float64(L, sizes, acts, n, mb, npol, nval):
+    """Whole update (GAE + value epochs + policy epochs) at the benched minibatch against (a) the reference-order fp32
+    oracle and (b) the float64 restatement (tests/f64ref.py) on the same permutations.
+    Stated tolerance: post-Adam weights within 1e-5 norm-wise of the oracle.  Where an element exceeds it, the float64
+    arbiter must show that the GPU is no further from the exact result than the reference-order fp32 arithmetic is
+    (Adam's first steps turn a gradient that is fp32 noise around zero into +-lr in ANY implementation)."""
+    gpu, T, b, perms, losses, (mu0, v0, ls0) = _run_update_three_ways(L, sizes, acts, n, mb, npol, nval, seed=300 + mb)
+    ref64 = f64ref.update(sizes, acts, mu0, v0, ls0, b, perms, mb, npol, nval)
+    rows = _report("update %s mb=%d:" % (sizes, mb), gpu, T, ref64)
+    assert np.max(np.abs(gpu["advantage"] - ref64[3])) < 2e-5
+    assert nerr(gpu["adv_target"], ref64[4]) < 1e-5
+    for r in rows:
+        assert r["gpu_vs_oracle"] < 1e-5 or r["gpu_vs_f64"] <= 2.0 * r["oracle_vs_f64"] + 1e-6, r
+        assert r["gpu_vs_f64"] < 1e-4 and r["frac_gpu_vs_oracle_gt_1e5"] < 0.01, r
+    assert np.max(np.abs(gpu["log_std"] - T.log_std)) < 1e-6
+    nb = n // mb
+    assert abs(gpu["v_loss"] - losses[:nval * nb].mean()) < 1e-5 * abs(losses[:nval * nb].mean()) + 1e-6
+    assert abs(gpu["p_loss"] - losses[nval * nb:].mean()) < 1e-5 + 1e-5 * abs(losses[nval * nb:].mean())
+
+
+def test_update_c3_minibatch_65536_matches_oracle(L):
+    """c3 as benched: 2x256 ReLU nets, S=17, A=6, minibatch 65 536 (the skinny-dW row splits + fold of the 17-wide first
+    layer and the 6 / 1-wide heads, split-K slabs of the 256x256 layers).  One value + one policy epoch of one minibatch
+    each (the naive-sgemm oracle needs ~40 GFLOP for this)."""
+    sizes, n, mb = [17, 256, 256, 6], 65536 + 300, 65536
+    gpu, T, b, perms, losses, _ = _run_update_three_ways(L, sizes, RELU3, n, mb, 1, 1, seed=65)
+    ev, em = nerr(gpu["v"], T.v), nerr(gpu["mu"], T.mu)
+    print("c3 mb=65536 post-Adam weight errors vs oracle (V, mu):", ev, em)
+    # one Adam step from zero moments moves every weight by lr * g/|g| = +-lr exactly, unless g is within fp32 noise of 0:
+    # the oracle sums 65 536 products sequentially in fp32 (error ~1e-5 of |dW|), the GPU in blocked order
+    scale_v, scale_m = np.max(np.abs(T.v)), np.max(np.abs(T.mu))
+    assert np.mean(np.abs(gpu["v"] - T.v) > 1e-5 * scale_v) < 0.01 and np.mean(np.abs(gpu["mu"] - T.mu) > 1e-5 * scale_m) < 0.01
+    assert ev < 2 * 3e-4 / scale_v + 1e-5 and em < 2 * 3e-4 / scale_m + 1e-5       # worst element: a sign flip = 2 lr
+    assert np.max(np.abs(gpu["advantage"] - b["advantage"])) < 5e-5
+    assert abs(gpu["v_loss"] - losses[0]) < 1e-4 * abs(losses[0]) and abs(gpu["p_loss"] - losses[1]) < 1e-4
+
+
+def test_tf32_update_vs_fp32_oracle_stated_tolerance(L):
+    """c4 path: 3x1024 ReLU nets with the 1024x1024 layers on the TF32 tcgen05 kernels, WHOLE update against the fp32
+    oracle.  Stated tolerance for this path (separate from the 1e-5 of the fp32 path, north star): TF32 operands carry
+    11 significand bits (RNA rounding), so a gradient element is exact to ~1e-3 of the tensor's scale; through Adam's
+    first step every weight moves by +-lr, so a post-Adam weight differs from the fp32 result by at most 2*lr per step
+    (sign flip of a gradient inside TF32 noise of zero) — asserted as: >= 97 % of the weights within 1e-5 of scale + the
+    rest bounded by 2*lr*steps, and the value loss within 1e-3 relative."""
+    sizes, acts, n, mb = [17, 1024, 1024, 1024, 6], ["relu", "relu", "relu", "none"], 1024, 512
+    gpu, T, b, perms, losses, _ = _run_update_three_ways(L, sizes, acts, n, mb, 1, 1, seed=44, precision=1)
+    steps = n // mb
+    out = {}
+    for name, got, orc in (("V", gpu["v"], T.v), ("mu", gpu["mu"], T.mu)):
+        d = np.abs(got - orc)
+        scale = np.max(np.abs(orc))
+        out[name] = dict(max_abs=float(d.max()), nerr=float(d.max() / scale), frac_gt_1e5=float(np.mean(d > 1e-5 * scale)),
+                         frac_gt_lr=float(np.mean(d > 3e-4)))
+        assert d.max() <= 2 * 3e-4 * steps * 1.01, out
+        assert out[name]["frac_gt_lr"] < 0.03, out
+    print("TF32 update vs fp32 oracle:", json.dumps(out), "v_loss", gpu["v_loss"], float(losses[:steps].mean()))
+    assert abs(gpu["v_loss"] - losses[:steps].mean()) < 1e-3 * abs(losses[:steps].mean())
+    assert np.max(np.abs(gpu["advantage"] - b["advantage"])) < 5e-3          # V forward in TF32 feeds the GAE
+
+
+def test_eval_ppo_matches_oracle_and_reference_golden(L):
+    """eval_ppo (src/ppo.cu:560-583) on the toy env from the reference's rand() stream: exact episode count, J and R
+    within 1e-5 of the oracle's, which itself reproduces the line the unmodified reference printed (golden)."""
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_golden.json")))
+    for c in cases:
+        if c["train_epochs"]:
+            continue
+        sizes = [1, c["hidden"], c["hidden"], 1]
+        cabi.srand(c["seed"])
+        env = L.create_simple_env(0, c["seed"])
+        ppo = make_ppo(L, sizes, RELU3, c["capacity"])
+        if c["mu_bias"] is not None:
+            p = b200.nn_get_params(L, ppo.contents.policy.contents.mu)
+            p[-1] = c["mu_bias"]
+            b200.nn_set_params(L, ppo.contents.policy.contents.mu, p)
+        L.eval_ppo(ppo, env, c["steps"])
+        J, R, n = C.c_float(), C.c_float(), C.c_int()
+        L.ppo_b200_last_eval(ppo, C.byref(J), C.byref(R), C.byref(n))
+        assert cabi.rand() == c["rand_after"]                    # same rand() consumption as the reference
+        cabi.srand(c["seed"])
+        T = oracle.Trainer(sizes, RELU3)
+        if c["mu_bias"] is not None:
+            T.mu[-1] = c["mu_bias"]
+        oJ, oR, on = T.eval(T.make_buffer(c["capacity"]), c["steps"], 0)
+        assert "J: %f R: %f Episodes: %d" % (oJ, oR, on) == c["line"]
+        assert n.value == on and abs(J.value - oJ) <= 1e-5 * max(1, abs(oJ)) and abs(R.value - oR) <= 1e-5 * max(1, abs(oR)), (c, J.value, R.value, n.value)
+        L.free_ppo(ppo)
+        env.contents.free_env()
+
+
+@pytest.mark.parametrize("acts", [TANH3, RELU3], ids=["tanh", "relu"])
+def test_device_mean_return_matches_host_recomputation(L, acts):
+    """ppo_b200_last_mean_return (eval_ppo's "R" for the device envs, src/ppo.cu:581) against a host recomputation from the
+    mirrored buffer: sum of rewards / number of episodes (every env contributes T/200 complete episodes)."""
+    n_envs, T = 512, 400
+    cabi.srand(2)
+    env = L.create_pendulum_env_cuda(n_envs, 5)
+    ppo = make_ppo(L, [3, 64, 64, 1], acts, n_envs * T)
+    L.ppo_b200_train_iterations(ppo, env, 1, 4096, 1, 1)
+    got = L.ppo_b200_last_mean_return(ppo)
+    L.ppo_b200_sync_host(ppo)
+    rw = host_field(ppo, "reward", (n_envs * T,)).astype(np.float64)
+    done = host_field(ppo, "truncated", (n_envs * T,), u8) | host_field(ppo, "terminated", (n_envs * T,), u8)
+    assert done.sum() == n_envs * T // 200
+    want = rw.sum() / done.sum()
+    assert abs(got - want) < 1e-4 * abs(want), (got, want)
+    L.free_ppo(ppo)
+    env.contents.free_env()

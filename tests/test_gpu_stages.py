@@ -375,6 +375,24 @@ def test_mat_mul_cuda_entry_points(L):
     assert np.array_equal(dgrad.numpy(), np.where(np.maximum(y, 0) > 0, g, 0))
 
 
+@pytest.mark.parametrize("shapes", [[(32768, 3, 64), (32768, 64, 1)], [(32768, 64, 1), (32768, 17, 64), (32768, 3, 64)],
+                                    [(20000, 64, 6), (20000, 64, 6)]])
+def test_mat_mul_backwards_cuda_narrow_layers_large_m(L, shapes):
+    """Narrow layers at large m take the skinny row-split dW kernels (R > 1 staging + fold).  Their staging must not
+    alias or free the caller's split-K slabs (round-1 advisor finding: both lived in one scratch slot); called back
+    to back with growing and shrinking shapes, every gradient must match float64."""
+    rng = np.random.default_rng(7)
+    for (m, n, l) in shapes:
+        x, w, g = (rng.standard_normal(s).astype(f32) for s in [(m, n), (l, n), (m, l)])
+        dx, dw, dg, dgx, dgw = b200.dev(x), b200.dev(w), b200.dev(g), b200.dev_empty((m, n)), b200.dev_empty((l, n))
+        L.mat_mul_backwards_cuda(None, dgx.fp(), dgw.fp(), dg.fp(), dx.fp(), dw.fp(), m, n, l)
+        x64, w64, g64 = x.astype(np.float64), w.astype(np.float64), g.astype(np.float64)
+        assert nerr(dgw.numpy(), g64.T @ x64) < TOL, (m, n, l)
+        assert nerr(dgx.numpy(), g64 @ w64) < TOL, (m, n, l)
+        for d in (dx, dw, dg, dgx, dgw):
+            d.free()
+
+
 # ------------------------------------------------------------------------------------------ policy
 def _policy(L, sizes, params, log_std):
     pol = L.create_gaussian_policy(cabi.int_array(sizes), cabi.cstr_array(RELU3), len(sizes), 1.0)

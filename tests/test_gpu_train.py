@@ -184,8 +184,9 @@ def test_host_pendulum_env_semantics(L):
         assert not term.value and trunc.value == (t == 199)
 
 
-@pytest.mark.parametrize("H", [64, 128, 32])
-def test_device_rollout_is_self_consistent(L, H):
+@pytest.mark.parametrize("H,acts", [(64, ["tanh", "tanh", "none"]), (64, RELU3), (128, RELU3), (128, ["tanh", "tanh", "none"]), (32, RELU3)],
+                         ids=["64-tanh(bench config)", "64-relu", "128-relu", "128-tanh", "32-relu"])
+def test_device_rollout_is_self_consistent(L, H, acts):
     """Fused device rollout (4096 envs x 16 steps; hidden widths 64 / 128 (two 64-unit blocks) / 32): every stored row must be reproducible by the
     oracle from the stored state/action: log-prob under the policy, reward and next state from the
     Pendulum definition, reference bookkeeping of next_state -> state and the forced last-step flag."""
@@ -194,7 +195,7 @@ def test_device_rollout_is_self_consistent(L, H):
     env = L.create_pendulum_env_cuda(n_envs, 7)
     assert L.ppo_b200_env_is_device(env) == 1 and L.ppo_b200_env_num_envs(env) == n_envs
     sizes = [3, H, H, 1]
-    ppo = make_ppo(L, sizes, RELU3, n_envs * T)
+    ppo = make_ppo(L, sizes, acts, n_envs * T)
     L.collect_trajectories(ppo.contents.buffer, env, ppo.contents.policy, n_envs * T)
     L.ppo_b200_sync_host(ppo)
     n = n_envs * T
@@ -205,7 +206,7 @@ def test_device_rollout_is_self_consistent(L, H):
     assert np.array_equal(st[:, 1:], ns[:, :-1])                      # src/ppo.cu:68
     assert np.max(np.abs(st[..., 0] ** 2 + st[..., 1] ** 2 - 1)) < 1e-5
     p = b200.nn_get_params(L, ppo.contents.policy.contents.mu)
-    mu, _ = oracle.mlp_forward(p, sizes, RELU3, st.reshape(n, 3))
+    mu, _ = oracle.mlp_forward(p, sizes, acts, st.reshape(n, 3))
     lp_o = oracle.log_prob(mu, np.zeros(1, f32), ac.reshape(n, 1))
     assert np.max(np.abs(lp.ravel() - lp_o)) < 2e-5
     z = (ac.ravel() - mu.ravel())                                      # std = 1 -> noise
@@ -263,14 +264,15 @@ def test_obs_normalisation_running_statistics(L):
     env.contents.free_env()
 
 
-def test_pendulum_learns_on_device(L):
+@pytest.mark.parametrize("acts", [["tanh", "tanh", "none"], RELU3], ids=["tanh(bench config)", "relu"])
+def test_pendulum_learns_on_device(L, acts):
     """Learning-curve check: 1024 vectorised envs, full 200-step episodes, reference
     hyper-parameters except minibatch 4096: mean episode return must rise well above the random
     policy's (about -1200 .. -1500) within 40 iterations."""
     n_envs, T = 1024, 200
     cabi.srand(1)
     env = L.create_pendulum_env_cuda(n_envs, 1)
-    ppo = make_ppo(L, [3, 64, 64, 1], RELU3, n_envs * T)
+    ppo = make_ppo(L, [3, 64, 64, 1], acts, n_envs * T)
     L.ppo_b200_set_permutation_mode(ppo, 1, 99)
     L.ppo_b200_train_iterations(ppo, env, 1, 4096, 4, 10)
     r0 = L.ppo_b200_last_mean_return(ppo)

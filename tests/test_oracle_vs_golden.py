@@ -153,3 +153,26 @@ def test_welford_combine_matches_numpy():
     mean, m2, n = oracle.welford_combine(means, m2s, [len(c) for c in chunks])
     allx = np.concatenate(chunks).astype(np.float64)
     assert n == allx.size and abs(mean - allx.mean()) < 1e-5 and abs(m2 / n - allx.var()) < 1e-4
+
+
+def test_eval_ppo_matches_reference_output():
+    """eval_ppo (src/ppo.cu:560-583): the oracle's J / R / Episodes, formatted like the reference's printf, must equal the
+    line the unmodified reference printed (tests/golden/eval_golden.json, minted by tests/golden/make_eval_golden.py),
+    and the rand() stream must sit at the same position afterwards."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_golden.json")))
+    assert len(cases) >= 4
+    for c in cases:
+        cabi.srand(c["seed"])
+        sizes = [1, c["hidden"], c["hidden"], 1]
+        T = oracle.Trainer(sizes, ["relu", "relu", "none"], batch_size=64, n_epochs_policy=1, n_epochs_value=2)
+        if c["mu_bias"] is not None:
+            T.mu[-1] = c["mu_bias"]
+        b = T.make_buffer(c["capacity"])
+        for _ in range(c["train_epochs"]):
+            T.collect(b, c["capacity"], 0)
+            T.update(b)
+        J, R, n = T.eval(b, c["steps"], 0)
+        assert "J: %f R: %f Episodes: %d" % (J, R, n) == c["line"], c
+        assert cabi.rand() == c["rand_after"]
