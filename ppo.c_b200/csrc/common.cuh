@@ -95,6 +95,17 @@ extern bool g_profiling;
         if (::b200::g_profiling) ::b200::profile_mark(#kernel, false);                          \
     } while (0)
 
+// Cooperative launch (every CTA co-resident: the kernel may use grid-wide barriers).  `args_ptr` = address of the one
+// by-value argument struct.
+#define B200_LAUNCH_COOP(kernel, grid, block, smem, args_ptr)                                    \
+    do {                                                                                        \
+        if (::b200::g_profiling) ::b200::profile_mark(#kernel, true);                           \
+        void* kargs__[1] = {(void*)(args_ptr)};                                                 \
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(block), kargs__, (smem), ::b200::stream())); \
+        ++::b200::g_launches;                                                                   \
+        if (::b200::g_profiling) ::b200::profile_mark(#kernel, false);                          \
+    } while (0)
+
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers -----------------------------------------------------------------------------

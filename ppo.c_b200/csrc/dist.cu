@@ -172,6 +172,35 @@ PeerView dist_peer_next(size_t vec_floats) {
     return v;
 }
 
+PeerView dist_peer_reserve(size_t vec_floats, int count) {
+    PeerView v{};
+    if (!dist_active() || count <= 0) return v;
+    peer_setup();
+    if (!g_peer.ready || vec_floats > kPeerCap) return v;
+    const unsigned long long first = g_peer.epoch + 1;
+    g_peer.epoch += (unsigned long long)count;
+    if ((first >> 32) != (g_peer.epoch >> 32) || (first & 0xffffffffull) == 0) B200_FATAL("peer exchange epoch wrapped");
+    v.ready = 1;
+    v.world = g_world;
+    v.rank = g_rank;
+    v.epoch = (unsigned int)first;
+    v.parity_stride = kPeerMaxRanks * kPeerCap;
+    v.my_recv = reinterpret_cast<unsigned long long*>(g_peer.local);
+    for (int r = 0; r < g_world; r++)
+        v.peer_recv[r] = reinterpret_cast<unsigned long long*>(g_peer.base[r]) + (size_t)g_rank * kPeerCap;
+    return v;
+}
+
+long long dist_spin_limit() {
+    static long long cached = 0;
+    if (!cached) {
+        const char* e = getenv("PPO_B200_SPIN_TIMEOUT_S");
+        const double sec = e ? atof(e) : 120.0;
+        cached = (long long)(std::max(1.0, sec) * 2.0e9);
+    }
+    return cached;
+}
+
 }  // namespace b200
 
 using namespace b200;

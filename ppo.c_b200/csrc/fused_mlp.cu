@@ -121,6 +121,10 @@ __device__ __forceinline__ void t64_stamp(const FusedArgs& p, int slot) {
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 bcast2(float x) { return make_float2(x, x); }
 
+// Barrier over the 256 threads that own one 64-row tile.  The one-tile-per-CTA kernel passes id 0 (== __syncthreads for its
+// 256-thread CTA); the persistent phase kernel runs two tiles side by side in one 512-thread CTA on ids 1 and 2.
+__device__ __forceinline__ void tile_sync(int bar) { asm volatile("bar.sync %0, 256;" :: "r"(bar) : "memory"); }
+
 __device__ __forceinline__ void t64_load8(const float* base, float (&a)[8]) {
     const float4 a0 = *reinterpret_cast<const float4*>(base);
     const float4 a1 = *reinterpret_cast<const float4*>(base + 32);
@@ -137,10 +141,10 @@ __device__ __forceinline__ void t64_store8(float* base, const float (&a)[8]) {
 //   finalise through `xch` ([64][TMP]) and adds (lower-k partial) + (upper-k partial) for its own quad, so
 //   the activation epilogue is spread over all 256 threads.
 // n_in < 16: no split; group g simply computes its own row quad (4x4 tile) over all of k.
-// Contains one __syncthreads.
+// Contains one tile_sync.
 __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
                                             const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ xch,
-                                            int n_in, int n_out, int act, int lt, int g, int cb) {
+                                            int n_in, int n_out, int act, int lt, int g, int cb, int bar) {
     // cb = first column of the 64-column block this call computes (layers wider than 64 are done block by block)
     const int tr = lt & 7, tc = lt >> 3;
     const bool live = cb + 4 * tc < pad4(n_out);
@@ -201,7 +205,7 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
             }
         }
     }
-    __syncthreads();
+    tile_sync(bar);
     if (live) {
         const float4 b = *reinterpret_cast<const float4*>(bias + cb + 4 * tc);     // bias block is zero-padded to pad4
         const float bv[4] = {b.x, b.y, b.z, b.w};
@@ -222,11 +226,11 @@ __device__ __forceinline__ void t64_forward(const float* __restrict__ Xt, const 
 }
 
 // Skinny forward, n_out <= 8: thread = (row, k-quarter); the quarters meet through `scratch` (>= 3*8*64 floats).
-// Contains one __syncthreads: every thread of the CTA must call it.
+// Contains one tile_sync: every thread of the tile must call it.
 __device__ __forceinline__ void t64_forward_skinny(const float* __restrict__ Xt, const float* __restrict__ Wt, int ldw,
                                                    const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ scratch,
-                                                   int n_in, int n_out, int act) {
-    const int r = threadIdx.x & 63, h = threadIdx.x >> 6;      // h = 0..3
+                                                   int n_in, int n_out, int act, int tid, int bar) {
+    const int r = tid & 63, h = tid >> 6;      // h = 0..3
     const int kq = (n_in + 3) >> 2;
     const int k0 = min(n_in, h * kq), k1 = min(n_in, k0 + kq);
     float acc[8];
@@ -245,7 +249,7 @@ __device__ __forceinline__ void t64_forward_skinny(const float* __restrict__ Xt,
 #pragma unroll
         for (int j = 0; j < 8; j++) if (j < n_out) scratch[((h - 1) * 8 + j) * 64 + r] = acc[j];
     }
-    __syncthreads();
+    tile_sync(bar);
     if (!h) {
         const int out_pad = pad4(n_out);
 #pragma unroll
@@ -312,7 +316,7 @@ __device__ __forceinline__ void t64_backward_input(const float* __restrict__ Gt,
 // and 8 X rows a warp loads per instruction are consecutive features.
 template <int JJ, int KK>
 __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                     float* __restrict__ gW, int n_in, int n_out, int lt, int jb, int kb) {
+                                                     float* __restrict__ gW, int n_in, int n_out, int lt, int jb, int kb, bool accum) {
     // (jb, kb) = first output row / input column of the 64x64 block of gW this call produces
     const int tk = lt & 7, tj = lt >> 3;
     if (jb + (tj & ~3) >= n_out) return;     // warp-uniform: this warp owns no valid output row
@@ -348,7 +352,11 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
 #pragma unroll
         for (int b = 0; b < KK; b++) {
             const int k = kb + tk + 8 * b;
-            if (k < n_in) gW[(size_t)j * n_in + k] = acc[a][b].x + acc[a][b].y;
+            if (k < n_in) {
+                float* dst = gW + (size_t)j * n_in + k;
+                const float v = acc[a][b].x + acc[a][b].y;
+                *dst = accum ? *dst + v : v;        // accum: this (CTA, tile slot) adds a further tile of the same minibatch
+            }
         }
     }
 }
@@ -358,7 +366,7 @@ __device__ __forceinline__ void t64_backward_weights(const float* __restrict__ G
 // The two row halves meet through one shuffle; sums run in a fixed order.
 template <bool WIDE_IS_K>
 __device__ __forceinline__ void t64_backward_weights_skinny(const float* __restrict__ Gt, const float* __restrict__ Xt,
-                                                            float* __restrict__ gW, int n_in, int n_out, int lt, int wb) {
+                                                            float* __restrict__ gW, int n_in, int n_out, int lt, int wb, bool accum) {
     const int wide = wb + (lt >> 1), h = lt & 1;       // wb = first of the 64 wide-side features of this call
     const int n_wide = WIDE_IS_K ? n_in : n_out, n_small = WIDE_IS_K ? n_out : n_in;
     const float* wide_base = (WIDE_IS_K ? Xt : Gt) + min(wide, n_wide - 1) * kT64TMP + 32 * h;
@@ -383,29 +391,29 @@ __device__ __forceinline__ void t64_backward_weights_skinny(const float* __restr
 #pragma unroll
         for (int q = 0; q < 8; q++)
             if (q < n_small) {
-                if (WIDE_IS_K) gW[(size_t)q * n_in + wide] = acc[q];
-                else gW[(size_t)wide * n_in + q] = acc[q];
+                float* dst = WIDE_IS_K ? gW + (size_t)q * n_in + wide : gW + (size_t)wide * n_in + q;
+                *dst = accum ? *dst + acc[q] : acc[q];
             }
     }
 }
 
-__device__ __forceinline__ void t64_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out, int lt) {
+__device__ __forceinline__ void t64_weights_dispatch(const float* Gt, const float* Xt, float* gW, int n_in, int n_out, int lt, bool accum) {
     // few tile shapes only (instruction-cache footprint); layers wider than 64 go 64x64 block by block
     if (n_out <= 8) {
-        for (int wb = 0; wb < n_in; wb += 64) t64_backward_weights_skinny<true>(Gt, Xt, gW, n_in, n_out, lt, wb);
+        for (int wb = 0; wb < n_in; wb += 64) t64_backward_weights_skinny<true>(Gt, Xt, gW, n_in, n_out, lt, wb, accum);
     } else if (n_in <= 8) {
-        for (int wb = 0; wb < n_out; wb += 64) t64_backward_weights_skinny<false>(Gt, Xt, gW, n_in, n_out, lt, wb);
+        for (int wb = 0; wb < n_out; wb += 64) t64_backward_weights_skinny<false>(Gt, Xt, gW, n_in, n_out, lt, wb, accum);
     } else {
         for (int jb = 0; jb < n_out; jb += 64)
             for (int kb = 0; kb < n_in; kb += 64) {
-                if (n_out - jb <= 16) t64_backward_weights<1, 8>(Gt, Xt, gW, n_in, n_out, lt, jb, kb);
-                else t64_backward_weights<4, 8>(Gt, Xt, gW, n_in, n_out, lt, jb, kb);
+                if (n_out - jb <= 16) t64_backward_weights<1, 8>(Gt, Xt, gW, n_in, n_out, lt, jb, kb, accum);
+                else t64_backward_weights<4, 8>(Gt, Xt, gW, n_in, n_out, lt, jb, kb, accum);
             }
     }
 }
 
 // gb[j] = sum_r Gt[j][r]: thread = (j, row half), fixed-order sums
-__device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out, int lt) {
+__device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, float* __restrict__ gb, int n_out, int lt, bool accum) {
     for (int jb = 0; jb < n_out; jb += 64) {
         const int j = jb + (lt >> 1), h = lt & 1;
         float s = 0.f;
@@ -418,7 +426,74 @@ __device__ __forceinline__ void t64_bias_grad(const float* __restrict__ Gt, floa
             }
         }
         s += __shfl_xor_sync(kFull, s, 1);
-        if (h == 0 && j < n_out) gb[j] = s;
+        if (h == 0 && j < n_out) gb[j] = accum ? gb[j] + s : s;
+    }
+}
+
+// ---- fused loss head (src/loss.cu:5-23 | src/policy.cu:67-111 + src/ppo.cu:89-98): dLoss/dy written IN PLACE over the
+// output tile Yt (rows >= OUT of it stay zero); the tile's loss term and log_std gradient go to the slab tail.
+// Threads tid < 64 own one row each; contains one tile_sync.
+struct HeadCtx { int mode, m_total, OUT, P, out_act; const float* log_std; float epsilon; };
+__device__ __forceinline__ void t64_loss_head(const HeadCtx& c, float* __restrict__ Yt, float* __restrict__ red, float* __restrict__ slab,
+                                              int tid, int bar, bool row_valid, float h_target, float h_adv, float h_lp_old,
+                                              const float (&h_act)[8], bool accum) {
+    constexpr int TMP = kT64TMP;
+    const int OUT = c.OUT;
+    float loss_term = 0.f;
+    float gls[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) gls[j] = 0.f;
+    if (tid < kT64TM) {
+        float gout[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) gout[j] = 0.f;
+        float yv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) yv[j] = (j < OUT) ? Yt[j * TMP + tid] : 0.f;
+        if (row_valid) {
+            if (c.mode == kFusedValue) {            // src/loss.cu:5-23
+                gout[0] = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(yv[0], h_target)), (float)c.m_total);
+                const float d = __fsub_rn(h_target, yv[0]);
+                loss_term = __fmul_rn(d, d);
+            } else {                                // src/policy.cu:67-111 + src/ppo.cu:89-98
+                float lsv[8];                       // L2 loads: another SM's Adam may have just updated log_std (persistent kernel)
+#pragma unroll
+                for (int j = 0; j < 8; j++) lsv[j] = (j < OUT) ? __ldcg(c.log_std + j) : 0.f;
+                const float lp = fused_log_prob(yv, lsv, h_act, OUT);
+                const float ratio = expf(__fsub_rn(lp, h_lp_old));
+                const bool adv_pos = h_adv > 0.f;
+                const bool hi = ratio > 1.f + c.epsilon, lo = ratio < 1.f - c.epsilon;
+                const float sel = adv_pos ? (hi ? 1.f + c.epsilon : ratio) : (lo ? 1.f - c.epsilon : ratio);
+                loss_term = __fmul_rn(h_adv, sel);
+                const int keep = adv_pos ? !hi : !lo;
+                const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)c.m_total);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (j < OUT) {
+                        const float e2 = expf(-2.f * lsv[j]);
+                        const float diff = __fsub_rn(h_act[j], yv[j]);
+                        gout[j] = __fmul_rn(__fmul_rn(diff, e2), g);
+                        gls[j] = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), g);
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (j < OUT) Yt[j * TMP + tid] = act_grad(yv[j], gout[j], c.out_act);
+        const int warp = tid >> 5, lane = tid & 31;       // warps 0..1 hold the data
+        const float v = warp_sum(loss_term);
+        if (lane == 0) red[warp] = v;
+        if (c.mode == kFusedPolicy) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < OUT) { const float s = warp_sum(gls[j]); if (lane == 0) red[8 + j * 2 + warp] = s; }
+        }
+    }
+    tile_sync(bar);
+    if (tid == 0) { const float v = red[0] + red[1]; slab[c.P + OUT] = accum ? slab[c.P + OUT] + v : v; }
+    if (c.mode == kFusedPolicy && tid < OUT) {
+        const float v = red[8 + tid * 2] + red[8 + tid * 2 + 1];
+        slab[c.P + tid] = accum ? slab[c.P + tid] + v : v;
     }
 }
 
@@ -490,11 +565,11 @@ __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const Fuse
         const float* Xt = act0 + net.a_off[l];
         float* Yt = act0 + net.a_off[l + 1];
         if (net.sizes[l + 1] <= 8)
-            t64_forward_skinny(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, scratch, net.sizes[l], net.sizes[l + 1], net.acts[l]);
+            t64_forward_skinny(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, scratch, net.sizes[l], net.sizes[l + 1], net.acts[l], tid, 0);
         else
             for (int cb = 0; cb < pad4(net.sizes[l + 1]); cb += 64) {
                 if (cb) __syncthreads();           // the previous block's finalisation has read the exchange buffer
-                t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp, cb);
+                t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp, cb, 0);
             }
         __syncthreads();
         t64_stamp(p, 4 + l);
@@ -508,61 +583,11 @@ __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const Fuse
         return;
     }
     float* slab = p.partials + (size_t)blockIdx.x * p.slab;
-    // ---- fused loss head: dLoss/dy written IN PLACE over the output tile (rows >= OUT of it stay zero)
     {
-        float loss_term = 0.f;
-        float gls[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) gls[j] = 0.f;
-        if (tid < TM) {
-            float gout[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) gout[j] = 0.f;
-            float yv[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) yv[j] = (j < OUT) ? Yt[j * TMP + tid] : 0.f;
-            if (my_src >= 0) {
-                if (p.mode == kFusedValue) {            // src/loss.cu:5-23
-                    gout[0] = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(yv[0], h_target)), (float)p.m_total);
-                    const float d = __fsub_rn(h_target, yv[0]);
-                    loss_term = __fmul_rn(d, d);
-                } else {                                // src/policy.cu:67-111 + src/ppo.cu:89-98
-                    const float lp = fused_log_prob(yv, p.log_std, h_act, OUT);
-                    const float ratio = expf(__fsub_rn(lp, h_lp_old));
-                    const bool adv_pos = h_adv > 0.f;
-                    const bool hi = ratio > 1.f + p.epsilon, lo = ratio < 1.f - p.epsilon;
-                    const float sel = adv_pos ? (hi ? 1.f + p.epsilon : ratio) : (lo ? 1.f - p.epsilon : ratio);
-                    loss_term = __fmul_rn(h_adv, sel);
-                    const int keep = adv_pos ? !hi : !lo;
-                    const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)p.m_total);
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        if (j < OUT) {
-                            const float e2 = expf(-2.f * p.log_std[j]);
-                            const float diff = __fsub_rn(h_act[j], yv[j]);
-                            gout[j] = __fmul_rn(__fmul_rn(diff, e2), g);
-                            gls[j] = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), g);
-                        }
-                }
-            }
-            const int out_act = net.acts[net.L - 1];
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (j < OUT) Yt[j * TMP + tid] = act_grad(yv[j], gout[j], out_act);
-        }
-        if (tid < 64) {                                    // warps 0..1 hold the data
-            const int warp = tid >> 5, lane = tid & 31;
-            const float v = warp_sum(loss_term);
-            if (lane == 0) red[warp] = v;
-            if (p.mode == kFusedPolicy) {
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (j < OUT) { const float s = warp_sum(gls[j]); if (lane == 0) red[8 + j * 2 + warp] = s; }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) slab[net.P + OUT] = red[0] + red[1];
-        if (p.mode == kFusedPolicy && tid < OUT) slab[net.P + tid] = red[8 + tid * 2] + red[8 + tid * 2 + 1];
+        HeadCtx hc;
+        hc.mode = p.mode; hc.m_total = p.m_total; hc.OUT = OUT; hc.P = net.P; hc.out_act = net.acts[net.L - 1];
+        hc.log_std = p.log_std; hc.epsilon = p.epsilon;
+        t64_loss_head(hc, Yt, red, slab, tid, 0, my_src >= 0, h_target, h_adv, h_lp_old, h_act, false);
     }
     t64_stamp(p, 9);
     // ---- backward: group 0 -> dW_l, db_l; group 1 -> dX_l into the ping-pong buffer (both read G_{l+1}, A_l)
@@ -572,8 +597,8 @@ __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const Fuse
         const float* Xt = act0 + net.a_off[l];
         float* Gout = ebuf + ((net.L - 1 - l) & 1) * (net.max_width_pad * TMP);
         if (grp == 0) {
-            t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt);
-            t64_bias_grad(G, slab + net.b_off[l], n_out, lt);
+            t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt, false);
+            t64_bias_grad(G, slab + net.b_off[l], n_out, lt, false);
         } else if (l > 0) {
             for (int kb = 0; kb < pad4(n_in); kb += 64)
                 t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt, kb);
@@ -719,6 +744,335 @@ __global__ void __launch_bounds__(32 * kRedWarps) fused_reduce_adam_kernel(const
             *p.loss_slot += g / (float)p.m_total;
         } else {
             *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
+        }
+    }
+}
+
+// ===================================================================================================
+// Persistent phase kernel: ALL minibatches of all epochs of one phase (value or policy) in ONE cooperative launch.
+//
+// The reference's update is strictly sequential SGD (minibatch k+1 needs the weights after Adam step k,
+// src/ppo.cu:495-532), so the only parallelism is inside a minibatch.  One CTA per SM stays resident for the whole phase:
+//   [A] every CTA runs its tiles of the minibatch (two 64-row tiles side by side: 2 x 256 threads on named barriers 1/2;
+//       further tiles of the same minibatch are accumulated into the same slab) with the tile code above: gather ->
+//       forward -> loss head -> backward, activations in shared memory, weights from the shared image;
+//   [B] grid barrier; [C] CTA c reduces ITS 1/gridDim slice of the parameter vector over all slabs in fixed order
+//       (L2 reads), exchanges it with the other GPUs over NVLink peer memory under data parallelism, runs Adam on the
+//       slice (reference arithmetic, src/adam.cu:56-69) and refreshes those entries of the global weight image;
+//   [D] grid barrier; [E] every CTA re-stages the image with one TMA bulk copy.
+// The gather of the NEXT minibatch (permutation lookup, cp.async of the state rows, scalar loads) is issued before [B], so
+// it is in flight during [B]-[E].  Versus round 1 (two launches per minibatch, slabs through a second kernel): no launch
+// or programmatic-dependency latency per minibatch, half as many image loads, and the reduction + Adam of a minibatch
+// costs two grid barriers and one L2 round trip instead of a kernel.
+// Determinism: slab order, slice ownership and the rank order of the cross-GPU sum are fixed -> bitwise reproducible.
+// ===================================================================================================
+struct PhaseArgs {
+    FusedNet net;
+    float* image;                 // global weight image (TMA source; refreshed by [C])
+    const int* perms;             // [n_epochs][limit] permutations (null: identity)
+    int limit, mb, m_total, row0, batch_stride, num_batches, n_steps, mode;
+    const float *state, *action, *logprob, *advantage, *adv_target;
+    const float* log_std;         // device log_std (policy mode): read by the heads, updated through ls.w
+    float epsilon, ent_coeff;
+    float* partials;              // [nslabs][slab]
+    int slab, P, A;
+    int sub_floats, g_off, red_off;   // shared-memory floats per tile slot; offsets of E0|E1 and of the reduction scratch
+    AdamSeg netseg, ls;           // step_size / bc2 come from coef[step]
+    const float4* coef;           // [n_steps] {step_size_net, bc2_net, step_size_ls, bc2_ls} (host powf, src/adam.cu:56-59)
+    float* loss_slot;
+    unsigned int* barrier;        // grid barrier counter, zero at launch
+    PeerView peer;                // data parallelism: parity-0 lanes + parity stride; exchange s uses epoch + s
+    long long spin_limit;         // clock64 ticks a barrier / peer poll may wait before the kernel traps
+    unsigned long long* dbg;
+};
+
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int r;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
+// All threads of all CTAs call it the same number of times (cooperative launch: every CTA is resident).
+__device__ __forceinline__ void phase_grid_barrier(unsigned int* counter, unsigned int target, long long spin_limit) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // release the writes of this CTA (ordered by the bar.sync above)
+        atomicAdd(counter, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(counter) < target) {
+            if (clock64() - t0 > spin_limit) {
+                printf("ppo_b200: grid barrier timed out (block %d, target %u, counter %u)\n", blockIdx.x, target, *counter);
+                __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int kPhaseMaxThreads = 512;
+__global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const PhaseArgs p) {
+    constexpr int TM = kT64TM, TMP = kT64TMP;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ float redw[kPhaseMaxThreads / 32][33];
+    __shared__ float s_entropy;       // entropy of the policy BEFORE this step's Adam (the loss of step s is reported with it)
+    const FusedNet& net = p.net;
+    const int nsub = blockDim.x >> 8;
+    const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255, lt = tid & 127, grp = tid >> 7;
+    const int bar = 1 + sub;
+    const int S = net.sizes[0], OUT = net.sizes[net.L], SP = pad4(S);
+    float* img = smem;
+    float* act0 = smem + net.img_floats + sub * p.sub_floats;
+    float* ebuf = act0 + p.g_off;
+    float* red = act0 + p.red_off;                        // 64 floats
+    int* src_rows = reinterpret_cast<int*>(red + 64);     // TM ints
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + net.img_floats + nsub * p.sub_floats);
+    float* scratch = ebuf;
+    float* Xt0 = act0 + net.a_off[0];
+
+    const int n_tiles = (p.mb + TM - 1) / TM;
+    const int stride = gridDim.x * nsub;
+    const int t0 = blockIdx.x * nsub + sub;
+    const int rounds = t0 < n_tiles ? (n_tiles - t0 + stride - 1) / stride : 0;
+    const int nslabs = min(n_tiles, stride);
+    float* slab = p.partials + (size_t)t0 * p.slab;
+    unsigned int bar_gen = 0;
+
+    HeadCtx hc;
+    hc.mode = p.mode; hc.m_total = p.m_total; hc.OUT = OUT; hc.P = net.P; hc.out_act = net.acts[net.L - 1];
+    hc.log_std = p.log_std; hc.epsilon = p.epsilon;
+
+    // source row of buffer for row r of tile t at step s (src/trajectory_buffer.cu:208-209)
+    auto src_of = [&](int s, int t, int r) -> int {
+        const int row = t * TM + r;
+        if (row >= p.mb) return -1;
+        const int e = s / p.num_batches, k = s - e * p.num_batches;
+        const int off = (k * p.batch_stride + p.row0 + row) % p.limit;
+        return p.perms ? __ldg(p.perms + (size_t)e * p.limit + off) : off;
+    };
+    float h_target = 0.f, h_adv = 0.f, h_lp_old = 0.f, h_act[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) h_act[j] = 0.f;
+    int my_src = -1;
+    // issue the gather of one tile: state rows by cp.async into Xt0 (feature-major), per-row scalars into registers
+    auto issue_gather = [&]() {
+        for (int e = tid; e < TM * SP; e += 256) {
+            const int r = e / SP, k = e - r * SP;
+            const int src = src_rows[r];
+            float* dst = Xt0 + k * TMP + r;
+            if (src >= 0 && k < S) cp_async4(dst, p.state + (size_t)src * S + k);
+            else *dst = 0.f;
+        }
+        if (tid < TM) {
+            my_src = src_rows[tid];
+            h_target = 0.f; h_adv = 0.f; h_lp_old = 0.f;
+            if (my_src >= 0) {
+                if (p.mode == kFusedValue) {
+                    h_target = __ldg(p.adv_target + my_src);
+                } else {
+                    h_adv = __ldg(p.advantage + my_src);
+                    h_lp_old = __ldg(p.logprob + my_src);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (j < OUT) h_act[j] = __ldg(p.action + (size_t)my_src * OUT + j);
+                }
+            }
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    int nxt_src = -1;
+    if (rounds > 0) {
+        if (tid < TM) src_rows[tid] = src_of(0, t0, tid);
+        tile_sync(bar);
+        issue_gather();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+        tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+    }
+    uint32_t img_parity = 0;
+    mbar_wait(mbar, img_parity);
+    img_parity ^= 1;
+
+    for (int s = 0; s < p.n_steps; s++) {
+        if (threadIdx.x == 0 && p.mode == kFusedPolicy) {     // log_std is stable here: last written in [C] of step s-1, before [D]
+            float ent = (float)(p.A * 0.5 * (1 + log(2 * kPiF)));             // src/policy.cu:171-178
+            for (int j = 0; j < p.A; j++) ent += __ldcg(p.log_std + j);
+            s_entropy = ent;                                   // read by the owner of the loss element after barrier [B]
+        }
+        // ---- [A] this slot's tiles of minibatch s
+        for (int rd = 0; rd < rounds; rd++) {
+            const bool accum = rd > 0;
+            cp_async_wait_all();
+            tile_sync(bar);                                // the gathered tile is complete and visible
+            int ns = s, nt = t0 + (rd + 1) * stride;       // the item after this one
+            if (rd + 1 >= rounds) { ns = s + 1; nt = t0; }
+            const bool have_next = ns < p.n_steps;
+            if (have_next && tid < TM) nxt_src = src_of(ns, nt, tid);     // in flight during the tile
+            if (p.dbg && tid == 0 && sub == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 3] = t; }
+            for (int l = 0; l < net.L; l++) {
+                const float* Xt = act0 + net.a_off[l];
+                float* Yt = act0 + net.a_off[l + 1];
+                if (net.sizes[l + 1] <= 8)
+                    t64_forward_skinny(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, scratch, net.sizes[l], net.sizes[l + 1], net.acts[l], tid, bar);
+                else
+                    for (int cb = 0; cb < pad4(net.sizes[l + 1]); cb += 64) {
+                        if (cb) tile_sync(bar);
+                        t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp, cb, bar);
+                    }
+                tile_sync(bar);
+            }
+            float* Yt = act0 + net.a_off[net.L];
+            t64_loss_head(hc, Yt, red, slab, tid, bar, my_src >= 0, h_target, h_adv, h_lp_old, h_act, accum);
+            const float* G = Yt;
+            for (int l = net.L - 1; l >= 0; l--) {
+                const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
+                const float* Xt = act0 + net.a_off[l];
+                float* Gout = ebuf + ((net.L - 1 - l) & 1) * (net.max_width_pad * TMP);
+                if (grp == 0) {
+                    t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt, accum);
+                    t64_bias_grad(G, slab + net.b_off[l], n_out, lt, accum);
+                } else if (l > 0) {
+                    for (int kb = 0; kb < pad4(n_in); kb += 64)
+                        t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt, kb);
+                }
+                tile_sync(bar);                            // (also after l == 0: Xt0 / src_rows are about to be refilled)
+                G = Gout;
+            }
+            if (have_next) {
+                if (tid < TM) src_rows[tid] = nxt_src;
+                tile_sync(bar);
+                issue_gather();
+            }
+        }
+        if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 4] = t; }
+        // ---- [B] every slab of minibatch s is written
+        ++bar_gen;
+        phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
+        if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 5] = t; }
+        // ---- [C] slice reduction + (cross-GPU sum) + Adam + image refresh
+        {
+            const int total = p.P + p.A + 1;
+            const int G_ = gridDim.x;
+            const int chunk = 32 * ((total + 32 * G_ - 1) / (32 * G_));
+            const int e0 = blockIdx.x * chunk, e1 = min(total, e0 + chunk);
+            const int ngroups = e1 > e0 ? (e1 - e0 + 31) >> 5 : 0;
+            const int W = blockDim.x >> 5;
+            int ways = 1;
+            while (ways * 2 * max(ngroups, 1) <= W) ways *= 2;
+            const int gpr = W / ways;                      // 32-element groups handled per round
+            const int per = (nslabs + ways - 1) / ways;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const float4 cf = __ldg(p.coef + s);
+            for (int g0 = 0; g0 < ngroups; g0 += gpr) {
+                const int gi = g0 + warp / ways, part = warp % ways;
+                const int e = e0 + gi * 32 + lane;
+                const bool live = gi < ngroups && e < e1;
+                const bool fin = live && part == 0;
+                const bool is_net = e < p.P, is_ls = !is_net && e < p.P + p.A && p.mode == kFusedPolicy;
+                float pm = 0.f, pv = 0.f, pw = 0.f;
+                if (fin) {      // optimiser state of this element (only ever touched by this thread): overlaps the slab loads
+                    if (is_net) { pm = p.netseg.m[e]; pv = p.netseg.v[e]; pw = p.netseg.w[e]; }
+                    else if (is_ls) { pm = p.ls.m[e - p.P]; pv = p.ls.v[e - p.P]; pw = p.ls.w[e - p.P]; }
+                    else if (e == p.P + p.A && p.mode == kFusedPolicy) pw = s_entropy;
+                }
+                float sum = 0.f;
+                if (live) {
+                    const int b0 = part * per, b1 = min(nslabs, b0 + per);
+                    const float* src = p.partials + e;
+                    int b = b0;
+                    for (; b + 16 <= b1; b += 16) {
+                        float t[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) t[u] = __ldcg(src + (size_t)(b + u) * p.slab);
+#pragma unroll
+                        for (int u = 0; u < 16; u++) sum += t[u];
+                    }
+                    for (; b + 4 <= b1; b += 4) {
+                        float t[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) t[u] = __ldcg(src + (size_t)(b + u) * p.slab);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) sum += t[u];
+                    }
+                    for (; b < b1; b++) sum += __ldcg(src + (size_t)b * p.slab);
+                }
+                redw[warp][lane] = sum;
+                __syncthreads();
+                if (fin) {
+                    float g = redw[warp][lane];
+                    for (int q = 1; q < ways; q++) g += redw[warp + q][lane];
+                    if (p.peer.ready) {
+                        // gradient exchange over NVLink peer memory (dist.cu "peer arena"): push {tag, value}, poll, ordered sum
+                        const PeerView& pvw = p.peer;
+                        const unsigned int epoch = pvw.epoch + (unsigned int)s;
+                        const size_t poff = (size_t)(epoch & 1u) * pvw.parity_stride;
+                        const unsigned long long packed = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(g);
+                        for (int r = 0; r < pvw.world; r++)
+                            if (r != pvw.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(pvw.peer_recv[r] + poff + e), "l"(packed) : "memory");
+                        const long long tstart = clock64();
+                        float acc = 0.f;
+                        for (int r = 0; r < pvw.world; r++) {
+                            float x = g;
+                            if (r != pvw.rank) {
+                                const unsigned long long* srcw = pvw.my_recv + poff + (size_t)r * kPeerCap + e;
+                                unsigned long long w;
+                                do {
+                                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(srcw) : "memory");
+                                    if ((unsigned int)(w >> 32) != epoch && clock64() - tstart > p.spin_limit) {
+                                        printf("ppo_b200: peer exchange timed out (rank %d waiting for rank %d, exchange %u)\n", pvw.rank, r, epoch);
+                                        __trap();
+                                    }
+                                } while ((unsigned int)(w >> 32) != epoch);
+                                x = __uint_as_float((unsigned int)w);
+                            }
+                            acc += x;                      // same numbers, same (rank) order on every GPU
+                        }
+                        g = acc;
+                    }
+                    if (is_net) {
+                        AdamSeg sg = p.netseg;
+                        sg.step_size = cf.x; sg.bc2 = cf.y;
+                        const float w = adam_apply(sg, e, g, pm, pv, pw);
+                        const int ii = image_index(p.net, e);
+                        if (ii >= 0) p.image[ii] = w;
+                    } else if (e < p.P + p.A) {
+                        if (is_ls) {
+                            AdamSeg sg = p.ls;
+                            sg.step_size = cf.z; sg.bc2 = cf.w;
+                            adam_apply(sg, e - p.P, g + (-p.ent_coeff), pm, pv, pw);     // src/ppo.cu:436-438
+                        }
+                    } else {
+                        if (p.mode == kFusedValue) *p.loss_slot += g / (float)p.m_total;
+                        else *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 6] = t; }
+        if (s + 1 < p.n_steps) {
+            // ---- [D] every slice of the new weights is in the global image; [E] re-stage it
+            ++bar_gen;
+            phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this TMA (async proxy) read
+                mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+                tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+            }
+            mbar_wait(mbar, img_parity);
+            img_parity ^= 1;
+            if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 7] = t; }
         }
     }
 }
@@ -919,6 +1273,120 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
     }
     B200_LAUNCH_PDL(fused_reduce_adam_kernel, div_up(slab, 32), 32 * kRedWarps, 0, pdl, r);
     return true;
+}
+
+// ---- persistent phase launch ------------------------------------------------------------------------
+static bool phase_enabled() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("PPO_B200_PERSISTENT"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
+
+struct PhaseGeom { bool ok; int nsub, grid; size_t smem; int sub_floats; };
+static PhaseGeom phase_geometry(const FusedPlan& pl, int mb) {
+    PhaseGeom g{};
+    if (!pl.ok) return g;
+    // one tile slot: [activations | E0 E1 | reduction scratch] = everything of the plan after the image
+    const int sub_floats = ((int)(pl.smem_bytes / sizeof(float)) - pl.net.img_floats + 3) & ~3;
+    const int n_tiles = div_up(mb, kT64TM);
+    const size_t limit = 226 * 1024;
+    auto bytes = [&](int nsub) { return (size_t)(pl.net.img_floats + nsub * sub_floats + 4) * sizeof(float); };
+    int nsub = (n_tiles > num_sms() && bytes(2) <= limit) ? 2 : 1;
+    if (bytes(nsub) > limit) return g;
+    g.ok = true;
+    g.nsub = nsub;
+    g.sub_floats = sub_floats;
+    g.smem = bytes(nsub);
+    g.grid = std::max(1, std::min(num_sms(), div_up(n_tiles, nsub)));
+    return g;
+}
+
+bool fused_phase_supported(NeuralNetwork* nn) {
+    if (!phase_enabled()) return false;
+    const FusedPlan pl = choose_plan(net_dev(nn));
+    return pl.ok && phase_geometry(pl, 64).ok;
+}
+
+static unsigned int* g_phase_barrier = nullptr;
+static float4* g_phase_coef = nullptr;
+static int g_phase_coef_cap = 0;
+
+void fused_phase_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr, const int* perms,
+                        int limit, int mb, int m_total, int row0, int batch_stride, int num_batches, int n_epochs,
+                        const TrajectoryBuffer* b, float epsilon, float ent_coeff, float* loss_slot, bool dp_peer) {
+    NetDev* nd = net_dev(nn);
+    const FusedPlan pl = choose_plan(nd);
+    const PhaseGeom geo = phase_geometry(pl, mb);
+    if (!geo.ok) B200_FATAL("fused_phase_update on an unsupported net");
+    const int n_steps = n_epochs * num_batches;
+    if (n_steps <= 0 || mb <= 0) return;
+    const int A = policy ? policy->action_size : 1;
+    const int slab = (int)nd->param_count + A + 1;
+    const int nslabs = std::min(div_up(mb, kT64TM), geo.grid * geo.nsub);
+    const size_t need = (size_t)nslabs * slab;
+    if (need > nd->partials_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
+        nd->partials = dmalloc<float>(need);
+        nd->partials_cap = need;
+    }
+    if (!g_phase_barrier) g_phase_barrier = dmalloc<unsigned int>(32);
+    if (n_steps > g_phase_coef_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (g_phase_coef) CUDA_CHECK(cudaFree(g_phase_coef));
+        g_phase_coef_cap = n_steps + 64;
+        g_phase_coef = dmalloc<float4>(g_phase_coef_cap);
+    }
+    // per-step bias corrections, host powf exactly as src/adam.cu:56-59 evaluates them
+    std::vector<float4> coef(n_steps);
+    for (int s = 0; s < n_steps; s++) {
+        const int tn = adam_net->time_step + s + 1;
+        coef[s].x = lr / (1 - powf(adam_net->beta1, tn));
+        coef[s].y = 1 - powf(adam_net->beta2, tn);
+        coef[s].z = coef[s].w = 0.f;
+        if (policy) {
+            const int tl = adam_ls->time_step + s + 1;
+            coef[s].z = lr / (1 - powf(adam_ls->beta1, tl));
+            coef[s].w = 1 - powf(adam_ls->beta2, tl);
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(g_phase_coef, coef.data(), (size_t)n_steps * sizeof(float4), cudaMemcpyHostToDevice, stream()));
+    CUDA_CHECK(cudaMemsetAsync(g_phase_barrier, 0, sizeof(unsigned int), stream()));
+
+    PhaseArgs a{};
+    a.net = pl.net;
+    a.image = ensure_image(nd, pl);
+    a.perms = perms; a.limit = limit; a.mb = mb; a.m_total = m_total; a.row0 = row0; a.batch_stride = batch_stride;
+    a.num_batches = num_batches; a.n_steps = n_steps;
+    a.mode = policy ? kFusedPolicy : kFusedValue;
+    a.state = b->d_state_p; a.action = b->d_action_p; a.logprob = b->d_logprob_p;
+    a.advantage = b->d_advantage_p; a.adv_target = b->d_adv_target_p;
+    a.log_std = policy ? policy->d_log_std : nullptr;
+    a.epsilon = epsilon; a.ent_coeff = ent_coeff;
+    a.partials = nd->partials; a.slab = slab; a.P = (int)nd->param_count; a.A = A;
+    a.sub_floats = geo.sub_floats;
+    a.g_off = pl.g_off - pl.net.img_floats;
+    a.red_off = pl.red_off - pl.net.img_floats;
+    a.netseg = make_seg(nd->params, nd->grads, adam_net, lr);
+    if (policy) a.ls = make_seg(policy->d_log_std, policy->d_log_std_grad, adam_ls, lr);
+    a.coef = g_phase_coef;
+    a.loss_slot = loss_slot;
+    a.barrier = g_phase_barrier;
+    a.spin_limit = dist_spin_limit();
+    a.dbg = phase_dbg();
+    if (dp_peer) {
+        a.peer = dist_peer_reserve((size_t)slab, n_steps);
+        if (!a.peer.ready) B200_FATAL("peer exchange requested but the peer arena is not available (slab %d floats)", slab);
+    }
+    static size_t configured = 0;
+    if (geo.smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(fused_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+        configured = geo.smem;
+    }
+    B200_LAUNCH_COOP(fused_phase_kernel, geo.grid, 256 * geo.nsub, geo.smem, &a);
+    adam_net->time_step += n_steps;
+    if (policy) adam_ls->time_step += n_steps;
+    nd->last_splits = nslabs;
 }
 
 }  // namespace b200

@@ -132,6 +132,12 @@ __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 bool fused_image64(NeuralNetwork* nn, FusedNet* layout, const float** image);   // false: net outside the 64-wide kernels
 bool fused_supported(NeuralNetwork* nn);
 void fused_forward(NeuralNetwork* nn, const float* x, int m, float* y_out);
+// One persistent cooperative launch for `n_epochs` x `num_batches` minibatches of one net (fused_phase_kernel).
+// perms: [n_epochs][limit] device permutations.  Minibatch k of an epoch covers rows k*batch_stride + row0 .. + mb of the permutation.
+bool fused_phase_supported(NeuralNetwork* nn);
+void fused_phase_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr, const int* perms,
+                        int limit, int mb, int m_total, int row0, int batch_stride, int num_batches, int n_epochs,
+                        const TrajectoryBuffer* b, float epsilon, float ent_coeff, float* loss_slot, bool dp_peer);
 bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_net, Adam* adam_ls, float lr,
                             const int* perm, int offset, int limit, int m, int m_total, const TrajectoryBuffer* b,
                             float epsilon, float ent_coeff, float* loss_slot, float* reduced_out, bool chained = false,
@@ -181,8 +187,12 @@ struct PeerView {                                    // kernel argument: one gra
     unsigned int epoch;                              // tag of this exchange (never 0)
     unsigned long long* my_recv;                     // my receive lanes of this epoch's parity: [source rank][kPeerCap]
     unsigned long long* peer_recv[kPeerMaxRanks];    // lane [my rank] inside rank r's receive buffer (same parity)
+    size_t parity_stride;                            // dist_peer_reserve views: pointers are parity 0, exchange e uses (e & 1) * parity_stride
 };
 PeerView dist_peer_next(size_t vec_floats);
+// `count` consecutive exchanges for one persistent kernel: epoch = tag of the first; pointers address parity 0
+PeerView dist_peer_reserve(size_t vec_floats, int count);
+long long dist_spin_limit();                          // clock64 ticks a device-side wait may last (PPO_B200_SPIN_TIMEOUT_S, default 120 s)
 bool dist_peer_ready();
 bool dist_active();
 int dist_rank();

@@ -28,6 +28,11 @@ struct Trainer {
     int* d_perm[2] = {nullptr, nullptr};
     cudaEvent_t perm_evt[2] = {nullptr, nullptr};
     int perm_cap = 0, perm_slot = 0;
+    int* h_perm_all = nullptr;   // all permutations of one phase (persistent phase kernel): [epochs][limit]
+    int* d_perm_all = nullptr;
+    size_t perm_all_cap = 0;
+    cudaEvent_t perm_all_evt = nullptr;
+    float* d_align = nullptr;    // one float all-reduced at the start of a data-parallel update (rank alignment)
     int perm_mode = -1;          // -1 auto: device generator after a device rollout, reference rand() chain otherwise
     bool last_rollout_on_device = false;
     unsigned long long perm_seed = 0, perm_epoch = 0;
@@ -39,6 +44,12 @@ struct Trainer {
     int eval_episodes = 0;
 };
 static std::unordered_map<PPO*, Trainer*> g_trainers;
+
+__global__ void add_scalar_kernel(float* x, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += v;
+}
+static void add_scalar(float* x, int n, float v) { B200_LAUNCH(add_scalar_kernel, div_up(n, 64), 64, 0, x, n, v); }
 
 static Trainer* trainer(PPO* ppo) {
     auto it = g_trainers.find(ppo);
@@ -54,6 +65,7 @@ static Trainer* attach_trainer(PPO* ppo) {
     t->d_dist_triples = dmalloc<double>(3 * 64);
     CUDA_CHECK(cudaEventCreateWithFlags(&t->perm_evt[0], cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&t->perm_evt[1], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&t->perm_all_evt, cudaEventDisableTiming));
     g_trainers[ppo] = t;
     return t;
 }
@@ -101,6 +113,46 @@ static const int* next_permutation(Trainer* t, int n) {
         CUDA_CHECK(cudaEventRecord(t->perm_evt[s], stream()));
     }
     return t->d_perm[s];
+}
+
+// The permutations of `n_epochs` consecutive epochs, [n_epochs][n] on the device, generated up front: nothing but the
+// shuffles draws from rand() during the update phase, so producing them before the first minibatch of
+// the phase leaves the reference's rand() stream untouched.
+static const int* phase_permutations(Trainer* t, int n, int n_epochs) {
+    const size_t need = (size_t)n * n_epochs;
+    if (need > t->perm_all_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (t->h_perm_all) CUDA_CHECK(cudaFreeHost(t->h_perm_all));
+        if (t->d_perm_all) CUDA_CHECK(cudaFree(t->d_perm_all));
+        t->h_perm_all = nullptr;
+        t->d_perm_all = dmalloc<int>(need);
+        t->perm_all_cap = need;
+    }
+    const bool on_device = t->perm_mode == 1 || (t->perm_mode < 0 && t->last_rollout_on_device);
+    if (on_device) {
+        for (int e = 0; e < n_epochs; e++) ppo_b200_permutation(t->d_perm_all + (size_t)e * n, n, t->perm_seed, t->perm_epoch++);
+    } else {
+        if (!t->h_perm_all) t->h_perm_all = hmalloc_pinned<int>(t->perm_all_cap);
+        CUDA_CHECK(cudaEventSynchronize(t->perm_all_evt));     // the upload that last read this pinned buffer
+        for (int e = 0; e < n_epochs; e++) host_shuffle(t->h_perm_all + (size_t)e * n, n);   // glibc rand(), reference order
+        CUDA_CHECK(cudaMemcpyAsync(t->d_perm_all, t->h_perm_all, need * sizeof(int), cudaMemcpyHostToDevice, stream()));
+        CUDA_CHECK(cudaEventRecord(t->perm_all_evt, stream()));
+    }
+    return t->d_perm_all;
+}
+
+// One phase (all value epochs or all policy epochs) through the persistent kernel, in launches of as many epochs as fit
+// the permutation budget.
+static void phase_epochs(Trainer* t, NeuralNetwork* nn, GaussianPolicy* pol, Adam* adam_net, Adam* adam_ls, float lr, int limit,
+                         int mb_local, int mb_total, int row0, int batch_size, int num_batches, int n_epochs,
+                         const TrajectoryBuffer* b, float epsilon, float ent_coeff, float* loss_slot, bool peer) {
+    const int per_launch = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_epochs, (size_t(256) << 20) / ((size_t)limit * sizeof(int))));
+    for (int e0 = 0; e0 < n_epochs; e0 += per_launch) {
+        const int ne = std::min(per_launch, n_epochs - e0);
+        const int* perms = phase_permutations(t, limit, ne);
+        fused_phase_update(nn, pol, adam_net, adam_ls, lr, perms, limit, mb_local, mb_total, row0, batch_size, num_batches, ne, b,
+                           epsilon, ent_coeff, loss_slot, peer);
+    }
 }
 
 // PPO_B200_FUSED=0 forces the generic layer-wise kernels (A/B testing, parity tests of both paths).
@@ -165,17 +217,32 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
     NetDev* ndP = net_dev(pol->mu);
     const bool fusedV = use_fused() && fused_supported(ppo->V);
     const bool fusedP = use_fused() && fused_supported(pol->mu);
-    // small-net gradients cross the GPUs inside the Adam kernel over NVLink peer memory when it can be mapped
-    const bool peer = G > 1 && (fusedV || fusedP) && dist_peer_ready();
+    // small-net gradients cross the GPUs inside the update kernel over NVLink peer memory when it can be mapped and the
+    // net's slab fits a receive lane; otherwise that net goes slab-reduce -> NCCL all-reduce -> Adam
+    const bool peer_ok = G > 1 && (fusedV || fusedP) && dist_peer_ready();
+    const bool peerV = peer_ok && fusedV && ndV->param_count + 2 <= kPeerCap;
+    const bool peerP = peer_ok && fusedP && ndP->param_count + A + 1 <= kPeerCap;
+    if (peerV || peerP) {
+        // ranks enter the exchange loop together: benign skew (a slow host shuffle, first-iteration allocations) is absorbed
+        // by a stream-ordered NCCL collective instead of the in-kernel poll
+        if (!t->d_align) { t->d_align = dmalloc<float>(1); CUDA_CHECK(cudaMemsetAsync(t->d_align, 0, sizeof(float), stream())); }
+        dist_allreduce_sum(t->d_align, 1);
+    }
     CUDA_CHECK(cudaMemsetAsync(t->d_scalars, 0, 2 * sizeof(float), stream()));
     t->n_v_steps = n_epochs_value * num_batches;
     t->n_p_steps = n_epochs_policy * num_batches;
+    const bool phaseV = fusedV && (G == 1 || peerV) && fused_phase_supported(ppo->V);
+    const bool phaseP = fusedP && (G == 1 || peerP) && fused_phase_supported(pol->mu);
 
     // ---- value epochs, src/ppo.cu:491-510
-    for (int j = 0; j < n_epochs_value; j++) {
+    if (phaseV && num_batches > 0)
+        phase_epochs(t, ppo->V, nullptr, ppo->adam_V, nullptr, ppo->lr_V, limit, mb_local, mb_total, row0, batch_size, num_batches,
+                     n_epochs_value, b, 0.f, 0.f, t->d_scalars + 0, peerV);
+    for (int j = 0; j < (phaseV ? 0 : n_epochs_value); j++) {
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
             if (fusedV) {
+                const bool peer = peerV;
                 float* red = (G > 1 && !peer) ? static_cast<float*>(scratch(kScratchMisc, (ndV->param_count + 2) * sizeof(float))) : nullptr;
                 fused_minibatch_update(ppo->V, nullptr, ppo->adam_V, nullptr, ppo->lr_V, perm, k * batch_size + row0, limit,
                                        mb_local, mb_total, b, 0.f, 0.f, t->d_scalars + 0, red, k > 0, peer);
@@ -207,18 +274,22 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
         }
     }
     // ---- policy epochs, src/ppo.cu:512-533
-    for (int j = 0; j < n_epochs_policy; j++) {
+    if (phaseP && num_batches > 0)
+        phase_epochs(t, pol->mu, pol, ppo->adam_policy, ppo->adam_entropy, ppo->lr_policy, limit, mb_local, mb_total, row0, batch_size,
+                     num_batches, n_epochs_policy, b, ppo->epsilon, ppo->ent_coeff, t->d_scalars + 1, peerP);
+    for (int j = 0; j < (phaseP ? 0 : n_epochs_policy); j++) {
         const int* perm = next_permutation(t, limit);
         for (int k = 0; k < num_batches; k++) {
             if (fusedP) {
+                const bool peer = peerP;
                 float* red = (G > 1 && !peer) ? static_cast<float*>(scratch(kScratchMisc, (ndP->param_count + A + 1) * sizeof(float))) : nullptr;
-                if (G > 1 && ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
                 fused_minibatch_update(pol->mu, pol, ppo->adam_policy, ppo->adam_entropy, ppo->lr_policy, perm,
                                        k * batch_size + row0, limit, mb_local, mb_total, b, ppo->epsilon, ppo->ent_coeff,
                                        t->d_scalars + 1, red, k > 0, peer);
                 if (G > 1 && !peer) {
-                    if (ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
                     dist_allreduce_sum(red, ndP->param_count + A + 1);
+                    // entropy gradient (src/ppo.cu:436-438): added once, AFTER the cross-rank sum
+                    if (ppo->ent_coeff != 0.f) add_scalar(red + ndP->param_count, A, -ppo->ent_coeff);
                     ppo->adam_entropy->time_step += 1;
                     ppo->adam_policy->time_step += 1;
                     adam_flat(pol->d_log_std, red + ndP->param_count, ppo->adam_entropy->m, ppo->adam_entropy->v, A, ppo->lr_policy,
@@ -241,7 +312,8 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
                 net_reduce_grads(pol->mu);
                 dist_allreduce_sum(ndP->grads, ndP->param_count);
                 dist_allreduce_sum(pol->d_log_std_grad, A);
-                if (ppo->ent_coeff != 0.f) B200_FATAL("ent_coeff != 0 under data parallelism is not supported yet");
+                // launch_policy_head added -ent_coeff on every rank: the sum carries it G times, the reference once
+                if (ppo->ent_coeff != 0.f) add_scalar(pol->d_log_std_grad, A, (G - 1) * ppo->ent_coeff);
             }
             // log_std first, then the mu-net (src/ppo.cu:529-531)
             adam_flat(pol->d_log_std, pol->d_log_std_grad, ppo->adam_entropy->m, ppo->adam_entropy->v, A, ppo->lr_policy,
@@ -313,6 +385,10 @@ void free_ppo(PPO* ppo) {
         float* ptrs[] = {t->states, t->actions, t->lp_old, t->adv, t->advt, t->lp, t->gl, t->gmu, t->d_scalars};
         for (float* p : ptrs) if (p) CUDA_CHECK(cudaFree(p));
         CUDA_CHECK(cudaFree(t->d_dist_triples));
+        if (t->h_perm_all) CUDA_CHECK(cudaFreeHost(t->h_perm_all));
+        if (t->d_perm_all) CUDA_CHECK(cudaFree(t->d_perm_all));
+        if (t->d_align) CUDA_CHECK(cudaFree(t->d_align));
+        CUDA_CHECK(cudaEventDestroy(t->perm_all_evt));
         for (int s = 0; s < 2; s++) {
             if (t->h_perm[s]) CUDA_CHECK(cudaFreeHost(t->h_perm[s]));
             if (t->d_perm[s]) CUDA_CHECK(cudaFree(t->d_perm[s]));
