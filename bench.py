@@ -4,6 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
 Workloads = BASELINE.json configs:
+  c1 (configs[0])  the reference's own default run: Pendulum-v1 behind the Env hooks (host env, one step at a time), 2x64 ReLU,
+       capacity 3000, minibatch 64, 10 value + 4 policy epochs, 30 000 env-steps per train_ppo_epoch (src/main.c:33-43).
+       GPU arm = the drop-in library behind the unmodified call; CPU arm = the UNMODIFIED reference (oracle/_ref) linked
+       against the image's OpenBLAS (one thread, src/main.c:18) or, if that cannot load, its sequential-k cblas shim.
   c2 (default, configs[1])  Pendulum-v1 PPO, 4096 device envs/GPU x T=200, 2x64 tanh, fp32.  One step =
        one PPO iteration: fused device rollout (819 200 env-steps/GPU) + GAE + 10 value + 4 policy
        epochs of minibatch 18 944 = 148 SMs x 2 CTAs x 64 rows (the reference schedule, src/main.c:33-43).  Unit: env-steps/s.
@@ -44,6 +48,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 f32, u8 = np.float32, np.uint8
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FMA lanes x 2 x 1.965 GHz (nominal)
+FP32_MEASURED = {}     # filled live by run_gpu_arm: ppo_b200_measure_fp32_peak (csrc/ubench.cu)
 
 
 def load_peaks():
@@ -120,6 +125,88 @@ def synthetic_rollout(rng, T, N, S, A):
     return dict(state=rng.standard_normal((n, S), dtype=f32), next_state=rng.standard_normal((n, S), dtype=f32),
                 action=rng.standard_normal((n, A), dtype=f32), reward=rng.standard_normal(n, dtype=f32),
                 logprob=np.zeros(n, f32), terminated=(rng.random(n) < 1e-3).astype(u8), truncated=trunc.astype(u8))
+
+
+class C1(Workload):
+    """BASELINE.json configs[0]: the reference's default run (src/main.c:20-43) — one Pendulum env behind the Env hooks."""
+    name = "c1"
+    SIZES, ACTS = [3, 64, 64, 1], ["relu", "relu", "none"]
+    CAP, STEPS, MB, N_POL, N_VAL = 3000, 30000, 64, 4, 10
+
+    def setup(self):
+        import cabi
+        L = self.L
+        cabi.srand(1234)
+        self.env = L.create_pendulum_env(0, 100 + self.rank)          # host env: same hooks as the reference's gym bridge
+        self.ppo = L.create_ppo(cabi.cstr_array(self.ACTS), cabi.int_array(self.SIZES), len(self.SIZES), self.CAP,
+                                3e-4, 3e-4, 0.95, 0.2, 0.0, 1.0, True)
+
+    def step_device(self, k):
+        for _ in range(k):
+            self.L.train_ppo_epoch(self.ppo, self.env, self.STEPS, self.MB, self.N_POL, self.N_VAL)
+
+    step_e2e = step_device      # the env lives on the host: every transition crosses the boundary in both legs
+
+    def units_per_step(self):
+        return self.STEPS
+
+    def e2e_bytes(self):
+        S, A = self.SIZES[0], self.SIZES[-1]
+        iters = self.STEPS // self.CAP
+        buf = self.CAP * (4 * (2 * S + A + 4) + 2)
+        p = mlp_params(self.SIZES) + mlp_params(self.SIZES[:-1] + [1]) + A
+        # per env step: the state goes up, action + log-prob come down; per iteration: buffer up, buffer + weights down
+        return self.STEPS * 4 * S + iters * buf, self.STEPS * 4 * (A + 1) + iters * (buf + 4 * p)
+
+    def config(self):
+        return {"workload": "c1: the reference's default run (src/main.c:20-43): Pendulum-v1 behind the Env hooks (one host env), "
+                            "2x64 ReLU, capacity %d, minibatch %d, %d value + %d policy epochs, %d env-steps per train_ppo_epoch "
+                            "(BASELINE.json configs[0])" % (self.CAP, self.MB, self.N_VAL, self.N_POL, self.STEPS),
+                "parallelism": "replicas x%d" % self.world,
+                "l2": "latency-bound config (18 KB nets, 3000-row buffer): everything is cache resident by construction, as in the reference",
+                "permutation": "reference rand() swap chain (bit-exact mode)",
+                "e2e_call": "train_ppo_epoch(ppo, env, 30000, 64, 4, 10) with a HOST env: per step the state crosses to the device and "
+                            "the sampled action / log-prob come back; per iteration buffer_to_device + update + host mirrors"}
+
+    def extra(self, ms):
+        nb = self.CAP // self.MB
+        return {"update_samples_per_s": self.world * (self.STEPS // self.CAP) * (self.N_POL + self.N_VAL) * nb * self.MB / (ms * 1e-3)}
+
+    def roofline_work(self, kernels):
+        it, nb = self.STEPS // self.CAP, self.CAP // self.MB
+        sv = self.SIZES[:-1] + [1]
+        flops = it * nb * (self.N_VAL * train_flops(sv, self.MB) + self.N_POL * train_flops(self.SIZES, self.MB))
+        return {"fused_phase_kernel": ("fp32", flops), "sample_action": ("fp32", 2.0 * self.STEPS * mlp_weights(self.SIZES))}
+
+    def teardown(self):
+        self.L.free_ppo(self.ppo)
+        self.env.contents.free_env()
+
+    # CPU arm: the UNMODIFIED reference on the oracle's C Pendulum behind its own Env hooks
+    ref_kind = "reference"
+
+    def cpu_sample(self, n_iters, seed=1, blas=True):
+        import cabi
+        import oracle
+        cabi.unlimit_stack()
+        lib = cabi.load_ref_blas() if blas else None
+        self.cpu_blas = "OpenBLAS 0.3.15 (bundled with the image), 1 thread" if lib is not None else "sequential-k cblas shim (oracle/shim)"
+        if lib is None:
+            lib = cabi.load_ref()
+        env = cabi.oracle_pendulum_env(oracle.lib())
+        cabi.srand(seed)
+        ppo = lib.create_ppo(cabi.cstr_array(self.ACTS), cabi.int_array(self.SIZES), len(self.SIZES), self.CAP, C.c_float(3e-4),
+                             C.c_float(3e-4), C.c_float(0.95), C.c_float(0.2), C.c_float(0.0), C.c_float(1.0), False)
+        times = []
+        for _ in range(n_iters):
+            t0 = time.perf_counter()
+            lib.train_ppo_epoch(ppo, C.byref(env), self.STEPS, self.MB, self.N_POL, self.N_VAL)
+            times.append(time.perf_counter() - t0)
+        return times, self.STEPS
+
+    def cpu_sample_desc(self):
+        return ("the UNMODIFIED reference (oracle/_ref, use_cuda=false) through its own train_ppo_epoch on the C Pendulum behind "
+                "its Env hooks; BLAS = %s; %d env-steps per step" % (getattr(self, "cpu_blas", "OpenBLAS if loadable"), self.STEPS))
 
 
 class C2(Workload):
@@ -201,6 +288,11 @@ class C2(Workload):
         red_bytes = (self.N_VAL * nb * (ctas * slab_v * 4 + 32 * mlp_params(sv))
                      + self.N_POL * nb * (ctas * slab_p * 4 + 32 * mlp_params(self.SIZES)))
         roll_flops = 2 * B * mlp_weights(self.SIZES)
+        if any("fused_phase_kernel" in k for k in kernels):          # persistent path: the whole update is one kernel per phase
+            gae_fwd = 2 * 2 * B * mlp_weights(sv)
+            return {"fused_phase_kernel": ("fp32", upd_flops - gae_fwd), "fused_tile64_kernel": ("fp32", gae_fwd),
+                    "rollout64_kernel": ("fp32", roll_flops), "rollout_kernel": ("fp32", roll_flops),
+                    "gae_scan": ("hbm", 22.0 * B), "gae_normalize_kernel": ("hbm", 8.0 * B)}
         return {"fused_tile64_kernel": ("fp32", upd_flops),
                 "fused_reduce_adam_kernel": ("hbm", red_bytes),      # slab reads + 28 B/param Adam + 4 B/param image
                 "rollout64_kernel": ("fp32", roll_flops), "rollout_kernel": ("fp32", roll_flops),
@@ -608,7 +700,7 @@ class GatherStage(StageWorkload):
         return "oracle port of get_batch (src/trajectory_buffer.cu:202-220) over %d rows" % self.CPU_B
 
 
-WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5, "adam": AdamStage, "gather": GatherStage}
+WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c4": C4, "c5": C5, "adam": AdamStage, "gather": GatherStage}
 
 
 # ======================================================================================= CPU arm
@@ -618,12 +710,24 @@ def _cpu_worker(args):
     return wl.cpu_sample(n_iters, seed)
 
 
+CPU_BUILD = ("oracle port, timing-only build: gcc -O3 -march=native -ffast-math, GEMM loops in vectorisable order "
+             "(`make -C oracle fast`, compiled on this host); the parity tests use the -O2 -ffp-contract=off build")
+
+
+def use_fast_oracle():
+    import oracle
+    oracle.use_fast_build()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cls = WORKLOADS[args.workload]
+    kind = getattr(cls, "ref_kind", "port")
+    if kind == "port":
+        use_fast_oracle()                 # before the fork: the workers inherit the selected build
     cores = max(1, min(len(os.sched_getaffinity(0)), 128))
     with mp.get_context("fork").Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(args.workload, args.warmup + args.steps, 1 + i) for i in range(cores)])
@@ -638,8 +742,9 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
-        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": cores, "kind": "port",
-                         "sample": wl.cpu_sample_desc() + "; %d independent replicas, one per host core" % cores},
+        "cpu_baseline": {"value": value, "unit": cls.unit, "cores": cores, "kind": kind,
+                         "sample": wl.cpu_sample_desc() + "; %d independent replicas, one per host core" % cores,
+                         "build": CPU_BUILD if kind == "port" else "unmodified reference sources, nvcc -O3 (oracle/Makefile)"},
         "e2e": {"value": value, "unit": cls.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -736,12 +841,19 @@ def build_roofline(kernels, work, traffic_file=None):
             psrc = pk["src"] + ": sustained cuBLAS bf16 / 2 (TF32 dense rate is half of bf16)"
             bound = "tensor"
         else:
-            ach, peak, unit = amount / sec / 1e12, FP32_PEAK_TFLOPS, "TFLOP/s"
-            psrc = ("nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json); "
-                    "a register-operand 8x4 FFMA tile measures 48 TFLOP/s (scalar) / 65 TFLOP/s (packed FFMA2) on this part, profiles/NOTES.md")
+            ach, unit = amount / sec / 1e12, "TFLOP/s"
+            peak = FP32_MEASURED.get("ffma_const_operands") or FP32_PEAK_TFLOPS
+            psrc = ("measured in this run (csrc/ubench.cu): FFMA stream with constant-bank operands = the fp32 pipe's peak"
+                    if FP32_MEASURED else "nominal fp32 FFMA: 148 SMs x 128 lanes x 2 x 1.965 GHz")
         out[prefix] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                        "launches": agg[prefix]["launches"], "avg_us": 1e3 * agg[prefix]["total_ms"] / agg[prefix]["launches"],
                        "peak_source": psrc}
+        if bound == "fp32":
+            out[prefix]["peak_nominal"] = FP32_PEAK_TFLOPS
+            if FP32_MEASURED.get("ffma2_register_operands"):
+                # what a GEMM-like inner loop with three REGISTER operands can issue (weights change every minibatch)
+                out[prefix]["peak_register_operand_ffma2"] = FP32_MEASURED["ffma2_register_operands"]
+                out[prefix]["frac_of_register_operand_ceiling"] = ach / FP32_MEASURED["ffma2_register_operands"]
     total = sum(k["total_ms"] for k in kernels.values())
     if not out:
         return None
@@ -757,7 +869,7 @@ def build_roofline(kernels, work, traffic_file=None):
     except (OSError, ValueError):
         pass
     r.update({"kernel": dom, "share_of_step": agg[dom]["total_ms"] / total if total > 0 else None, "traffic": traffic,
-              "per_kernel": out})
+              "sum_of_kernel_ms": total, "per_kernel": out})
     return r
 
 
@@ -788,6 +900,10 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if rank == 0 and not args.only_value:
+        FP32_MEASURED["ffma_const_operands"] = L.ppo_b200_measure_fp32_peak(0)
+        FP32_MEASURED["ffma_register_operands"] = L.ppo_b200_measure_fp32_peak(1)
+        FP32_MEASURED["ffma2_register_operands"] = L.ppo_b200_measure_fp32_peak(2)
     wl = WORKLOADS[args.workload](L, rank, world)
     if args.mb > 0 and hasattr(wl, "MB"):
         wl.MB = args.mb
@@ -867,14 +983,22 @@ def run_gpu_arm(args):
         roofline = build_roofline(kernels, wl.roofline_work(kernels))
     barrier()
 
+    units = world * wl.units_per_step()
+    h2d, d2h = wl.e2e_bytes()
+    cfg = wl.config()
+    wl.teardown()
+
+    # ---- the other named shapes, short runs, so that ONE default invocation carries every BASELINE.json config -----------
+    secondary = None
+    if args.workload == "c2" and not args.no_secondary:
+        secondary = run_secondary(L, rank, world, stream, barrier, torch, dist)
+
     if rank == 0:
-        units = world * wl.units_per_step()
-        h2d, d2h = wl.e2e_bytes()
         line = {
             "metric": wl.metric, "value": units * args.steps / (ms * 1e-3), "unit": wl.unit,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": wl.config(),
+            "config": cfg,
             "e2e": {"value": units * e2e_steps / (e2e_ms * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
             "api": None if api_ms is None else {"value": units * e2e_steps / (api_ms * 1e-3), "unit": wl.unit,
@@ -885,17 +1009,105 @@ def run_gpu_arm(args):
         line.update(extra)
         line["roofline"] = roofline
         line["kernels"] = kernels
+        line["fp32_peaks_measured_tflops"] = dict(FP32_MEASURED, nominal=FP32_PEAK_TFLOPS)
         if world == 1:
+            kind = getattr(wl, "ref_kind", "port")
+            parity_value = None
+            if kind == "port":
+                t_par, u_par = wl.cpu_sample(2)              # the bit-exact parity build, for the record
+                parity_value = u_par / t_par[-1]
+                use_fast_oracle()
             times, cpu_units = wl.cpu_sample(args.cpu_iters + 1)
             times = times[1:]
-            line["cpu_baseline"] = {"value": cpu_units / statistics.mean(times), "unit": wl.unit, "cores": 1, "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_units / statistics.mean(times), "unit": wl.unit, "cores": 1, "kind": kind,
                                     "sample": wl.cpu_sample_desc() + "; %d timed steps, one thread (the reference is "
-                                              "single-threaded, src/main.c:18)" % len(times)}
+                                              "single-threaded, src/main.c:18)" % len(times),
+                                    "build": CPU_BUILD if kind == "port" else "unmodified reference sources, nvcc -O3 (oracle/Makefile)"}
+            if parity_value is not None:
+                line["cpu_baseline"]["parity_build_value"] = parity_value
+        if secondary:
+            line["secondary"] = secondary
         emit(line)
-    wl.teardown()
     if world > 1:
         L.ppo_b200_dist_finalize()
         dist.destroy_process_group()
+
+
+def run_secondary(L, rank, world, stream, barrier, torch, dist):
+    """Short runs of the other BASELINE.json configs after the headline workload: value (device-resident, CUDA events, max over
+    ranks) + the roofline of the dominant kernel from one profiled step.  c1 (host env, not collective) only at N = 1."""
+    out = {}
+    for name, steps in (("c3", 2), ("c4", 2), ("c5", 5)):
+        wl = WORKLOADS[name](L, rank, world)
+        wl.setup()
+        wl.step_device(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        wl.step_device(steps)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.cpu()[0])
+        roof = None
+        if rank == 0:
+            L.ppo_b200_profile_begin()
+        wl.step_device(1)
+        if rank == 0:
+            buf = C.create_string_buffer(1 << 16)
+            L.ppo_b200_profile_end(buf, len(buf))
+            kernels = {}
+            for ln in buf.value.decode().splitlines():
+                kname, cnt, tot = ln.rsplit(" ", 2)
+                kernels[kname] = {"launches": int(cnt), "total_ms": float(tot)}
+            r = build_roofline(kernels, wl.roofline_work(kernels))
+            if r:
+                roof = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step", "peak_source")}
+                roof["whole_step_frac"] = whole_step_fraction(wl, ms / steps)
+        barrier()
+        out[name] = {"metric": wl.metric, "value": world * wl.units_per_step() * steps / (ms * 1e-3), "unit": wl.unit, "n_gpus": world,
+                     "steps": steps, "warmup": 1, "ms_per_step": ms / steps, "dtype": wl.dtype, "config": wl.config()["workload"],
+                     "roofline": roof}
+        wl.teardown()
+    if world == 1:
+        wl = WORKLOADS["c1"](L, rank, world)
+        wl.setup()
+        wl.step_device(1)
+        L.ppo_b200_sync()
+        t0 = time.perf_counter()
+        wl.step_device(2)
+        L.ppo_b200_sync()
+        sec = (time.perf_counter() - t0) / 2
+        wl.teardown()
+        c1 = {"metric": wl.metric, "value": wl.STEPS / sec, "unit": wl.unit, "n_gpus": 1, "steps": 2, "warmup": 1,
+              "s_per_epoch": sec, "config": wl.config()["workload"], "timing": "wall clock around train_ppo_epoch (host-driven env loop)"}
+        try:
+            t_blas, _ = wl.cpu_sample(2, blas=True)
+            c1["reference_cpu"] = {"value": wl.STEPS / t_blas[-1], "s_per_epoch": t_blas[-1], "kind": "reference", "cores": 1, "blas": wl.cpu_blas}
+            if "OpenBLAS" in wl.cpu_blas:
+                t_nv, _ = wl.cpu_sample(1, blas=False)
+                c1["reference_cpu_naive_cblas"] = {"value": wl.STEPS / t_nv[-1], "s_per_epoch": t_nv[-1], "kind": "reference", "cores": 1,
+                                                   "blas": wl.cpu_blas}
+        except Exception as exc:                                    # the reference .so did not travel / cannot load
+            c1["reference_cpu"] = {"unavailable": repr(exc)}
+        out["c1"] = c1
+    return out
+
+
+def whole_step_fraction(wl, ms_per_step):
+    """Whole-step arithmetic rate of a GEMM-bound workload against its peak (c4: TF32 tensor; c3: fp32), or None."""
+    if not hasattr(wl, "SIZES") or not hasattr(wl, "N_VAL") or not hasattr(wl, "cap"):
+        return None
+    nb = wl.cap // wl.MB
+    sv = wl.SIZES[:-1] + [1]
+    flops = (wl.N_VAL * nb * train_flops(sv, wl.MB) + wl.N_POL * nb * train_flops(wl.SIZES, wl.MB) + 2 * 2 * wl.cap * mlp_weights(sv))
+    tfs = flops / (ms_per_step * 1e-3) / 1e12
+    pk = load_peaks()
+    peak = pk["bf16"] / 2 if getattr(wl, "TF32", 0) else (FP32_MEASURED.get("ffma_const_operands") or FP32_PEAK_TFLOPS)
+    return {"tflops": tfs, "peak": peak, "frac": tfs / peak}
 
 
 _REAL_STDOUT = None
@@ -926,6 +1138,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: --steps)")
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--mb", type=int, default=0, help="override the workload's minibatch size per GPU (c2/c3/c4)")
+    ap.add_argument("--no-secondary", action="store_true", help="c2 only: skip the short c3 / c4 / c5 / c1 runs that fill `secondary`")
     ap.add_argument("--only-value", action="store_true",
                     help="skip the e2e / per-kernel / CPU legs (short command for ncu passes; not a bench line)")
     args = ap.parse_args()

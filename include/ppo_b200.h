@@ -354,6 +354,9 @@ void  ppo_b200_memset(void* dst, int value, size_t bytes);
 void  ppo_b200_sync(void);
 unsigned long long ppo_b200_launch_count(void); /* kernels launched by this library so far */
 const char* ppo_b200_version(void);
+/* measured fp32 FMA throughput of the current device in TFLOP/s: form 0 = FFMA with constant-bank operands (the pipe's peak),
+ * 1 = scalar FFMA on a register 8x4 tile, 2 = packed FFMA2 on the same tile (the form the MLP kernels issue) */
+double ppo_b200_measure_fp32_peak(int form);
 /* Per-kernel timing without a profiler: between begin and end every launch of the library is
  * bracketed by a CUDA-event pair on the launching stream.  end() writes "name count total_ms" lines. */
 void ppo_b200_profile_begin(void);

@@ -50,6 +50,18 @@ const float* orc_mlp_output(const float* cache, const int* sizes, int num_layers
 
 /* mat_mul.cu:39-55 with the sequential-k sgemm of oracle/shim: out = (sum_p x*w from 0) + b. */
 static void orc_mat_mul(float* out, const float* x, const float* w, const float* b, int m, int n, int l) {
+#ifdef ORC_FAST /* timing-only build (oracle/Makefile `fast`): dot products the compiler may vectorise over p (-ffast-math) */
+    for (int j = 0; j < m; j++)
+        for (int k = 0; k < l; k++) {
+            const float* xr = x + (size_t)j * n;
+            const float* wr = w + (size_t)k * n;
+            float acc = 0.0f;
+#pragma GCC ivdep
+            for (int p = 0; p < n; p++) acc += xr[p] * wr[p];
+            out[(size_t)j * l + k] = acc + b[k];
+        }
+    return;
+#endif
     for (int j = 0; j < m; j++)
         for (int k = 0; k < l; k++) {
             float acc = 0.0f;
@@ -124,6 +136,24 @@ void orc_mlp_backward(const float* params, const int* sizes, const int* acts, in
         }
         /* mat_mul.cu:57-80: grad_x = g . W ; grad_w = g^T . x (sequential sums from 0) */
         float* gx = (float*)malloc((size_t)m * n * sizeof(float));
+#ifdef ORC_FAST /* timing-only build: axpy forms (unit-stride inner loops over j), same products, different summation order */
+        memset(gx, 0, (size_t)m * n * sizeof(float));
+        for (int r = 0; r < m; r++)
+            for (int k = 0; k < l; k++) {
+                const float g = layer_grad[(size_t)r * l + k];
+                const float* wr = w + (size_t)k * n;
+                float* o = gx + (size_t)r * n;
+                for (int j = 0; j < n; j++) o[j] += g * wr[j];
+            }
+        memset(gw, 0, (size_t)l * n * sizeof(float));
+        for (int k = 0; k < m; k++)
+            for (int a = 0; a < l; a++) {
+                const float g = layer_grad[(size_t)k * l + a];
+                const float* xr = x + (size_t)k * n;
+                float* o = gw + (size_t)a * n;
+                for (int j = 0; j < n; j++) o[j] += g * xr[j];
+            }
+#else
         for (int r = 0; r < m; r++)
             for (int j = 0; j < n; j++) {
                 float s = 0.0f;
@@ -136,6 +166,7 @@ void orc_mlp_backward(const float* params, const int* sizes, const int* acts, in
                 for (int k = 0; k < m; k++) s += layer_grad[(size_t)k * l + a] * x[(size_t)k * n + j];
                 gw[(size_t)a * n + j] = s;
             }
+#endif
         free(layer_grad);
         layer_grad = gx;
         /* neural_network.cu:224-226 */
@@ -551,3 +582,16 @@ void orc_eval(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int c
     *R_out = rewards / n_episodes;
     *episodes_out = n_episodes;
 }
+
+/* [EXT] The Pendulum above behind the reference's Env hook signatures (include/env.h:7-15), so the UNMODIFIED reference
+ * (oracle/_ref) can be driven through its own train_ppo_epoch on the benchmark's env: bench.py's C1 line and
+ * tests/test_oracle_vs_ref.py.  Same state, same rand() draws at reset as env_id 1 of orc_collect. */
+void orc_pendulum_hook_reset(float* obs) { env_reset(1, obs); }
+void orc_pendulum_hook_step(float* action, float* obs, float* reward, _Bool* terminated, _Bool* truncated, int action_size) {
+    (void)action_size;
+    uint8_t te = 0, tr = 0;
+    env_step(1, action, obs, reward, &te, &tr);
+    *terminated = te != 0;
+    *truncated = tr != 0;
+}
+void orc_pendulum_hook_free(void) {}

@@ -120,6 +120,11 @@ int orc_collect(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int
 void orc_eval(const OrcConfig* cfg, const OrcModel* model, OrcBuffer* buf, int capacity, int steps, int env_id,
               float gamma, float* J_out, float* R_out, int* episodes_out);
 
+/* [EXT] Pendulum behind the reference's Env hooks (include/env.h:7-15): lets the unmodified reference train on it. */
+void orc_pendulum_hook_reset(float* obs);
+void orc_pendulum_hook_step(float* action, float* obs, float* reward, _Bool* terminated, _Bool* truncated, int action_size);
+void orc_pendulum_hook_free(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,7 @@ EXTENSION_API = {
     "ppo_b200_sync": (None, []),
     "ppo_b200_launch_count": (C.c_ulonglong, []),
     "ppo_b200_version": (C.c_char_p, []),
+    "ppo_b200_measure_fp32_peak": (C.c_double, [C.c_int]),
     "ppo_b200_profile_begin": (None, []),
     "ppo_b200_profile_end": (C.c_int, [C.c_char_p, C.c_int]),
     "ppo_b200_debug_phase_stamps": (None, [vp, C.c_int]),

@@ -1,4 +1,4 @@
-"""PPO_B200_PHASE_DEBUG=1 python scratch/phase_debug.py — per-phase globaltimer stamps of fused_tile64_kernel."""
+"""PPO_B200_PHASE_DEBUG=1 python scripts/phase_debug.py — per-phase globaltimer stamps of fused_tile64_kernel."""
 import ctypes as C, os, sys
 os.environ["PPO_B200_PHASE_DEBUG"] = "1"
 sys.path.insert(0, "tests")

@@ -256,6 +256,52 @@ def load_ref():
     return lib
 
 
+REF_BLAS_SO = os.path.join(ROOT, "oracle", "_ref", "libppo_ref_blas.so")
+_OPENBLAS_DIR = os.path.join(os.path.dirname(os.path.dirname(C.__file__)), "site-packages", "opencv_python_headless.libs")
+
+
+def load_openblas():
+    """The OpenBLAS 0.3.15 bundled with the image's opencv wheel (unprefixed cblas_* symbols), RTLD_GLOBAL so that
+    oracle/_ref/libppo_ref_blas.so binds its undefined cblas_sgemm / cblas_sgemv to it.  Returns the handle or None."""
+    import glob
+    import sys
+    dirs = [_OPENBLAS_DIR] + [os.path.join(p, "opencv_python_headless.libs") for p in sys.path if p.endswith("site-packages")]
+    for d in dirs:
+        libs = sorted(glob.glob(os.path.join(d, "libopenblas*.so")))
+        if not libs:
+            continue
+        try:
+            for pat in ("libquadmath*", "libgfortran*"):
+                for f in sorted(glob.glob(os.path.join(d, pat))):
+                    C.CDLL(f, mode=C.RTLD_GLOBAL)
+            h = C.CDLL(libs[0], mode=C.RTLD_GLOBAL)
+            h.openblas_set_num_threads.argtypes = [C.c_int]
+            h.openblas_set_num_threads(1)          # src/main.c:18
+            return h
+        except OSError:
+            continue
+    return None
+
+
+def load_ref_blas():
+    """The unmodified reference linked against a real BLAS (the way its own Makefile:5 links it), or None."""
+    if not os.path.exists(REF_BLAS_SO) or load_openblas() is None:
+        return None
+    lib = C.CDLL(REF_BLAS_SO, mode=C.RTLD_LOCAL)
+    bind(lib, REFERENCE_API)
+    return lib
+
+
+def oracle_pendulum_env(oracle_lib):
+    """An `Env` (include/env.h:7-15) whose hooks are the C Pendulum of oracle/ppo_oracle.c: no Python in the loop."""
+    env = Env()
+    env.free_env = C.cast(oracle_lib.orc_pendulum_hook_free, FREE_FN)
+    env.reset_env = C.cast(oracle_lib.orc_pendulum_hook_reset, RESET_FN)
+    env.step_env = C.cast(oracle_lib.orc_pendulum_hook_step, STEP_FN)
+    env.state_size, env.action_size, env.horizon, env.gamma = 3, 1, 200, 0.99
+    return env
+
+
 def fptr(arr):
     return arr.ctypes.data_as(c_float_p)
 

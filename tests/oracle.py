@@ -47,6 +47,16 @@ def _build():
 _lib = None
 
 
+def use_fast_build():
+    """bench.py's CPU arms only: switch to the timing-only build (`make -C oracle fast`: -O3 -march=native -ffast-math, the
+    GEMM loops in vectorisable axpy order).  Rebuilt on the spot because -march=native must match the host that runs it.
+    The parity tests never call this (they need the -O2 -ffp-contract=off build, bit-exact against the reference)."""
+    global SO, _lib
+    subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "fast"])
+    SO = os.path.join(ROOT, "oracle", "libppo_oracle_fast.so")
+    _lib = None
+
+
 def lib():
     global _lib
     if _lib is None:

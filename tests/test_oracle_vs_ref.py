@@ -57,3 +57,34 @@ def test_whole_path_live(R):
     for k in ["mu", "v", "log_std"]:
         assert np.array_equal(getattr(T, k), res[k]), k
     assert np.array_equal(b["advantage"], res["advantage"])
+
+
+@pytest.mark.parametrize("blas", [False, True], ids=["naive-cblas", "openblas"])
+def test_pendulum_training_live(R, blas):
+    """The unmodified reference's train_ppo_epoch on the C Pendulum (oracle hooks behind include/env.h) against the oracle
+    port, same srand: bit-exact with the sequential-k cblas shim; with the real OpenBLAS (its own summation order) the
+    weights agree to fp32 rounding - this is the reference build bench.py's C1 line times."""
+    import ctypes as C
+    lib = cabi.load_ref_blas() if blas else R.lib
+    if lib is None:
+        pytest.skip("bundled OpenBLAS not loadable")
+    sizes, acts, cap, mb = [3, 64, 64, 1], ["relu", "relu", "none"], 600, 64
+    env = cabi.oracle_pendulum_env(oracle.lib())
+    cabi.srand(9)
+    ppo = lib.create_ppo(cabi.cstr_array(acts), cabi.int_array(sizes), 4, cap, C.c_float(3e-4), C.c_float(3e-4),
+                         C.c_float(0.95), C.c_float(0.2), C.c_float(0.0), C.c_float(1.0), False)
+    lib.train_ppo_epoch(ppo, C.byref(env), cap, mb, 1, 2)
+    after = cabi.rand()
+    import refdrive
+    mu, v = refdrive.Ref.nn_get_params(ppo.contents.policy.contents.mu), refdrive.Ref.nn_get_params(ppo.contents.V)
+    cabi.srand(9)
+    T = oracle.Trainer(sizes, acts, batch_size=mb, n_epochs_policy=1, n_epochs_value=2)
+    b = T.make_buffer(cap)
+    T.collect(b, cap, 1)
+    T.update(b)
+    assert cabi.rand() == after
+    rw = np.ctypeslib.as_array(ppo.contents.buffer.contents.reward_p, shape=(cap,))
+    if blas:
+        assert np.max(np.abs(rw - b["reward"])) < 1e-3 and np.max(np.abs(mu - T.mu)) < 1e-4 and np.max(np.abs(v - T.v)) < 1e-4
+    else:
+        assert np.array_equal(rw, b["reward"]) and np.array_equal(mu, T.mu) and np.array_equal(v, T.v)
