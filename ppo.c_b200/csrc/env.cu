@@ -695,6 +695,226 @@ void launch_sample_action(GaussianPolicy* policy, const float* state, float* act
     B200_LAUNCH(sample_action_kernel, 1, 128, sm, a);
 }
 
+// ================================ persistent sampler for opaque host envs ==============================
+// collect_trajectories with an opaque host env (the reference's hook signature: one env, host pointers, one step at a
+// time, src/ppo.cu:54-79) needs one policy sample per env step.  One kernel launch + stream sync per step costs ~20 us; the
+// reference's default run makes 3000 of them per iteration.  Instead ONE single-CTA kernel stays resident for the whole
+// rollout and talks to the host through a mailbox in mapped pinned memory:
+//   request  words  req[0] = {seq : cmd}, req[1..S] = {seq : state bits}, req[1+S..] = {seq : rand() draw}
+//   response words  resp[0..A-1] = {seq : action bits}, resp[A] = {seq : log-prob bits}
+// Every word is one naturally atomic 64-bit store carrying its own sequence tag (no fences, no separate flag): the
+// device polls its request words with ONE warp-wide system-scope load per PCIe round trip, the host polls its own memory.
+// The weights are staged once per launch in shared memory in the k-major image layout (thread j owns output unit j, the
+// k-loop runs sequentially with separate mul and add = the reference's sequential-k sgemv order, src/mat_mul.cu:28-44).
+// The kernel leaves on a stop request or after `idle_limit` clocks without one (the host relaunches it on demand), so a
+// host that dies mid-rollout never leaves a kernel spinning.
+constexpr int kMailReq = 192, kMailResp = 64;        // 64-bit words
+struct SamplerMailbox { unsigned long long req[kMailReq]; unsigned long long resp[kMailResp]; unsigned long long exit_word; };
+struct HostSamplerArgs {
+    FusedNet net;
+    const float* image;
+    const float* log_std;
+    SamplerMailbox* box;          // mapped pinned host memory
+    int S, A, n_draws;
+    unsigned int first_seq, launch_id;
+    long long idle_limit;
+};
+enum { kSamplerStep = 1, kSamplerStop = 2 };
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128) host_sampler_kernel(const HostSamplerArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const FusedNet& net = p.net;
+    float* img = smem;
+    float* hA = smem + net.img_floats;
+    float* hB = hA + 128;
+    int* draws = reinterpret_cast<int*>(hB + 128);       // 16 ints
+    const int tid = threadIdx.x;
+    for (int i = tid; i < net.img_floats; i += blockDim.x) img[i] = __ldg(p.image + i);
+    __syncthreads();
+    const int n_words = 1 + p.S + p.n_draws;
+    unsigned int seq = p.first_seq;
+    long long idle_since = clock64();
+    for (;;) {
+        // ---- wait for request `seq`
+        bool stop = false;
+        for (;;) {
+            bool ok = true;
+            int cmd = 0;
+            for (int w = tid; w < n_words; w += blockDim.x) {
+                const unsigned long long v = ld_sys_u64(p.box->req + w);
+                if ((unsigned int)(v >> 32) != seq) ok = false;
+                else if (w == 0) cmd = (int)(unsigned int)v;
+                else if (w <= p.S) hA[w - 1] = __uint_as_float((unsigned int)v);
+                else draws[w - 1 - p.S] = (int)(unsigned int)v;
+            }
+            const bool timed_out = tid == 0 && clock64() - idle_since > p.idle_limit;
+            if (__syncthreads_or((tid == 0 && cmd == kSamplerStop) || timed_out)) { stop = true; break; }
+            if (__syncthreads_and(ok)) break;
+        }
+        if (stop) break;
+        // ---- mu = net(state): thread j = output unit j
+        float* hin = hA;
+        float* hout = hB;
+        for (int l = 0; l < net.L; l++) {
+            const int n = net.sizes[l], o = net.sizes[l + 1];
+            if (tid < o) {
+                const float* wt = img + net.wt_off[l] + tid;
+                float acc = 0.f;
+                for (int k = 0; k < n; k++) acc = __fadd_rn(acc, __fmul_rn(hin[k], wt[k * net.ldw[l]]));
+                hout[tid] = act_apply(__fadd_rn(acc, img[net.bs_off[l] + tid]), net.acts[l]);
+            }
+            __syncthreads();
+            float* tmp = hin; hin = hout; hout = tmp;
+        }
+        if (tid == 0) {
+            // generate_gaussian_noise (src/policy.cu:46-65, loop bound corrected for n >= 6) from the host's rand() draws
+            const int A = p.A;
+            const float rmax = 2147483647.f;
+            float act[32];
+            for (int j = 0; j < A; j++) {
+                float z;
+                if (A == 1 || ((A & 1) && j == A - 1)) {
+                    const int base = (A == 1) ? 0 : (A - 1);
+                    const float u1 = __fdiv_rn((float)draws[base], rmax);
+                    const double th = 2 * kPiD * (double)(float)draws[base + 1] / 2147483647.0;
+                    z = sqrtf(-2.f * logf(u1)) * cosf((float)th);
+                } else {
+                    const int pair = j >> 1;
+                    const float u1 = __fdiv_rn((float)draws[2 * pair], rmax), u2 = __fdiv_rn((float)draws[2 * pair + 1], rmax);
+                    const float r = sqrtf(-2.f * logf(u1));
+                    const float theta = (float)(2 * kPiD * (double)u2);
+                    z = (j & 1) ? r * sinf(theta) : r * cosf(theta);
+                }
+                act[j] = hin[j] + z * expf(p.log_std[j]);           // src/policy.cu:85
+            }
+            const float lp = log_prob_dev(hin, p.log_std, act, A);
+            const unsigned long long tag = (unsigned long long)seq << 32;
+            for (int j = 0; j < A; j++) st_sys_u64(p.box->resp + j, tag | __float_as_uint(act[j]));
+            st_sys_u64(p.box->resp + A, tag | __float_as_uint(lp));
+            idle_since = clock64();
+        }
+        __syncthreads();        // hA / draws are rewritten by the next poll
+        ++seq;
+    }
+    if (tid == 0) st_sys_u64(&p.box->exit_word, ((unsigned long long)p.launch_id << 32) | seq);
+}
+
+struct HostSampler {
+    SamplerMailbox* box = nullptr;
+    unsigned int seq = 0, launch_id = 0;
+    bool running = false;
+    GaussianPolicy* policy = nullptr;
+};
+static HostSampler g_sampler;
+
+static bool sampler_enabled() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("PPO_B200_MAILBOX"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
+
+static void sampler_launch(GaussianPolicy* policy, int n_draws, unsigned int first_seq) {
+    HostSamplerArgs a{};
+    const float* image = nullptr;
+    if (!fused_image64(policy->mu, &a.net, &image)) B200_FATAL("host sampler on an unsupported net");
+    a.image = image;
+    a.log_std = policy->d_log_std;
+    a.box = g_sampler.box;
+    a.S = policy->state_size; a.A = policy->action_size; a.n_draws = n_draws;
+    a.first_seq = first_seq;
+    a.launch_id = ++g_sampler.launch_id;
+    a.idle_limit = 100000000ll;       // ~50 ms at 1.9 GHz
+    const size_t smem = (size_t)(a.net.img_floats + 256 + 16) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(host_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    B200_LAUNCH(host_sampler_kernel, 1, 128, smem, a);
+    g_sampler.running = true;
+    g_sampler.policy = policy;
+}
+
+// true when this policy / env shape can use the mailbox kernel
+bool host_sampler_supported(GaussianPolicy* policy) {
+    if (!sampler_enabled()) return false;
+    FusedNet net;
+    const float* image;
+    const int S = policy->state_size, A = policy->action_size;
+    if (S > 128 || A > 8 || 1 + S + 16 > kMailReq) return false;
+    return fused_image64(policy->mu, &net, &image);
+}
+
+static bool sampler_exited() {
+    const unsigned long long w = __atomic_load_n(&g_sampler.box->exit_word, __ATOMIC_ACQUIRE);
+    return (unsigned int)(w >> 32) == g_sampler.launch_id;
+}
+
+// One policy sample through the mailbox: state[S] (host) -> action[A], *logprob (host).
+void host_sampler_step(GaussianPolicy* policy, const float* state, float* action, float* logprob, const int* draws, int n_draws) {
+    HostSampler& hs = g_sampler;
+    if (!hs.box) {
+        hs.box = hmalloc_pinned<SamplerMailbox>(1);
+        memset(hs.box, 0, sizeof(SamplerMailbox));
+    }
+    const int S = policy->state_size, A = policy->action_size;
+    const unsigned int seq = ++hs.seq;
+    if (seq == 0) B200_FATAL("host sampler sequence wrapped");
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    for (int k = 0; k < S; k++) {
+        unsigned int bits;
+        memcpy(&bits, state + k, 4);
+        __atomic_store_n(&hs.box->req[1 + k], tag | bits, __ATOMIC_RELAXED);
+    }
+    for (int d = 0; d < n_draws; d++) __atomic_store_n(&hs.box->req[1 + S + d], tag | (unsigned int)draws[d], __ATOMIC_RELAXED);
+    __atomic_store_n(&hs.box->req[0], tag | (unsigned long long)kSamplerStep, __ATOMIC_RELEASE);
+    if (hs.running && (hs.policy != policy || sampler_exited())) hs.running = false;
+    if (!hs.running) sampler_launch(policy, n_draws, seq);
+    // wait for the response; relaunch if the kernel idled out in between
+    long long spins = 0;
+    for (;;) {
+        bool ok = true;
+        for (int j = 0; j <= A && ok; j++)
+            ok = (unsigned int)(__atomic_load_n(&hs.box->resp[j], __ATOMIC_ACQUIRE) >> 32) == seq;
+        if (ok) break;
+        if ((++spins & 0x3ff) == 0) {
+            if (sampler_exited()) { hs.running = false; sampler_launch(policy, n_draws, seq); }
+            if (spins > (1ll << 34)) B200_FATAL("host sampler: no response from the device");
+            const cudaError_t err = cudaStreamQuery(stream());
+            if (err != cudaSuccess && err != cudaErrorNotReady) B200_FATAL("host sampler kernel failed: %s", cudaGetErrorString(err));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    for (int j = 0; j < A; j++) {
+        const unsigned int bits = (unsigned int)hs.box->resp[j];
+        memcpy(action + j, &bits, 4);
+    }
+    const unsigned int lb = (unsigned int)hs.box->resp[A];
+    memcpy(logprob, &lb, 4);
+}
+
+// End of a rollout: tell the resident kernel to leave (it would also leave by itself after the idle limit).
+void host_sampler_stop() {
+    HostSampler& hs = g_sampler;
+    if (!hs.box || !hs.running) return;
+    if (!sampler_exited()) {
+        const unsigned int seq = ++hs.seq;
+        __atomic_store_n(&hs.box->req[0], ((unsigned long long)seq << 32) | (unsigned long long)kSamplerStop, __ATOMIC_RELEASE);
+    }
+    hs.running = false;
+}
+
 __global__ void pendulum_step_kernel(double* theta, double* theta_dot, const float* action, float* obs, float* reward, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

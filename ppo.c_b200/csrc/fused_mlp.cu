@@ -497,6 +497,71 @@ __device__ __forceinline__ void t64_loss_head(const HeadCtx& c, float* __restric
     }
 }
 
+// ---- single-output nets (value head; Pendulum's action mean): last layer + loss head + dX of the last layer in ONE pass.
+// Four threads per row (lane = (row % 8) * 4 + q, q = interleaved quarter of k):
+//   y_r = sum_k H[k][r] w[k] + b  (quarters meet through two shuffles)  ->  loss head on y_r (all four threads, redundantly)
+//   ->  g_r = dLoss/dy_r through the output activation  ->  Yt[0][r] = g_r (dW / db of this layer read it afterwards)
+//   ->  Gout[k][r] = g_r * w[k] * act'(H[k][r])  for the thread's own k's (the dX tile the next backward layer consumes).
+// Replaces: skinny forward (smem exchange + barrier) -> head on 64 threads (+ barrier) -> a 64x64-tile dX with one live row.
+// Contains one tile_sync.
+__device__ __forceinline__ void t64_head_fused1(const HeadCtx& c, const float* __restrict__ H, const float* __restrict__ Wt, int ldw,
+                                                const float* __restrict__ bias, float* __restrict__ Yt, float* __restrict__ Gout,
+                                                float* __restrict__ red, float* __restrict__ slab, int n_in, int act_prev, int tid, int bar,
+                                                bool row_valid, float h_target, float h_adv, float h_lp_old, float h_act0, bool accum) {
+    constexpr int TMP = kT64TMP;
+    const int r = tid >> 2, q = tid & 3;
+    float part = 0.f;
+    for (int k = q; k < n_in; k += 4) part = fmaf(H[k * TMP + r], Wt[k * ldw], part);
+    part += __shfl_xor_sync(kFull, part, 1);
+    part += __shfl_xor_sync(kFull, part, 2);
+    const float y = act_apply(part + bias[0], c.out_act);
+    float loss_term = 0.f, gout = 0.f, gls = 0.f;
+    if (row_valid) {
+        if (c.mode == kFusedValue) {            // src/loss.cu:5-23
+            gout = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(y, h_target)), (float)c.m_total);
+            const float d = __fsub_rn(h_target, y);
+            loss_term = __fmul_rn(d, d);
+        } else {                                // src/policy.cu:67-111 + src/ppo.cu:89-98
+            const float ls = __ldcg(c.log_std);
+            const float lp = fused_log_prob(&y, &ls, &h_act0, 1);
+            const float ratio = expf(__fsub_rn(lp, h_lp_old));
+            const bool adv_pos = h_adv > 0.f;
+            const bool hi = ratio > 1.f + c.epsilon, lo = ratio < 1.f - c.epsilon;
+            const float sel = adv_pos ? (hi ? 1.f + c.epsilon : ratio) : (lo ? 1.f - c.epsilon : ratio);
+            loss_term = __fmul_rn(h_adv, sel);
+            const int keep = adv_pos ? !hi : !lo;
+            const float g = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)c.m_total);
+            const float e2 = expf(-2.f * ls);
+            const float diff = __fsub_rn(h_act0, y);
+            gout = __fmul_rn(__fmul_rn(diff, e2), g);
+            gls = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), g);
+        }
+    }
+    const float g = act_grad(y, gout, c.out_act);
+    if (q == 0) Yt[r] = g;
+    for (int k = q; k < pad4(n_in); k += 4)
+        Gout[k * TMP + r] = (k < n_in) ? act_grad(H[k * TMP + r], __fmul_rn(g, Wt[k * ldw]), act_prev) : 0.f;
+    {   // tile sums of the loss term / log_std gradient: one contribution per row (q == 0), warps in fixed order
+        const int warp = tid >> 5, lane = tid & 31;
+        const float v = warp_sum(q == 0 ? loss_term : 0.f);
+        if (lane == 0) red[warp] = v;
+        if (c.mode == kFusedPolicy) { const float s2 = warp_sum(q == 0 ? gls : 0.f); if (lane == 0) red[8 + warp] = s2; }
+    }
+    tile_sync(bar);
+    if (tid == 0) {
+        float v = red[0];
+#pragma unroll
+        for (int w = 1; w < 8; w++) v += red[w];
+        slab[c.P + 1] = accum ? slab[c.P + 1] + v : v;
+    }
+    if (c.mode == kFusedPolicy && tid == 32) {
+        float v = red[8];
+#pragma unroll
+        for (int w = 1; w < 8; w++) v += red[8 + w];
+        slab[c.P] = accum ? slab[c.P] + v : v;
+    }
+}
+
 __global__ void __launch_bounds__(kT64Threads, 2) fused_tile64_kernel(const FusedArgs p) {
     constexpr int TM = kT64TM, TMP = kT64TMP;
     extern __shared__ __align__(128) float smem[];
@@ -799,6 +864,11 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 
 // All threads of all CTAs call it the same number of times (cooperative launch: every CTA is resident).
 __device__ __forceinline__ void phase_grid_barrier(unsigned int* counter, unsigned int target, long long spin_limit) {
+    if (gridDim.x == 1) {            // one CTA (small minibatches): a block barrier is the grid barrier
+        __threadfence();
+        __syncthreads();
+        return;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();                                   // release the writes of this CTA (ordered by the bar.sync above)
@@ -846,6 +916,9 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
     HeadCtx hc;
     hc.mode = p.mode; hc.m_total = p.m_total; hc.OUT = OUT; hc.P = net.P; hc.out_act = net.acts[net.L - 1];
     hc.log_std = p.log_std; hc.epsilon = p.epsilon;
+    const bool head1 = OUT == 1 && net.L >= 2;            // single-output nets: fused last layer + head + dX (t64_head_fused1)
+    const int hrow = head1 ? (tid >> 2) : tid;            // the row whose per-row scalars this thread holds
+    const bool hholds = head1 || tid < TM;
 
     // source row of buffer for row r of tile t at step s (src/trajectory_buffer.cu:208-209)
     auto src_of = [&](int s, int t, int r) -> int {
@@ -868,8 +941,8 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             if (src >= 0 && k < S) cp_async4(dst, p.state + (size_t)src * S + k);
             else *dst = 0.f;
         }
-        if (tid < TM) {
-            my_src = src_rows[tid];
+        if (hholds) {
+            my_src = src_rows[hrow];
             h_target = 0.f; h_adv = 0.f; h_lp_old = 0.f;
             if (my_src >= 0) {
                 if (p.mode == kFusedValue) {
@@ -920,7 +993,8 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             const bool have_next = ns < p.n_steps;
             if (have_next && tid < TM) nxt_src = src_of(ns, nt, tid);     // in flight during the tile
             if (p.dbg && tid == 0 && sub == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 3] = t; }
-            for (int l = 0; l < net.L; l++) {
+            const int n_fwd = head1 ? net.L - 1 : net.L;
+            for (int l = 0; l < n_fwd; l++) {
                 const float* Xt = act0 + net.a_off[l];
                 float* Yt = act0 + net.a_off[l + 1];
                 if (net.sizes[l + 1] <= 8)
@@ -933,20 +1007,27 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
                 tile_sync(bar);
             }
             float* Yt = act0 + net.a_off[net.L];
-            t64_loss_head(hc, Yt, red, slab, tid, bar, my_src >= 0, h_target, h_adv, h_lp_old, h_act, accum);
+            if (head1) {
+                const int lh = net.L - 1;
+                t64_head_fused1(hc, act0 + net.a_off[lh], img + net.wt_off[lh], net.ldw[lh], img + net.bs_off[lh], Yt, ebuf, red, slab,
+                                net.sizes[lh], net.acts[lh - 1], tid, bar, my_src >= 0, h_target, h_adv, h_lp_old, h_act[0], accum);
+            } else {
+                t64_loss_head(hc, Yt, red, slab, tid, bar, my_src >= 0, h_target, h_adv, h_lp_old, h_act, accum);
+            }
             const float* G = Yt;
             for (int l = net.L - 1; l >= 0; l--) {
                 const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
                 const float* Xt = act0 + net.a_off[l];
                 float* Gout = ebuf + ((net.L - 1 - l) & 1) * (net.max_width_pad * TMP);
+                const bool dx_done = head1 && l == net.L - 1;      // the fused head already wrote this layer's dX into E0
                 if (grp == 0) {
                     t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt, accum);
                     t64_bias_grad(G, slab + net.b_off[l], n_out, lt, accum);
-                } else if (l > 0) {
+                } else if (l > 0 && !dx_done) {
                     for (int kb = 0; kb < pad4(n_in); kb += 64)
                         t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt, kb);
                 }
-                tile_sync(bar);                            // (also after l == 0: Xt0 / src_rows are about to be refilled)
+                if (!dx_done) tile_sync(bar);              // (also after l == 0: Xt0 / src_rows are about to be refilled)
                 G = Gout;
             }
             if (have_next) {
@@ -968,24 +1049,100 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             const int e0 = blockIdx.x * chunk, e1 = min(total, e0 + chunk);
             const int ngroups = e1 > e0 ? (e1 - e0 + 31) >> 5 : 0;
             const int W = blockDim.x >> 5;
-            int ways = 1;
-            while (ways * 2 * max(ngroups, 1) <= W) ways *= 2;
-            const int gpr = W / ways;                      // 32-element groups handled per round
-            const int per = (nslabs + ways - 1) / ways;
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             const float4 cf = __ldg(p.coef + s);
-            for (int g0 = 0; g0 < ngroups; g0 += gpr) {
-                const int gi = g0 + warp / ways, part = warp % ways;
+            const bool single = gridDim.x == 1;
+            // optimiser state of element e (only ever touched by the thread that owns e, in every step)
+            auto load_state = [&](int e, float& pm, float& pv, float& pw) {
+                pm = 0.f; pv = 0.f; pw = 0.f;
+                if (e < p.P) { pm = p.netseg.m[e]; pv = p.netseg.v[e]; pw = p.netseg.w[e]; }
+                else if (e < p.P + p.A) { if (p.mode == kFusedPolicy) { pm = p.ls.m[e - p.P]; pv = p.ls.v[e - p.P]; pw = p.ls.w[e - p.P]; } }
+                else if (p.mode == kFusedPolicy) pw = s_entropy;
+            };
+            // local sum g of element e -> (cross-GPU sum) -> Adam / loss accumulation
+            auto finalize = [&](int e, float g, float pm, float pv, float pw) {
+                if (p.peer.ready) {
+                    // gradient exchange over NVLink peer memory (dist.cu "peer arena"): push {tag, value}, poll, ordered sum
+                    const PeerView& pvw = p.peer;
+                    const unsigned int epoch = pvw.epoch + (unsigned int)s;
+                    const size_t poff = (size_t)(epoch & 1u) * pvw.parity_stride;
+                    const unsigned long long packed = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(g);
+                    for (int r = 0; r < pvw.world; r++)
+                        if (r != pvw.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(pvw.peer_recv[r] + poff + e), "l"(packed) : "memory");
+                    const long long tstart = clock64();
+                    float acc = 0.f;
+                    for (int r = 0; r < pvw.world; r++) {
+                        float x = g;
+                        if (r != pvw.rank) {
+                            const unsigned long long* srcw = pvw.my_recv + poff + (size_t)r * kPeerCap + e;
+                            unsigned long long w;
+                            do {
+                                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(srcw) : "memory");
+                                if ((unsigned int)(w >> 32) != epoch && clock64() - tstart > p.spin_limit) {
+                                    printf("ppo_b200: peer exchange timed out (rank %d waiting for rank %d, exchange %u)\n", pvw.rank, r, epoch);
+                                    __trap();
+                                }
+                            } while ((unsigned int)(w >> 32) != epoch);
+                            x = __uint_as_float((unsigned int)w);
+                        }
+                        acc += x;                      // same numbers, same (rank) order on every GPU
+                    }
+                    g = acc;
+                }
+                if (e < p.P) {
+                    AdamSeg sg = p.netseg;
+                    sg.step_size = cf.x; sg.bc2 = cf.y;
+                    const float w = adam_apply(sg, e, g, pm, pv, pw);
+                    const int ii = image_index(p.net, e);
+                    if (ii >= 0) {
+                        p.image[ii] = w;
+                        if (single) img[ii] = w;       // one CTA: the staged image is refreshed in place, no re-stage
+                    }
+                } else if (e < p.P + p.A) {
+                    if (p.mode == kFusedPolicy) {
+                        AdamSeg sg = p.ls;
+                        sg.step_size = cf.z; sg.bc2 = cf.w;
+                        adam_apply(sg, e - p.P, g + (-p.ent_coeff), pm, pv, pw);     // src/ppo.cu:436-438
+                    }
+                } else {
+                    if (p.mode == kFusedValue) *p.loss_slot += g / (float)p.m_total;
+                    else *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
+                }
+            };
+            if (ngroups >= W) {
+                // few CTAs, many elements each (small minibatches): one thread per element, four elements in flight
+                for (int base = e0 + (int)threadIdx.x; base < e1; base += 4 * (int)blockDim.x) {
+                    float g[4], pm[4], pv[4], pw[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = base + u * (int)blockDim.x;
+                        g[u] = 0.f;
+                        if (e < e1) load_state(e, pm[u], pv[u], pw[u]);
+                    }
+                    for (int b = 0; b < nslabs; b++) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int e = base + u * (int)blockDim.x;
+                            if (e < e1) g[u] += __ldcg(p.partials + (size_t)b * p.slab + e);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = base + u * (int)blockDim.x;
+                        if (e < e1) finalize(e, g[u], pm[u], pv[u], pw[u]);
+                    }
+                }
+            } else {
+                // many CTAs, <= W 32-element groups each: the warps split the slabs, fixed-order combine through shared memory
+                int ways = 1;
+                while (ways * 2 * max(ngroups, 1) <= W) ways *= 2;
+                const int per = (nslabs + ways - 1) / ways;
+                const int gi = warp / ways, part = warp % ways;
                 const int e = e0 + gi * 32 + lane;
                 const bool live = gi < ngroups && e < e1;
                 const bool fin = live && part == 0;
-                const bool is_net = e < p.P, is_ls = !is_net && e < p.P + p.A && p.mode == kFusedPolicy;
                 float pm = 0.f, pv = 0.f, pw = 0.f;
-                if (fin) {      // optimiser state of this element (only ever touched by this thread): overlaps the slab loads
-                    if (is_net) { pm = p.netseg.m[e]; pv = p.netseg.v[e]; pw = p.netseg.w[e]; }
-                    else if (is_ls) { pm = p.ls.m[e - p.P]; pv = p.ls.v[e - p.P]; pw = p.ls.w[e - p.P]; }
-                    else if (e == p.P + p.A && p.mode == kFusedPolicy) pw = s_entropy;
-                }
+                if (fin) load_state(e, pm, pv, pw);        // overlaps the slab loads
                 float sum = 0.f;
                 if (live) {
                     const int b0 = part * per, b1 = min(nslabs, b0 + per);
@@ -1012,52 +1169,8 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
                 if (fin) {
                     float g = redw[warp][lane];
                     for (int q = 1; q < ways; q++) g += redw[warp + q][lane];
-                    if (p.peer.ready) {
-                        // gradient exchange over NVLink peer memory (dist.cu "peer arena"): push {tag, value}, poll, ordered sum
-                        const PeerView& pvw = p.peer;
-                        const unsigned int epoch = pvw.epoch + (unsigned int)s;
-                        const size_t poff = (size_t)(epoch & 1u) * pvw.parity_stride;
-                        const unsigned long long packed = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(g);
-                        for (int r = 0; r < pvw.world; r++)
-                            if (r != pvw.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(pvw.peer_recv[r] + poff + e), "l"(packed) : "memory");
-                        const long long tstart = clock64();
-                        float acc = 0.f;
-                        for (int r = 0; r < pvw.world; r++) {
-                            float x = g;
-                            if (r != pvw.rank) {
-                                const unsigned long long* srcw = pvw.my_recv + poff + (size_t)r * kPeerCap + e;
-                                unsigned long long w;
-                                do {
-                                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(srcw) : "memory");
-                                    if ((unsigned int)(w >> 32) != epoch && clock64() - tstart > p.spin_limit) {
-                                        printf("ppo_b200: peer exchange timed out (rank %d waiting for rank %d, exchange %u)\n", pvw.rank, r, epoch);
-                                        __trap();
-                                    }
-                                } while ((unsigned int)(w >> 32) != epoch);
-                                x = __uint_as_float((unsigned int)w);
-                            }
-                            acc += x;                      // same numbers, same (rank) order on every GPU
-                        }
-                        g = acc;
-                    }
-                    if (is_net) {
-                        AdamSeg sg = p.netseg;
-                        sg.step_size = cf.x; sg.bc2 = cf.y;
-                        const float w = adam_apply(sg, e, g, pm, pv, pw);
-                        const int ii = image_index(p.net, e);
-                        if (ii >= 0) p.image[ii] = w;
-                    } else if (e < p.P + p.A) {
-                        if (is_ls) {
-                            AdamSeg sg = p.ls;
-                            sg.step_size = cf.z; sg.bc2 = cf.w;
-                            adam_apply(sg, e - p.P, g + (-p.ent_coeff), pm, pv, pw);     // src/ppo.cu:436-438
-                        }
-                    } else {
-                        if (p.mode == kFusedValue) *p.loss_slot += g / (float)p.m_total;
-                        else *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
-                    }
+                    finalize(e, g, pm, pv, pw);
                 }
-                __syncthreads();
             }
         }
         if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 6] = t; }
@@ -1065,13 +1178,15 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             // ---- [D] every slice of the new weights is in the global image; [E] re-stage it
             ++bar_gen;
             phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
-            if (threadIdx.x == 0) {
-                asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this TMA (async proxy) read
-                mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
-                tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+            if (gridDim.x > 1) {
+                if (threadIdx.x == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> this TMA (async proxy) read
+                    mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+                    tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+                }
+                mbar_wait(mbar, img_parity);
+                img_parity ^= 1;
             }
-            mbar_wait(mbar, img_parity);
-            img_parity ^= 1;
             if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 7] = t; }
         }
     }

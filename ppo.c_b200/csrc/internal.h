@@ -170,6 +170,10 @@ void device_rollout(DeviceEnv* e, GaussianPolicy* policy, TrajectoryBuffer* buff
                     const float* obs_mean, const float* obs_inv_std, float* return_stats /* dev: sum, episodes */);
 void device_env_reset_obs_norm(DeviceEnv* e);
 void device_env_set_obs_norm(bool enabled);
+// persistent mailbox sampler for opaque host envs (env.cu)
+bool host_sampler_supported(GaussianPolicy* policy);
+void host_sampler_step(GaussianPolicy* policy, const float* state, float* action, float* logprob, const int* draws, int n_draws);
+void host_sampler_stop();
 void launch_sample_action(GaussianPolicy* policy, const float* state_hostmapped, float* action_hostmapped,
                           float* logprob_hostmapped, const int* rand_draws, int n_draws);
 

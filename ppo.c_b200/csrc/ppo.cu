@@ -415,6 +415,7 @@ void collect_trajectories(TrajectoryBuffer* buffer, Env* env, GaussianPolicy* po
     // The active pointer set must be the host one (it is after create / buffer_to_host / reset).
     if (buffer->state_p != buffer->h_state_p) buffer_to_host(buffer);
     const int S = buffer->state_size, A = buffer->action_size;
+    const bool mailbox = host_sampler_supported(policy);      // resident sampler kernel instead of a launch + sync per step
     env->reset_env(buffer->state(buffer, buffer->idx));
     for (int i = 0; i < steps; i++) {
         const int idx = buffer->idx;
@@ -426,9 +427,14 @@ void collect_trajectories(TrajectoryBuffer* buffer, Env* env, GaussianPolicy* po
             for (int q = 0; q + 1 < A; q += 2) { draws[nd++] = rand(); draws[nd++] = rand(); }
             if (A & 1) { draws[nd++] = rand(); draws[nd++] = rand(); }
         }
-        launch_sample_action(policy, buffer->h_state_p + (size_t)idx * S, buffer->h_action_p + (size_t)idx * A,
-                             buffer->h_logprob_p + idx, draws, nd);
-        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (mailbox) {
+            host_sampler_step(policy, buffer->h_state_p + (size_t)idx * S, buffer->h_action_p + (size_t)idx * A,
+                              buffer->h_logprob_p + idx, draws, nd);
+        } else {
+            launch_sample_action(policy, buffer->h_state_p + (size_t)idx * S, buffer->h_action_p + (size_t)idx * A,
+                                 buffer->h_logprob_p + idx, draws, nd);
+            CUDA_CHECK(cudaStreamSynchronize(stream()));
+        }
         env->step_env(buffer->action(buffer, idx), buffer->next_state(buffer, idx), buffer->reward(buffer, idx),
                       buffer->terminated(buffer, idx), buffer->truncated(buffer, idx), buffer->action_size);
         const int new_idx = (idx + 1) % buffer->capacity;
@@ -441,6 +447,7 @@ void collect_trajectories(TrajectoryBuffer* buffer, Env* env, GaussianPolicy* po
         buffer->idx = new_idx;
         buffer->full = buffer->full || buffer->idx == 0;
     }
+    if (mailbox) host_sampler_stop();
 }
 
 void compute_gae_cuda(NeuralNetwork* V, TrajectoryBuffer* buffer, float gamma, float lambda, int horizon) {
