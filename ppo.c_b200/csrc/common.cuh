@@ -151,9 +151,24 @@ inline int act_code(const char* name) {
     if (name && strcmp(name, "tanh") == 0) return kActTanh;
     return kActNone;  // src/activation_function.cu:49-55: anything else is the identity
 }
+// tanh in ~14 branch-free instructions, two of them MUFU (libdevice tanhf is ~50 with a divergent branch; at 2x64 the 64x64
+// tanh epilogues were costing more issue slots than the K=3 layer they follow):
+//   |x| >= 1/16: 1 - 2 / (e^{2|x|} + 1)  with ex2.approx / rcp.approx: absolute error <= ~1.5e-7, i.e. <= 2.4e-6 relative
+//   |x| <  1/16: x (1 - x^2/3 + 2 x^4/15)                              : relative error < 4e-9 (next term 17 x^6 / 315)
+// [EXT] tanh has no counterpart in the reference (src/activation_function.cu:46-58); the oracle's is glibc tanhf.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float ax = fabsf(x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.88539008177792681f));      // e^{2|x|}
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    const float big = copysignf(fmaf(-2.0f, r, 1.0f), x);
+    const float x2 = x * x;
+    const float small = x * fmaf(x2, fmaf(x2, 0.13333333333f, -0.33333333333f), 1.0f);
+    return ax < 0.0625f ? small : big;
+}
 __device__ __forceinline__ float act_apply(float x, int act) {
     if (act == kActRelu) return x > 0.f ? x : 0.f;
-    if (act == kActTanh) return tanhf(x);
+    if (act == kActTanh) return tanh_fast(x);
     return x;
 }
 // derivative expressed through the POST-activation value y (src/activation_function.cu:11-15)

@@ -962,6 +962,13 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
         mbar_init(mbar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    auto stamp = [&](int slot) {      // PPO_B200_PHASE_DEBUG: globaltimer of tile slot 0, last item wins
+        if (p.dbg && sub == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            p.dbg[(size_t)blockIdx.x * 16 + slot] = t;
+        }
+    };
     int nxt_src = -1;
     if (rounds > 0) {
         if (tid < TM) src_rows[tid] = src_of(0, t0, tid);
@@ -978,11 +985,6 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
     img_parity ^= 1;
 
     for (int s = 0; s < p.n_steps; s++) {
-        if (threadIdx.x == 0 && p.mode == kFusedPolicy) {     // log_std is stable here: last written in [C] of step s-1, before [D]
-            float ent = (float)(p.A * 0.5 * (1 + log(2 * kPiF)));             // src/policy.cu:171-178
-            for (int j = 0; j < p.A; j++) ent += __ldcg(p.log_std + j);
-            s_entropy = ent;                                   // read by the owner of the loss element after barrier [B]
-        }
         // ---- [A] this slot's tiles of minibatch s
         for (int rd = 0; rd < rounds; rd++) {
             const bool accum = rd > 0;
@@ -992,7 +994,7 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             if (rd + 1 >= rounds) { ns = s + 1; nt = t0; }
             const bool have_next = ns < p.n_steps;
             if (have_next && tid < TM) nxt_src = src_of(ns, nt, tid);     // in flight during the tile
-            if (p.dbg && tid == 0 && sub == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 3] = t; }
+            stamp(3);
             const int n_fwd = head1 ? net.L - 1 : net.L;
             for (int l = 0; l < n_fwd; l++) {
                 const float* Xt = act0 + net.a_off[l];
@@ -1005,6 +1007,7 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
                         t64_forward(Xt, img + net.wt_off[l], net.ldw[l], img + net.bs_off[l], Yt, ebuf, net.sizes[l], net.sizes[l + 1], net.acts[l], lt, grp, cb, bar);
                     }
                 tile_sync(bar);
+                stamp(8 + l);
             }
             float* Yt = act0 + net.a_off[net.L];
             if (head1) {
@@ -1014,20 +1017,29 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             } else {
                 t64_loss_head(hc, Yt, red, slab, tid, bar, my_src >= 0, h_target, h_adv, h_lp_old, h_act, accum);
             }
+            stamp(11);
             const float* G = Yt;
             for (int l = net.L - 1; l >= 0; l--) {
                 const int n_in = net.sizes[l], n_out = net.sizes[l + 1];
                 const float* Xt = act0 + net.a_off[l];
                 float* Gout = ebuf + ((net.L - 1 - l) & 1) * (net.max_width_pad * TMP);
                 const bool dx_done = head1 && l == net.L - 1;      // the fused head already wrote this layer's dX into E0
-                if (grp == 0) {
+                if (dx_done) {
+                    // nothing left for the dX group at this layer: it takes the (small) dW / db of the last layer and then goes
+                    // straight on to dX of the layer below, while the dW group starts on that layer's dW: balanced halves
+                    if (grp == 1) {
+                        t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt, accum);
+                        t64_bias_grad(G, slab + net.b_off[l], n_out, lt, accum);
+                    }
+                } else if (grp == 0) {
                     t64_weights_dispatch(G, Xt, slab + net.w_off[l], n_in, n_out, lt, accum);
                     t64_bias_grad(G, slab + net.b_off[l], n_out, lt, accum);
-                } else if (l > 0 && !dx_done) {
+                } else if (l > 0) {
                     for (int kb = 0; kb < pad4(n_in); kb += 64)
                         t64_backward_input(G, img + net.wt_off[l], net.ldw[l], Xt, Gout, n_in, n_out, net.acts[l - 1], lt, kb);
                 }
                 if (!dx_done) tile_sync(bar);              // (also after l == 0: Xt0 / src_rows are about to be refilled)
+                if (l < 3) stamp(12 + l);
                 G = Gout;
             }
             if (have_next) {
@@ -1037,6 +1049,11 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
             }
         }
         if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 4] = t; }
+        if (threadIdx.x == 33 && p.mode == kFusedPolicy) {    // log_std is stable here: last written in [C] of step s-1, before [D]
+            float ent = (float)(p.A * 0.5 * (1 + log(2 * kPiF)));             // src/policy.cu:171-178
+            for (int j = 0; j < p.A; j++) ent += __ldcg(p.log_std + j);
+            s_entropy = ent;                                   // read by the owner of the loss element after barrier [B]
+        }
         // ---- [B] every slab of minibatch s is written
         ++bar_gen;
         phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
@@ -1147,22 +1164,15 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
                 if (live) {
                     const int b0 = part * per, b1 = min(nslabs, b0 + per);
                     const float* src = p.partials + e;
-                    int b = b0;
-                    for (; b + 16 <= b1; b += 16) {
-                        float t[16];
+                    // up to 24 independent L2 loads in flight per lane (296 slabs / 16 warps = 19: ONE round trip), summed in slab order
+                    for (int b = b0; b < b1; b += 24) {
+                        const int cnt = min(24, b1 - b);
+                        float t[24];
 #pragma unroll
-                        for (int u = 0; u < 16; u++) t[u] = __ldcg(src + (size_t)(b + u) * p.slab);
+                        for (int u = 0; u < 24; u++) t[u] = (u < cnt) ? __ldcg(src + (size_t)(b + u) * p.slab) : 0.f;
 #pragma unroll
-                        for (int u = 0; u < 16; u++) sum += t[u];
+                        for (int u = 0; u < 24; u++) sum += t[u];
                     }
-                    for (; b + 4 <= b1; b += 4) {
-                        float t[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) t[u] = __ldcg(src + (size_t)(b + u) * p.slab);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) sum += t[u];
-                    }
-                    for (; b < b1; b++) sum += __ldcg(src + (size_t)b * p.slab);
                 }
                 redw[warp][lane] = sum;
                 __syncthreads();

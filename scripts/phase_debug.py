@@ -26,4 +26,8 @@ print("CTAs", grid, "minibatch", MB)
 for name, d in [("[E]->tile start (gather wait)", us(3, 7)), ("[A] tiles (fwd+head+bwd)", us(4, 3)), ("[B] grid barrier wait", us(5, 4)),
                 ("[C] slice reduce + Adam", us(6, 5))]:
     print("%-34s median %.2f us  min %.2f  max %.2f" % (name, np.median(d), d.min(), d.max()))
+for name, a, b in [("  fwd L0", 8, 3), ("  fwd L1", 9, 8), ("  last layer + head (+dX)", 11, 9), ("  bwd l=1 (dW | dX)", 13, 11),
+                   ("  bwd l=0", 12, 13), ("  next gather issue -> [A] end", 4, 12)]:
+    d = us(a, b)
+    print("%-34s median %.2f us  min %.2f  max %.2f" % (name, np.median(d), d.min(), d.max()))
 print("step period estimate (t6 last - t7 prev): median %.2f us" % np.median(us(6, 7)))
