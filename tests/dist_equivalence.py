@@ -22,16 +22,16 @@ import oracle
 from test_gpu_train import fill_host_buffer, make_ppo, synthetic_buffer
 
 
-def run_update(L, sizes, acts, n, mb, seed, buf_seed):
+def run_update(L, sizes, acts, n, mb, seed, buf_seed, ent=0.0, npol=2, nval=2):
     cabi.srand(seed)
-    ppo = make_ppo(L, sizes, acts, n)
+    ppo = make_ppo(L, sizes, acts, n, ent=ent)
     T = oracle.Trainer(sizes, acts, batch_size=mb, n_epochs_policy=2, n_epochs_value=2, init=False)
     T.mu[:] = b200.nn_get_params(L, ppo.contents.policy.contents.mu)     # logprob_old from the same initial policy
     b = synthetic_buffer(T, np.random.default_rng(buf_seed), sizes, acts, n)
     fill_host_buffer(ppo, b)
     L.ppo_b200_set_permutation_mode(ppo, 0, 0)
     cabi.srand(seed + 1)
-    L.ppo_b200_update(ppo, 0.99, mb, 2, 2)
+    L.ppo_b200_update(ppo, 0.99, mb, npol, nval)
     after = cabi.rand()
     out = (b200.nn_get_params(L, ppo.contents.V).copy(), b200.nn_get_params(L, ppo.contents.policy.contents.mu).copy(),
            np.ctypeslib.as_array(ppo.contents.policy.contents.log_std, shape=(sizes[-1],)).copy(),
@@ -47,15 +47,17 @@ def main():
     L.ppo_b200_set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for sizes, acts, n, mb in [([3, 64, 64, 1], ["tanh", "tanh", "none"], 4096, 512),        # fused 64-wide kernels
-                               ([17, 256, 256, 6], ["relu", "relu", "none"], 4096, 1024)]:  # layer-wise kernels, A = 6
+    for sizes, acts, n, mb, ent in [([3, 64, 64, 1], ["tanh", "tanh", "none"], 4096, 512, 0.0),        # persistent phase kernel + NVLink peer exchange
+                                    ([3, 64, 64, 1], ["tanh", "tanh", "none"], 4096, 1024, 0.01),      # entropy bonus under DP (src/ppo.cu:436-438)
+                                    ([17, 32, 32, 6], ["relu", "relu", "none"], 4096, 1024, 0.01),     # A = 6, generic loss head
+                                    ([17, 256, 256, 6], ["relu", "relu", "none"], 4096, 1024, 0.01)]:  # layer-wise kernels + NCCL all-reduce
         b200.package().dist_init_from_torch(L)
         L.ppo_b200_dist_set_shard_mode(0)
-        dp = run_update(L, sizes, acts, n, mb, 5, 77)
+        dp = run_update(L, sizes, acts, n, mb, 5, 77, ent)
         L.ppo_b200_dist_set_shard_mode(1)
-        weak = run_update(L, sizes, acts, n, mb // world, 5, 100 + rank)      # different buffer per rank
+        weak = run_update(L, sizes, acts, n, mb // world, 5, 100 + rank, ent)      # different buffer per rank
         L.ppo_b200_dist_finalize()
-        single = run_update(L, sizes, acts, n, mb, 5, 77)
+        single = run_update(L, sizes, acts, n, mb, 5, 77, ent)
         for name, a, s in zip(("V", "mu", "log_std"), dp[:3], single[:3]):
             err = float(np.max(np.abs(a - s)) / max(np.max(np.abs(s)), 1e-30))
             frac = float(np.mean(np.abs(a - s) > 1e-5 * np.max(np.abs(s))))
@@ -68,6 +70,29 @@ def main():
             ref = t.clone()
             dist.broadcast(ref, 0)
             ok &= bool(torch.equal(t, ref))
+    # ---- soak: more than 2^16 consecutive gradient exchanges per net through the {tag, value} parity protocol of the phase
+    # kernel (one 64-row tile per rank and minibatch, tiny buffer, thousands of epochs): the replicas must stay bit-identical
+    # and finite.  DIST_SOAK_EXCHANGES=0 skips it.
+    target = int(os.environ.get("DIST_SOAK_EXCHANGES", "66000"))
+    if target > 0:
+        sizes, acts, n = [3, 64, 64, 1], ["tanh", "tanh", "none"], 1024
+        mb = 64 * world
+        epochs = -(-target // (n // mb))
+        b200.package().dist_init_from_torch(L)
+        L.ppo_b200_dist_set_shard_mode(0)
+        t0 = __import__("time").time()
+        soak = run_update(L, sizes, acts, n, mb, 9, 55, 0.0, npol=epochs, nval=epochs)
+        dt = __import__("time").time() - t0
+        L.ppo_b200_dist_finalize()
+        same = True
+        for a in soak[:3]:
+            t = torch.from_numpy(a.copy()).cuda()
+            ref = t.clone()
+            dist.broadcast(ref, 0)
+            same &= bool(torch.equal(t, ref)) and bool(np.isfinite(a).all())
+        print("rank %d soak: %d exchanges per net (%d epochs x %d minibatches, world %d) in %.1f s, Adam steps %d, replicas identical: %s"
+              % (rank, epochs * (n // mb), epochs, n // mb, world, dt, soak[3], same), flush=True)
+        ok &= same and soak[3] == epochs * (n // mb)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
