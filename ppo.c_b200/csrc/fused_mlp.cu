@@ -885,6 +885,135 @@ __device__ __forceinline__ void phase_grid_barrier(unsigned int* counter, unsign
     __syncthreads();
 }
 
+// ---- [C] of the persistent phase kernels: slice reduction + (cross-GPU sum) + Adam + image refresh.
+// CTA c reduces ITS 1/gridDim slice of the parameter vector over all slabs in fixed order, exchanges it with the other GPUs over
+// NVLink peer memory under data parallelism, runs Adam on the slice (src/adam.cu:56-69) and refreshes those entries of the global
+// weight image (and of the staged one when the grid is a single CTA).  Contains one __syncthreads on the many-CTA path.
+__device__ __forceinline__ void phase_reduce_adam(const PhaseArgs& p, int s, int nslabs, float* img, float (*redw)[33], float s_entropy_v) {
+    const int total = p.P + p.A + 1;
+    const int G_ = gridDim.x;
+    const int chunk = 32 * ((total + 32 * G_ - 1) / (32 * G_));
+    const int e0 = blockIdx.x * chunk, e1 = min(total, e0 + chunk);
+    const int ngroups = e1 > e0 ? (e1 - e0 + 31) >> 5 : 0;
+    const int W = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 cf = __ldg(p.coef + s);
+    const bool single = gridDim.x == 1;
+    // optimiser state of element e (only ever touched by the thread that owns e, in every step)
+    auto load_state = [&](int e, float& pm, float& pv, float& pw) {
+        pm = 0.f; pv = 0.f; pw = 0.f;
+        if (e < p.P) { pm = p.netseg.m[e]; pv = p.netseg.v[e]; pw = p.netseg.w[e]; }
+        else if (e < p.P + p.A) { if (p.mode == kFusedPolicy) { pm = p.ls.m[e - p.P]; pv = p.ls.v[e - p.P]; pw = p.ls.w[e - p.P]; } }
+        else if (p.mode == kFusedPolicy) pw = s_entropy_v;
+    };
+    // local sum g of element e -> (cross-GPU sum) -> Adam / loss accumulation
+    auto finalize = [&](int e, float g, float pm, float pv, float pw) {
+        if (p.peer.ready) {
+            // gradient exchange over NVLink peer memory (dist.cu "peer arena"): push {tag, value}, poll, ordered sum
+            const PeerView& pvw = p.peer;
+            const unsigned int epoch = pvw.epoch + (unsigned int)s;
+            const size_t poff = (size_t)(epoch & 1u) * pvw.parity_stride;
+            const unsigned long long packed = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(g);
+            for (int r = 0; r < pvw.world; r++)
+                if (r != pvw.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(pvw.peer_recv[r] + poff + e), "l"(packed) : "memory");
+            const long long tstart = clock64();
+            float acc = 0.f;
+            for (int r = 0; r < pvw.world; r++) {
+                float x = g;
+                if (r != pvw.rank) {
+                    const unsigned long long* srcw = pvw.my_recv + poff + (size_t)r * kPeerCap + e;
+                    unsigned long long w;
+                    do {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(srcw) : "memory");
+                        if ((unsigned int)(w >> 32) != epoch && clock64() - tstart > p.spin_limit) {
+                            printf("ppo_b200: peer exchange timed out (rank %d waiting for rank %d, exchange %u)\n", pvw.rank, r, epoch);
+                            __trap();
+                        }
+                    } while ((unsigned int)(w >> 32) != epoch);
+                    x = __uint_as_float((unsigned int)w);
+                }
+                acc += x;                      // same numbers, same (rank) order on every GPU
+            }
+            g = acc;
+        }
+        if (e < p.P) {
+            AdamSeg sg = p.netseg;
+            sg.step_size = cf.x; sg.bc2 = cf.y;
+            const float w = adam_apply(sg, e, g, pm, pv, pw);
+            const int ii = image_index(p.net, e);
+            if (ii >= 0) {
+                p.image[ii] = w;
+                if (single) img[ii] = w;       // one CTA: the staged image is refreshed in place, no re-stage
+            }
+        } else if (e < p.P + p.A) {
+            if (p.mode == kFusedPolicy) {
+                AdamSeg sg = p.ls;
+                sg.step_size = cf.z; sg.bc2 = cf.w;
+                adam_apply(sg, e - p.P, g + (-p.ent_coeff), pm, pv, pw);     // src/ppo.cu:436-438
+            }
+        } else {
+            if (p.mode == kFusedValue) *p.loss_slot += g / (float)p.m_total;
+            else *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
+        }
+    };
+    if (ngroups >= W) {
+        // few CTAs, many elements each (small minibatches): one thread per element, four elements in flight
+        for (int base = e0 + (int)threadIdx.x; base < e1; base += 4 * (int)blockDim.x) {
+            float g[4], pm[4], pv[4], pw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = base + u * (int)blockDim.x;
+                g[u] = 0.f;
+                if (e < e1) load_state(e, pm[u], pv[u], pw[u]);
+            }
+            for (int b = 0; b < nslabs; b++) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = base + u * (int)blockDim.x;
+                    if (e < e1) g[u] += __ldcg(p.partials + (size_t)b * p.slab + e);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = base + u * (int)blockDim.x;
+                if (e < e1) finalize(e, g[u], pm[u], pv[u], pw[u]);
+            }
+        }
+    } else {
+        // many CTAs, <= W 32-element groups each: the warps split the slabs, fixed-order combine through shared memory
+        int ways = 1;
+        while (ways * 2 * max(ngroups, 1) <= W) ways *= 2;
+        const int per = (nslabs + ways - 1) / ways;
+        const int gi = warp / ways, part = warp % ways;
+        const int e = e0 + gi * 32 + lane;
+        const bool live = gi < ngroups && e < e1;
+        const bool fin = live && part == 0;
+        float pm = 0.f, pv = 0.f, pw = 0.f;
+        if (fin) load_state(e, pm, pv, pw);        // overlaps the slab loads
+        float sum = 0.f;
+        if (live) {
+            const int b0 = part * per, b1 = min(nslabs, b0 + per);
+            const float* src = p.partials + e;
+            // up to 24 independent L2 loads in flight per lane (296 slabs / 16 warps = 19: ONE round trip), summed in slab order
+            for (int b = b0; b < b1; b += 24) {
+                const int cnt = min(24, b1 - b);
+                float t[24];
+#pragma unroll
+                for (int u = 0; u < 24; u++) t[u] = (u < cnt) ? __ldcg(src + (size_t)(b + u) * p.slab) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 24; u++) sum += t[u];
+            }
+        }
+        redw[warp][lane] = sum;
+        __syncthreads();
+        if (fin) {
+            float g = redw[warp][lane];
+            for (int q = 1; q < ways; q++) g += redw[warp + q][lane];
+            finalize(e, g, pm, pv, pw);
+        }
+    }
+}
+
 constexpr int kPhaseMaxThreads = 512;
 __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const PhaseArgs p) {
     constexpr int TM = kT64TM, TMP = kT64TMP;
@@ -1059,130 +1188,7 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
         phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
         if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 5] = t; }
         // ---- [C] slice reduction + (cross-GPU sum) + Adam + image refresh
-        {
-            const int total = p.P + p.A + 1;
-            const int G_ = gridDim.x;
-            const int chunk = 32 * ((total + 32 * G_ - 1) / (32 * G_));
-            const int e0 = blockIdx.x * chunk, e1 = min(total, e0 + chunk);
-            const int ngroups = e1 > e0 ? (e1 - e0 + 31) >> 5 : 0;
-            const int W = blockDim.x >> 5;
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-            const float4 cf = __ldg(p.coef + s);
-            const bool single = gridDim.x == 1;
-            // optimiser state of element e (only ever touched by the thread that owns e, in every step)
-            auto load_state = [&](int e, float& pm, float& pv, float& pw) {
-                pm = 0.f; pv = 0.f; pw = 0.f;
-                if (e < p.P) { pm = p.netseg.m[e]; pv = p.netseg.v[e]; pw = p.netseg.w[e]; }
-                else if (e < p.P + p.A) { if (p.mode == kFusedPolicy) { pm = p.ls.m[e - p.P]; pv = p.ls.v[e - p.P]; pw = p.ls.w[e - p.P]; } }
-                else if (p.mode == kFusedPolicy) pw = s_entropy;
-            };
-            // local sum g of element e -> (cross-GPU sum) -> Adam / loss accumulation
-            auto finalize = [&](int e, float g, float pm, float pv, float pw) {
-                if (p.peer.ready) {
-                    // gradient exchange over NVLink peer memory (dist.cu "peer arena"): push {tag, value}, poll, ordered sum
-                    const PeerView& pvw = p.peer;
-                    const unsigned int epoch = pvw.epoch + (unsigned int)s;
-                    const size_t poff = (size_t)(epoch & 1u) * pvw.parity_stride;
-                    const unsigned long long packed = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(g);
-                    for (int r = 0; r < pvw.world; r++)
-                        if (r != pvw.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(pvw.peer_recv[r] + poff + e), "l"(packed) : "memory");
-                    const long long tstart = clock64();
-                    float acc = 0.f;
-                    for (int r = 0; r < pvw.world; r++) {
-                        float x = g;
-                        if (r != pvw.rank) {
-                            const unsigned long long* srcw = pvw.my_recv + poff + (size_t)r * kPeerCap + e;
-                            unsigned long long w;
-                            do {
-                                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(srcw) : "memory");
-                                if ((unsigned int)(w >> 32) != epoch && clock64() - tstart > p.spin_limit) {
-                                    printf("ppo_b200: peer exchange timed out (rank %d waiting for rank %d, exchange %u)\n", pvw.rank, r, epoch);
-                                    __trap();
-                                }
-                            } while ((unsigned int)(w >> 32) != epoch);
-                            x = __uint_as_float((unsigned int)w);
-                        }
-                        acc += x;                      // same numbers, same (rank) order on every GPU
-                    }
-                    g = acc;
-                }
-                if (e < p.P) {
-                    AdamSeg sg = p.netseg;
-                    sg.step_size = cf.x; sg.bc2 = cf.y;
-                    const float w = adam_apply(sg, e, g, pm, pv, pw);
-                    const int ii = image_index(p.net, e);
-                    if (ii >= 0) {
-                        p.image[ii] = w;
-                        if (single) img[ii] = w;       // one CTA: the staged image is refreshed in place, no re-stage
-                    }
-                } else if (e < p.P + p.A) {
-                    if (p.mode == kFusedPolicy) {
-                        AdamSeg sg = p.ls;
-                        sg.step_size = cf.z; sg.bc2 = cf.w;
-                        adam_apply(sg, e - p.P, g + (-p.ent_coeff), pm, pv, pw);     // src/ppo.cu:436-438
-                    }
-                } else {
-                    if (p.mode == kFusedValue) *p.loss_slot += g / (float)p.m_total;
-                    else *p.loss_slot += -g / (float)p.m_total - p.ent_coeff * pw;
-                }
-            };
-            if (ngroups >= W) {
-                // few CTAs, many elements each (small minibatches): one thread per element, four elements in flight
-                for (int base = e0 + (int)threadIdx.x; base < e1; base += 4 * (int)blockDim.x) {
-                    float g[4], pm[4], pv[4], pw[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = base + u * (int)blockDim.x;
-                        g[u] = 0.f;
-                        if (e < e1) load_state(e, pm[u], pv[u], pw[u]);
-                    }
-                    for (int b = 0; b < nslabs; b++) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int e = base + u * (int)blockDim.x;
-                            if (e < e1) g[u] += __ldcg(p.partials + (size_t)b * p.slab + e);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int e = base + u * (int)blockDim.x;
-                        if (e < e1) finalize(e, g[u], pm[u], pv[u], pw[u]);
-                    }
-                }
-            } else {
-                // many CTAs, <= W 32-element groups each: the warps split the slabs, fixed-order combine through shared memory
-                int ways = 1;
-                while (ways * 2 * max(ngroups, 1) <= W) ways *= 2;
-                const int per = (nslabs + ways - 1) / ways;
-                const int gi = warp / ways, part = warp % ways;
-                const int e = e0 + gi * 32 + lane;
-                const bool live = gi < ngroups && e < e1;
-                const bool fin = live && part == 0;
-                float pm = 0.f, pv = 0.f, pw = 0.f;
-                if (fin) load_state(e, pm, pv, pw);        // overlaps the slab loads
-                float sum = 0.f;
-                if (live) {
-                    const int b0 = part * per, b1 = min(nslabs, b0 + per);
-                    const float* src = p.partials + e;
-                    // up to 24 independent L2 loads in flight per lane (296 slabs / 16 warps = 19: ONE round trip), summed in slab order
-                    for (int b = b0; b < b1; b += 24) {
-                        const int cnt = min(24, b1 - b);
-                        float t[24];
-#pragma unroll
-                        for (int u = 0; u < 24; u++) t[u] = (u < cnt) ? __ldcg(src + (size_t)(b + u) * p.slab) : 0.f;
-#pragma unroll
-                        for (int u = 0; u < 24; u++) sum += t[u];
-                    }
-                }
-                redw[warp][lane] = sum;
-                __syncthreads();
-                if (fin) {
-                    float g = redw[warp][lane];
-                    for (int q = 1; q < ways; q++) g += redw[warp + q][lane];
-                    finalize(e, g, pm, pv, pw);
-                }
-            }
-        }
+        phase_reduce_adam(p, s, nslabs, img, redw, s_entropy);
         if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 6] = t; }
         if (s + 1 < p.n_steps) {
             // ---- [D] every slice of the new weights is in the global image; [E] re-stage it
@@ -1198,6 +1204,453 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
                 img_parity ^= 1;
             }
             if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + 7] = t; }
+        }
+    }
+}
+
+// ===================================================================================================
+// Shape-specialised persistent phase kernel for the Pendulum-class nets  S -> 64 -> 64 -> 1  (S <= 8, one hidden activation,
+// single output: the value net and a one-dimensional action mean; BASELINE.json configs[1]).
+//
+// Same outer structure as fused_phase_kernel ([A] tiles, [B] barrier, [C] slice reduce + Adam, [D] barrier, [E] image re-stage)
+// and the same global weight image / slab / optimiser layout, but [A] is written for ONE 128-row tile per CTA with every
+// loop bound, stride and thread mapping a compile-time constant (the generic kernel spends 73 % of its issue slots on
+// address arithmetic, predicates and branches of runtime-shaped loops; ncu, profiles/r02_*):
+//   L0   (K = S)    512 threads x (4 rows x 4 units), weights warp-uniform
+//   L1   (64 x 64)  8 rows x 4 units per thread, split-K halves on the two 256-thread groups, register-prefetched fragments;
+//                   the epilogue also forms the partial dot products of the output layer (y = w2 . h2), so h2 is not re-read
+//   head            128 threads (one per row): loss head on y, dLoss/dy -> gvec
+//   dPre2           512 threads: G2 = g w2 act'(h2), dW2 (warp sums over the 128 rows), db2
+//   bwd l=1         threads 0-255: dX1 -> G1 (8 rows x 4 inputs per thread), then dW0 / db0 from G1 and the input tile;
+//                   threads 256-511: dW1 (4 x 8 outputs per thread, two 64-row halves combined through shared memory), db1
+// One slab per CTA (the generic kernel writes one per 64-row tile slot).  Arithmetic per element is the generic kernel's
+// (fma.rn chains in fixed order, packed two per FFMA2), so results agree with it to rounding of the changed summation splits.
+// ===================================================================================================
+constexpr int kS64TM = 128, kS64TMP = 132, kS64LDW = 68, kS64Threads = 512;
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+template <int ID, int N> __device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" :: "n"(ID), "n"(N) : "memory"); }
+
+// shared-memory floats after the weight image
+constexpr int kS64X0 = 0;                                  // [8][TMP]   input tile (feature-major)
+constexpr int kS64H1 = kS64X0 + 8 * kS64TMP;               // [64][TMP]  hidden 1
+constexpr int kS64H2 = kS64H1 + 64 * kS64TMP;              // [64][TMP]  hidden 2
+constexpr int kS64G2 = kS64H2 + 64 * kS64TMP;              // [64][TMP]  dLoss/d(pre-activation 2)
+constexpr int kS64G1 = kS64G2 + 64 * kS64TMP;              // [64][TMP]  dLoss/d(pre-activation 1); forward: split-K exchange
+constexpr int kS64CB = kS64G1 + 64 * kS64TMP;              // [4096]     dW1 half combine; forward: y partials [8][128]
+constexpr int kS64Red = kS64CB + 4096;                     // [64]       warp partials of the loss / log_std terms
+constexpr int kS64Gv = kS64Red + 64;                       // [128]      dLoss/dy per row
+constexpr int kS64Src = kS64Gv + 128;                      // [128] int  source rows of the tile
+constexpr int kS64Bar = kS64Src + 128;                     // mbarrier (8 bytes)
+constexpr int kS64Floats = kS64Bar + 4;
+
+template <int ACT>
+__global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(const PhaseArgs p) {
+    constexpr int TM = kS64TM, TMP = kS64TMP, LDW = kS64LDW;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ float redw[kS64Threads / 32][33];
+    __shared__ float s_entropy;
+    const FusedNet& net = p.net;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int S = net.sizes[0], SP = pad4(S);
+    float* img = smem;
+    float* base = smem + net.img_floats;
+    float* X0 = base + kS64X0;
+    float* H1 = base + kS64H1;
+    float* H2 = base + kS64H2;
+    float* G2 = base + kS64G2;
+    float* G1 = base + kS64G1;
+    float* CB = base + kS64CB;
+    float* red = base + kS64Red;
+    float* gvec = base + kS64Gv;
+    int* src_rows = reinterpret_cast<int*>(base + kS64Src);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + kS64Bar);
+    const float* W0 = img + net.wt_off[0];
+    const float* W1 = img + net.wt_off[1];
+    const float* W2 = img + net.wt_off[2];      // w2[k] = W2[k * 8]
+    const float* B0 = img + net.bs_off[0];
+    const float* B1 = img + net.bs_off[1];
+    const float* B2 = img + net.bs_off[2];
+    const int out_act = net.acts[2];
+
+    const int n_tiles = (p.mb + TM - 1) / TM;
+    const int stride = gridDim.x;
+    const int t0 = blockIdx.x;
+    const int rounds = t0 < n_tiles ? (n_tiles - t0 + stride - 1) / stride : 0;
+    const int nslabs = min(n_tiles, stride);
+    float* slab = p.partials + (size_t)t0 * p.slab;
+    unsigned int bar_gen = 0;
+
+    auto src_of = [&](int s, int tile, int r) -> int {      // src/trajectory_buffer.cu:208-209
+        const int row = tile * TM + r;
+        if (row >= p.mb) return -1;
+        const int e = s / p.num_batches, k = s - e * p.num_batches;
+        const int off = (k * p.batch_stride + p.row0 + row) % p.limit;
+        return p.perms ? __ldg(p.perms + (size_t)e * p.limit + off) : off;
+    };
+    float h_target = 0.f, h_adv = 0.f, h_lp_old = 0.f, h_act0 = 0.f;     // per-row scalars of row t (threads < 128)
+    int my_src = -1;
+    auto issue_gather = [&]() {
+        for (int e = t; e < TM * SP; e += kS64Threads) {
+            const int r = e / SP, k = e - r * SP;
+            const int src = src_rows[r];
+            float* dst = X0 + k * TMP + r;
+            if (src >= 0 && k < S) cp_async4(dst, p.state + (size_t)src * S + k);
+            else *dst = 0.f;
+        }
+        if (t < TM) {
+            my_src = src_rows[t];
+            h_target = 0.f; h_adv = 0.f; h_lp_old = 0.f; h_act0 = 0.f;
+            if (my_src >= 0) {
+                if (p.mode == kFusedValue) {
+                    h_target = __ldg(p.adv_target + my_src);
+                } else {
+                    h_adv = __ldg(p.advantage + my_src);
+                    h_lp_old = __ldg(p.logprob + my_src);
+                    h_act0 = __ldg(p.action + my_src);
+                }
+            }
+        }
+    };
+    auto stamp = [&](int slot) {
+        if (p.dbg && t == 0) {
+            unsigned long long tm;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm));
+            p.dbg[(size_t)blockIdx.x * 16 + slot] = tm;
+        }
+    };
+
+    if (t == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    int nxt_src = -1;
+    if (rounds > 0) {
+        if (t < TM) src_rows[t] = src_of(0, t0, t);
+        __syncthreads();
+        issue_gather();
+    }
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+        tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+    }
+    uint32_t img_parity = 0;
+    mbar_wait(mbar, img_parity);
+    img_parity ^= 1;
+
+    for (int s = 0; s < p.n_steps; s++) {
+        for (int rd = 0; rd < rounds; rd++) {
+            const bool accum = rd > 0;
+            auto put = [&](int idx, float v) { slab[idx] = accum ? slab[idx] + v : v; };
+            cp_async_wait_all();
+            __syncthreads();                                   // the gathered tile is complete and visible
+            int ns = s, nt = t0 + (rd + 1) * stride;
+            if (rd + 1 >= rounds) { ns = s + 1; nt = t0; }
+            const bool have_next = ns < p.n_steps;
+            if (have_next && t < TM) nxt_src = src_of(ns, nt, t);
+            stamp(3);
+            // ---- L0: H1[j][r] = act(sum_k X0[k][r] W0[k][j] + b0[j]);  rows 4*lane.., units 4*warp..
+            {
+                float2 acc[2][4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) { acc[0][c] = make_float2(0.f, 0.f); acc[1][c] = make_float2(0.f, 0.f); }
+                for (int k = 0; k < S; k++) {
+                    const float4 x = lds4(X0 + k * TMP + 4 * lane);
+                    const float4 w = lds4(W0 + k * LDW + 4 * warp);
+                    const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        acc[0][c] = ffma2(make_float2(x.x, x.y), bcast2(wv[c]), acc[0][c]);
+                        acc[1][c] = ffma2(make_float2(x.z, x.w), bcast2(wv[c]), acc[1][c]);
+                    }
+                }
+                const float4 b = lds4(B0 + 4 * warp);
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    sts4(H1 + (4 * warp + c) * TMP + 4 * lane, act_apply(acc[0][c].x + bv[c], ACT), act_apply(acc[0][c].y + bv[c], ACT),
+                         act_apply(acc[1][c].x + bv[c], ACT), act_apply(acc[1][c].y + bv[c], ACT));
+            }
+            __syncthreads();
+            stamp(8);
+            // ---- L1: split-K halves (group g: k in [32g, 32g + 32)), 8 rows x 4 units per thread
+            {
+                const int g = t >> 8, lt = t & 255, tr = lt & 15, tc = lt >> 4;
+                float2 acc[4][4];                   // row pairs (4tr, +1), (4tr+2, +3), (64+4tr, +1), (64+4tr+2, +3)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
+                const float* xp = H1 + 32 * g * TMP + 4 * tr;
+                const float* wp = W1 + 32 * g * LDW + 4 * tc;
+                float4 a0 = lds4(xp), a1 = lds4(xp + 64), w = lds4(wp);
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const float4 c0 = a0, c1 = a1, cw = w;
+                    if (k + 1 < 32) { a0 = lds4(xp + (k + 1) * TMP); a1 = lds4(xp + (k + 1) * TMP + 64); w = lds4(wp + (k + 1) * LDW); }
+                    const float2 ap[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+                    const float wv[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) acc[r][c] = ffma2(ap[r], bcast2(wv[c]), acc[r][c]);
+                }
+                // group 0 finalises rows 4tr.. (pairs 0,1), group 1 rows 64+4tr.. (pairs 2,3): pass the other quad through G1
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float* dst = G1 + (4 * tc + c) * TMP + 4 * tr + (g ? 0 : 64);
+                    if (g) sts4(dst, acc[0][c].x, acc[0][c].y, acc[1][c].x, acc[1][c].y);
+                    else sts4(dst, acc[2][c].x, acc[2][c].y, acc[3][c].x, acc[3][c].y);
+                }
+                __syncthreads();
+                const float4 b = lds4(B1 + 4 * tc);
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+                float yp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float2 lo = g ? acc[2][c] : acc[0][c], hi = g ? acc[3][c] : acc[1][c];
+                    const float4 q = lds4(G1 + (4 * tc + c) * TMP + 4 * tr + 64 * g);
+                    float o[4] = {lo.x, lo.y, hi.x, hi.y};
+                    const float qv[4] = {q.x, q.y, q.z, q.w};
+                    const float w2 = W2[(4 * tc + c) * 8];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        o[r] = g ? qv[r] + o[r] : o[r] + qv[r];            // lower-k partial + upper-k partial
+                        o[r] = act_apply(o[r] + bv[c], ACT);
+                        yp[r] = fmaf(o[r], w2, yp[r]);
+                    }
+                    sts4(H2 + (4 * tc + c) * TMP + 4 * tr + 64 * g, o[0], o[1], o[2], o[3]);
+                }
+                // y partials: the two unit groups of a warp meet through one shuffle; the 8 warps of a group through CB[8][128]
+#pragma unroll
+                for (int r = 0; r < 4; r++) yp[r] += __shfl_xor_sync(kFull, yp[r], 16);
+                if (lane < 16) sts4(CB + ((warp & 7) * TM) + 64 * g + 4 * tr, yp[0], yp[1], yp[2], yp[3]);
+            }
+            __syncthreads();
+            stamp(9);
+            // ---- head: one thread per row (src/loss.cu:5-23 | src/policy.cu:67-111 + src/ppo.cu:89-98)
+            if (t < TM) {
+                float part = CB[t];
+#pragma unroll
+                for (int w8 = 1; w8 < 8; w8++) part += CB[w8 * TM + t];
+                const float y = act_apply(part + B2[0], out_act);
+                float loss_term = 0.f, gout = 0.f, gls = 0.f;
+                if (my_src >= 0) {
+                    if (p.mode == kFusedValue) {
+                        gout = __fdiv_rn(__fmul_rn(2.f, __fsub_rn(y, h_target)), (float)p.m_total);
+                        const float d = __fsub_rn(h_target, y);
+                        loss_term = __fmul_rn(d, d);
+                    } else {
+                        const float ls = __ldcg(p.log_std);      // L2: another SM's Adam wrote it
+                        const float lp = fused_log_prob(&y, &ls, &h_act0, 1);
+                        const float ratio = expf(__fsub_rn(lp, h_lp_old));
+                        const bool adv_pos = h_adv > 0.f;
+                        const bool hi = ratio > 1.f + p.epsilon, lo = ratio < 1.f - p.epsilon;
+                        const float sel = adv_pos ? (hi ? 1.f + p.epsilon : ratio) : (lo ? 1.f - p.epsilon : ratio);
+                        loss_term = __fmul_rn(h_adv, sel);
+                        const int keep = adv_pos ? !hi : !lo;
+                        const float gg = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)p.m_total);
+                        const float e2 = expf(-2.f * ls);
+                        const float diff = __fsub_rn(h_act0, y);
+                        gout = __fmul_rn(__fmul_rn(diff, e2), gg);
+                        gls = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), gg);
+                    }
+                }
+                gvec[t] = act_grad(y, gout, out_act);
+                const float v = warp_sum(loss_term);
+                if (lane == 0) red[warp] = v;
+                if (p.mode == kFusedPolicy) { const float s2 = warp_sum(gls); if (lane == 0) red[8 + warp] = s2; }
+            }
+            __syncthreads();
+            // ---- dPre2: G2[k][r] = g_r w2[k] act'(H2[k][r]); dW2[k] = sum_r g_r H2[k][r]; db2 = sum_r g_r.  rows 4*lane.., k = 4*warp..
+            {
+                if (t == 0) put(net.P + 1, (red[0] + red[1]) + (red[2] + red[3]));
+                if (t == 32 && p.mode == kFusedPolicy) put(net.P, (red[8] + red[9]) + (red[10] + red[11]));
+                const float4 g4 = lds4(gvec + 4 * lane);
+                float pw[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int k = 4 * warp + c;
+                    const float4 h = lds4(H2 + k * TMP + 4 * lane);
+                    const float w2 = W2[k * 8];
+                    sts4(G2 + k * TMP + 4 * lane, act_grad(h.x, __fmul_rn(g4.x, w2), ACT), act_grad(h.y, __fmul_rn(g4.y, w2), ACT),
+                         act_grad(h.z, __fmul_rn(g4.z, w2), ACT), act_grad(h.w, __fmul_rn(g4.w, w2), ACT));
+                    pw[c] = fmaf(g4.w, h.w, fmaf(g4.z, h.z, fmaf(g4.y, h.y, g4.x * h.x)));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) pw[c] = warp_sum(pw[c]);
+                if (lane < 4) put(net.w_off[2] + 4 * warp + lane, lane == 0 ? pw[0] : lane == 1 ? pw[1] : lane == 2 ? pw[2] : pw[3]);
+                if (warp == 15) {
+                    const float sg = warp_sum((g4.x + g4.y) + (g4.z + g4.w));
+                    if (lane == 0) put(net.b_off[2], sg);
+                }
+            }
+            __syncthreads();
+            stamp(11);
+            // ---- backward of layer 1 (and layer 0 behind it)
+            if (t < 256) {
+                // dX1: G1[k][r] = (sum_j G2[j][r] W1[k][j]) act'(H1[k][r]);  k = tc + 16c, rows 4tr.. and 64+4tr..
+                const int tr = t & 15, tc = t >> 4;
+                float2 acc[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
+                const float* wrow = W1 + tc * LDW;
+                const float* gp = G2 + 4 * tr;
+#pragma unroll 2
+                for (int j0 = 0; j0 < 64; j0 += 4) {
+                    float wv[4][4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float4 w = lds4(wrow + 16 * c * LDW + j0);
+                        wv[c][0] = w.x; wv[c][1] = w.y; wv[c][2] = w.z; wv[c][3] = w.w;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        const float4 g0 = lds4(gp + (j0 + jj) * TMP);
+                        const float4 g1 = lds4(gp + (j0 + jj) * TMP + 64);
+                        const float2 gq[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+#pragma unroll
+                            for (int c = 0; c < 4; c++) acc[r][c] = ffma2(gq[r], bcast2(wv[c][jj]), acc[r][c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int k = tc + 16 * c;
+                    const float4 h0 = lds4(H1 + k * TMP + 4 * tr), h1 = lds4(H1 + k * TMP + 4 * tr + 64);
+                    sts4(G1 + k * TMP + 4 * tr, act_grad(h0.x, acc[0][c].x, ACT), act_grad(h0.y, acc[0][c].y, ACT),
+                         act_grad(h0.z, acc[1][c].x, ACT), act_grad(h0.w, acc[1][c].y, ACT));
+                    sts4(G1 + k * TMP + 4 * tr + 64, act_grad(h1.x, acc[2][c].x, ACT), act_grad(h1.y, acc[2][c].y, ACT),
+                         act_grad(h1.z, acc[3][c].x, ACT), act_grad(h1.w, acc[3][c].y, ACT));
+                }
+                named_sync<1, 256>();
+                // dW0[j][k] = sum_r G1[j][r] X0[k][r], db0[j] = sum_r G1[j][r]: j = 8*warp + (lane & 7), row quarter = lane >> 3
+                {
+                    const int j = 8 * warp + (lane & 7), rq = lane >> 3;
+                    float accw[8], accb = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) accw[k] = 0.f;
+                    const float* gq = G1 + j * TMP + 32 * rq;
+                    const float* xq = X0 + 32 * rq;
+#pragma unroll 2
+                    for (int i = 0; i < 8; i++) {
+                        const float4 gv = lds4(gq + 4 * i);
+                        accb += (gv.x + gv.y) + (gv.z + gv.w);
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (k < S) {
+                                const float4 xv = lds4(xq + k * TMP + 4 * i);
+                                accw[k] = fmaf(gv.w, xv.w, fmaf(gv.z, xv.z, fmaf(gv.y, xv.y, fmaf(gv.x, xv.x, accw[k]))));
+                            }
+                    }
+                    accb += __shfl_xor_sync(kFull, accb, 8);
+                    accb += __shfl_xor_sync(kFull, accb, 16);
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (k < S) {
+                            accw[k] += __shfl_xor_sync(kFull, accw[k], 8);
+                            accw[k] += __shfl_xor_sync(kFull, accw[k], 16);
+                        }
+                    if (rq == 0) {
+                        put(net.b_off[0] + j, accb);
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (k < S) put(net.w_off[0] + j * S + k, accw[k]);
+                    }
+                }
+            } else {
+                // dW1[j][k] = sum_r G2[j][r] H1[k][r]: j = tj + 16a, k = tk + 8b, rows [64*half, 64*half + 64)
+                const int lt = t - 256, half = lt >> 7, l7 = lt & 127, tk = l7 & 7, tj = l7 >> 3;
+                float2 acc[4][8];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 8; b++) acc[a][b] = make_float2(0.f, 0.f);
+                const float* gb = G2 + tj * TMP + 64 * half;
+                const float* xb = H1 + tk * TMP + 64 * half;
+#pragma unroll 1
+                for (int r = 0; r < 64; r += 4) {
+                    float4 g[4], x[8];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) g[a] = lds4(gb + 16 * a * TMP + r);
+#pragma unroll
+                    for (int b = 0; b < 8; b++) x[b] = lds4(xb + 8 * b * TMP + r);
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 8; b++) {
+                            acc[a][b] = ffma2(make_float2(g[a].x, g[a].y), make_float2(x[b].x, x[b].y), acc[a][b]);
+                            acc[a][b] = ffma2(make_float2(g[a].z, g[a].w), make_float2(x[b].z, x[b].w), acc[a][b]);
+                        }
+                }
+                if (half) {
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 8; b++) CB[(a * 8 + b) * 128 + l7] = acc[a][b].x + acc[a][b].y;
+                }
+                named_sync<2, 256>();
+                if (!half) {
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 8; b++)
+                            put(net.w_off[1] + (tj + 16 * a) * 64 + tk + 8 * b, (acc[a][b].x + acc[a][b].y) + CB[(a * 8 + b) * 128 + l7]);
+                } else {
+                    // db1[j] = sum_r G2[j][r]: j = 16*(warp & 3) + (lane & 15), row half = lane >> 4
+                    const int j = 16 * (warp & 3) + (lane & 15), hh = lane >> 4;
+                    const float* gq = G2 + j * TMP + 64 * hh;
+                    float sb = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float4 gv = lds4(gq + 4 * i);
+                        sb += (gv.x + gv.y) + (gv.z + gv.w);
+                    }
+                    sb += __shfl_xor_sync(kFull, sb, 16);
+                    if (hh == 0) put(net.b_off[1] + j, sb);
+                }
+            }
+            __syncthreads();                                   // X0 / src_rows / CB are about to be refilled
+            stamp(13);
+            if (have_next) {
+                if (t < TM) src_rows[t] = nxt_src;
+                __syncthreads();
+                issue_gather();
+            }
+            stamp(12);
+        }
+        stamp(4);
+        if (t == 33 && p.mode == kFusedPolicy) {               // log_std is stable here: last written in [C] of step s-1, before [D]
+            float ent = (float)(p.A * 0.5 * (1 + log(2 * kPiF)));             // src/policy.cu:171-178
+            for (int j = 0; j < p.A; j++) ent += __ldcg(p.log_std + j);
+            s_entropy = ent;
+        }
+        // ---- [B] every slab of minibatch s is written
+        ++bar_gen;
+        phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
+        stamp(5);
+        // ---- [C] slice reduction + (cross-GPU sum) + Adam + image refresh
+        phase_reduce_adam(p, s, nslabs, img, redw, s_entropy);
+        stamp(6);
+        if (s + 1 < p.n_steps) {
+            // ---- [D] every slice of the new weights is in the global image; [E] re-stage it
+            ++bar_gen;
+            phase_grid_barrier(p.barrier, bar_gen * gridDim.x, p.spin_limit);
+            if (gridDim.x > 1) {
+                if (t == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    mbar_expect_tx(mbar, (uint32_t)net.img_floats * 4u);
+                    tma_bulk_g2s(img, p.image, (uint32_t)net.img_floats * 4u, mbar);
+                }
+                mbar_wait(mbar, img_parity);
+                img_parity ^= 1;
+            }
+            stamp(7);
         }
     }
 }
@@ -1432,6 +1885,22 @@ bool fused_phase_supported(NeuralNetwork* nn) {
     return pl.ok && phase_geometry(pl, 64).ok;
 }
 
+// The shape-specialised kernel applies to  S<=8 -> 64 -> 64 -> 1  nets with one hidden activation (tanh / relu) when the minibatch
+// gives every SM at least one 128-row tile (smaller minibatches keep the generic kernel's 64-row tiles: more CTAs busy).
+// PPO_B200_SPEC64=0 disables it (A/B runs, parity tests of the generic kernel).
+static int spec64_kind(const FusedPlan& pl, int mb) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("PPO_B200_SPEC64"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    const FusedNet& n = pl.net;
+    if (!enabled || !pl.ok || n.L != 3) return 0;
+    if (n.sizes[0] > 8 || n.sizes[1] != 64 || n.sizes[2] != 64 || n.sizes[3] != 1) return 0;
+    if (n.acts[0] != n.acts[1] || (n.acts[0] != kActTanh && n.acts[0] != kActRelu)) return 0;
+    if (n.ldw[0] != kS64LDW || n.ldw[1] != kS64LDW || n.ldw[2] != 8) return 0;
+    if (div_up(mb, kT64TM) <= num_sms()) return 0;
+    if ((size_t)(n.img_floats + kS64Floats) * sizeof(float) > 220 * 1024) return 0;
+    return n.acts[0];
+}
+
 static unsigned int* g_phase_barrier = nullptr;
 static float4* g_phase_coef = nullptr;
 static int g_phase_coef_cap = 0;
@@ -1447,7 +1916,9 @@ void fused_phase_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_ne
     if (n_steps <= 0 || mb <= 0) return;
     const int A = policy ? policy->action_size : 1;
     const int slab = (int)nd->param_count + A + 1;
-    const int nslabs = std::min(div_up(mb, kT64TM), geo.grid * geo.nsub);
+    const int spec = spec64_kind(pl, mb);             // 0: generic kernel; else the hidden activation of the specialised one
+    const int spec_grid = std::max(1, std::min(num_sms(), div_up(mb, kS64TM)));
+    const int nslabs = spec ? spec_grid : std::min(div_up(mb, kT64TM), geo.grid * geo.nsub);
     const size_t need = (size_t)nslabs * slab;
     if (need > nd->partials_cap) {
         CUDA_CHECK(cudaStreamSynchronize(stream()));
@@ -1503,12 +1974,24 @@ void fused_phase_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* adam_ne
         a.peer = dist_peer_reserve((size_t)slab, n_steps);
         if (!a.peer.ready) B200_FATAL("peer exchange requested but the peer arena is not available (slab %d floats)", slab);
     }
-    static size_t configured = 0;
-    if (geo.smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(fused_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
-        configured = geo.smem;
+    if (spec) {
+        const size_t smem = (size_t)(pl.net.img_floats + kS64Floats) * sizeof(float);
+        static size_t configured64 = 0;
+        if (smem > configured64) {
+            CUDA_CHECK(cudaFuncSetAttribute(fused_phase_spec64_kernel<kActTanh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_CHECK(cudaFuncSetAttribute(fused_phase_spec64_kernel<kActRelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured64 = smem;
+        }
+        if (spec == kActTanh) B200_LAUNCH_COOP(fused_phase_spec64_kernel<kActTanh>, spec_grid, kS64Threads, smem, &a);
+        else B200_LAUNCH_COOP(fused_phase_spec64_kernel<kActRelu>, spec_grid, kS64Threads, smem, &a);
+    } else {
+        static size_t configured = 0;
+        if (geo.smem > configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(fused_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+            configured = geo.smem;
+        }
+        B200_LAUNCH_COOP(fused_phase_kernel, geo.grid, 256 * geo.nsub, geo.smem, &a);
     }
-    B200_LAUNCH_COOP(fused_phase_kernel, geo.grid, 256 * geo.nsub, geo.smem, &a);
     adam_net->time_step += n_steps;
     if (policy) adam_ls->time_step += n_steps;
     nd->last_splits = nslabs;
