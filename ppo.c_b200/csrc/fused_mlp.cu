@@ -1238,9 +1238,10 @@ constexpr int kS64H1 = kS64X0 + 8 * kS64TMP;               // [64][TMP]  hidden 
 constexpr int kS64H2 = kS64H1 + 64 * kS64TMP;              // [64][TMP]  hidden 2
 constexpr int kS64G2 = kS64H2 + 64 * kS64TMP;              // [64][TMP]  dLoss/d(pre-activation 2)
 constexpr int kS64G1 = kS64G2 + 64 * kS64TMP;              // [64][TMP]  dLoss/d(pre-activation 1); forward: split-K exchange
-constexpr int kS64CB = kS64G1 + 64 * kS64TMP;              // [4096]     dW1 half combine; forward: y partials [8][128]
-constexpr int kS64Red = kS64CB + 4096;                     // [64]       warp partials of the loss / log_std terms
-constexpr int kS64Gv = kS64Red + 64;                       // [128]      dLoss/dy per row
+constexpr int kS64CBLd = 72;                               // row stride of the dW1 partials: 8 * tj + tk hits 32 distinct banks
+constexpr int kS64CB = kS64G1 + 64 * kS64TMP;              // [2][64][72] dW1 partials of the two 64-row halves; forward: y partials [8][128]
+constexpr int kS64Red = kS64CB + 2 * 64 * kS64CBLd;        // [2][128]   per-row loss terms | per-row log_std gradient terms
+constexpr int kS64Gv = kS64Red + 256;                      // [128]      dLoss/dy per row
 constexpr int kS64Src = kS64Gv + 128;                      // [128] int  source rows of the tile
 constexpr int kS64Bar = kS64Src + 128;                     // mbarrier (8 bytes)
 constexpr int kS64Floats = kS64Bar + 4;
@@ -1251,6 +1252,7 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
     extern __shared__ __align__(128) float smem[];
     __shared__ float redw[kS64Threads / 32][33];
     __shared__ float s_entropy;
+    __shared__ float s_ls[4];         // per step: log_std, exp(log_std), exp(-2 log_std), -0.5 log(2 pi)   (policy mode)
     const FusedNet& net = p.net;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int S = net.sizes[0], SP = pad4(S);
@@ -1313,8 +1315,8 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
             }
         }
     };
-    auto stamp = [&](int slot) {
-        if (p.dbg && t == 0) {
+    auto stamp = [&](int slot, int who = 0) {
+        if (p.dbg && t == who) {
             unsigned long long tm;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm));
             p.dbg[(size_t)blockIdx.x * 16 + slot] = tm;
@@ -1341,6 +1343,16 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
     img_parity ^= 1;
 
     for (int s = 0; s < p.n_steps; s++) {
+        if (t == 64 && p.mode == kFusedPolicy) {
+            // log_std is final for this step (last written in [C] of step s-1, before [D]): ONE L2 read per CTA instead of one per
+            // head warp (592 simultaneous requests for one sector cost the heads ~2 us), and the row-independent terms of
+            // src/policy.cu:67-74 / :91-111 evaluated once
+            const float ls = __ldcg(p.log_std);
+            s_ls[0] = ls;
+            s_ls[1] = expf(ls);
+            s_ls[2] = expf(-2.f * ls);
+            s_ls[3] = (float)(-0.5 * (double)logf((float)(2 * kPiF)));
+        }
         for (int rd = 0; rd < rounds; rd++) {
             const bool accum = rd > 0;
             auto put = [&](int idx, float v) { slab[idx] = accum ? slab[idx] + v : v; };
@@ -1443,8 +1455,9 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                         const float d = __fsub_rn(h_target, y);
                         loss_term = __fmul_rn(d, d);
                     } else {
-                        const float ls = __ldcg(p.log_std);      // L2: another SM's Adam wrote it
-                        const float lp = fused_log_prob(&y, &ls, &h_act0, 1);
+                        const float ls = s_ls[0], e2 = s_ls[2];
+                        const float z = __fdiv_rn(__fsub_rn(h_act0, y), s_ls[1]);           // fused_log_prob with A = 1
+                        const float lp = (float)((double)s_ls[3] - ((double)ls + 0.5 * (double)__fmul_rn(z, z)));
                         const float ratio = expf(__fsub_rn(lp, h_lp_old));
                         const bool adv_pos = h_adv > 0.f;
                         const bool hi = ratio > 1.f + p.epsilon, lo = ratio < 1.f - p.epsilon;
@@ -1452,39 +1465,46 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                         loss_term = __fmul_rn(h_adv, sel);
                         const int keep = adv_pos ? !hi : !lo;
                         const float gg = __fdiv_rn(__fmul_rn(__fmul_rn((float)(-keep), h_adv), ratio), (float)p.m_total);
-                        const float e2 = expf(-2.f * ls);
                         const float diff = __fsub_rn(h_act0, y);
                         gout = __fmul_rn(__fmul_rn(diff, e2), gg);
                         gls = __fmul_rn(__fadd_rn(-1.f, __fmul_rn(__fmul_rn(diff, diff), e2)), gg);
                     }
                 }
                 gvec[t] = act_grad(y, gout, out_act);
-                const float v = warp_sum(loss_term);
-                if (lane == 0) red[warp] = v;
-                if (p.mode == kFusedPolicy) { const float s2 = warp_sum(gls); if (lane == 0) red[8 + warp] = s2; }
+                red[t] = loss_term;                            // summed (fixed order) in the tail of the dX group, off this chain
+                red[128 + t] = gls;
             }
             __syncthreads();
-            // ---- dPre2: G2[k][r] = g_r w2[k] act'(H2[k][r]); dW2[k] = sum_r g_r H2[k][r]; db2 = sum_r g_r.  rows 4*lane.., k = 4*warp..
+            stamp(10);
+            // ---- dPre2: G2[k][r] = g_r w2[k] act'(H2[k][r]); dW2[k] = sum_r g_r H2[k][r]; db1[k] = sum_r G2[k][r]; db2 = sum_r g_r.
+            // Eight lanes per hidden unit k = t >> 3; lane l8 takes the row quads l8, l8 + 8, l8 + 16, l8 + 24 (a quarter-warp reads 128
+            // contiguous bytes); the eight partial sums of a unit meet through three shuffles.
             {
-                if (t == 0) put(net.P + 1, (red[0] + red[1]) + (red[2] + red[3]));
-                if (t == 32 && p.mode == kFusedPolicy) put(net.P, (red[8] + red[9]) + (red[10] + red[11]));
-                const float4 g4 = lds4(gvec + 4 * lane);
-                float pw[4];
+                const int k = t >> 3, l8 = t & 7;
+                const float w2 = W2[k * 8];
+                float pw = 0.f, pb = 0.f, pg = 0.f;
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int k = 4 * warp + c;
-                    const float4 h = lds4(H2 + k * TMP + 4 * lane);
-                    const float w2 = W2[k * 8];
-                    sts4(G2 + k * TMP + 4 * lane, act_grad(h.x, __fmul_rn(g4.x, w2), ACT), act_grad(h.y, __fmul_rn(g4.y, w2), ACT),
-                         act_grad(h.z, __fmul_rn(g4.z, w2), ACT), act_grad(h.w, __fmul_rn(g4.w, w2), ACT));
-                    pw[c] = fmaf(g4.w, h.w, fmaf(g4.z, h.z, fmaf(g4.y, h.y, g4.x * h.x)));
+                for (int i = 0; i < 4; i++) {
+                    const int r0 = 4 * (l8 + 8 * i);
+                    const float4 h = lds4(H2 + k * TMP + r0);
+                    const float4 g4 = lds4(gvec + r0);
+                    const float d0 = act_grad(h.x, __fmul_rn(g4.x, w2), ACT), d1 = act_grad(h.y, __fmul_rn(g4.y, w2), ACT);
+                    const float d2 = act_grad(h.z, __fmul_rn(g4.z, w2), ACT), d3 = act_grad(h.w, __fmul_rn(g4.w, w2), ACT);
+                    sts4(G2 + k * TMP + r0, d0, d1, d2, d3);
+                    pw = fmaf(g4.w, h.w, fmaf(g4.z, h.z, fmaf(g4.y, h.y, fmaf(g4.x, h.x, pw))));
+                    pb += (d0 + d1) + (d2 + d3);
+                    pg += (g4.x + g4.y) + (g4.z + g4.w);
                 }
 #pragma unroll
-                for (int c = 0; c < 4; c++) pw[c] = warp_sum(pw[c]);
-                if (lane < 4) put(net.w_off[2] + 4 * warp + lane, lane == 0 ? pw[0] : lane == 1 ? pw[1] : lane == 2 ? pw[2] : pw[3]);
-                if (warp == 15) {
-                    const float sg = warp_sum((g4.x + g4.y) + (g4.z + g4.w));
-                    if (lane == 0) put(net.b_off[2], sg);
+                for (int o = 1; o < 8; o <<= 1) {
+                    pw += __shfl_xor_sync(kFull, pw, o);
+                    pb += __shfl_xor_sync(kFull, pb, o);
+                    pg += __shfl_xor_sync(kFull, pg, o);
+                }
+                if (l8 == 0) {
+                    put(net.w_off[2] + k, pw);
+                    put(net.b_off[1] + k, pb);
+                    if (k == 0) put(net.b_off[2], pg);
                 }
             }
             __syncthreads();
@@ -1528,6 +1548,7 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                     sts4(G1 + k * TMP + 4 * tr + 64, act_grad(h1.x, acc[2][c].x, ACT), act_grad(h1.y, acc[2][c].y, ACT),
                          act_grad(h1.z, acc[3][c].x, ACT), act_grad(h1.w, acc[3][c].y, ACT));
                 }
+                stamp(14);
                 named_sync<1, 256>();
                 // dW0[j][k] = sum_r G1[j][r] X0[k][r], db0[j] = sum_r G1[j][r]: j = 8*warp + (lane & 7), row quarter = lane >> 3
                 {
@@ -1563,6 +1584,13 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                             if (k < S) put(net.w_off[0] + j * S + k, accw[k]);
                     }
                 }
+                // tile sums of the loss terms (warp 0) and of the log_std gradient terms (warp 1): fixed order
+                if (warp < 2 && (warp == 0 || p.mode == kFusedPolicy)) {
+                    const float4 v = lds4(red + 128 * warp + 4 * lane);
+                    const float sv = warp_sum((v.x + v.y) + (v.z + v.w));
+                    if (lane == 0) put(warp == 0 ? net.P + 1 : net.P, sv);
+                }
+                stamp(15);
             } else {
                 // dW1[j][k] = sum_r G2[j][r] H1[k][r]: j = tj + 16a, k = tk + 8b, rows [64*half, 64*half + 64)
                 const int lt = t - 256, half = lt >> 7, l7 = lt & 127, tk = l7 & 7, tj = l7 >> 3;
@@ -1573,50 +1601,33 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                     for (int b = 0; b < 8; b++) acc[a][b] = make_float2(0.f, 0.f);
                 const float* gb = G2 + tj * TMP + 64 * half;
                 const float* xb = H1 + tk * TMP + 64 * half;
-#pragma unroll 1
-                for (int r = 0; r < 64; r += 4) {
-                    float4 g[4], x[8];
+#pragma unroll 4
+                for (int r = 0; r < 64; r += 2) {          // two rows per step (LDS.64): operands fit beside the 64 accumulators,
+                    float2 g[4], x[8];                      // so the loads of the next steps can be hoisted above this step's math
 #pragma unroll
-                    for (int a = 0; a < 4; a++) g[a] = lds4(gb + 16 * a * TMP + r);
+                    for (int a = 0; a < 4; a++) g[a] = *reinterpret_cast<const float2*>(gb + 16 * a * TMP + r);
 #pragma unroll
-                    for (int b = 0; b < 8; b++) x[b] = lds4(xb + 8 * b * TMP + r);
-#pragma unroll
-                    for (int a = 0; a < 4; a++)
-#pragma unroll
-                        for (int b = 0; b < 8; b++) {
-                            acc[a][b] = ffma2(make_float2(g[a].x, g[a].y), make_float2(x[b].x, x[b].y), acc[a][b]);
-                            acc[a][b] = ffma2(make_float2(g[a].z, g[a].w), make_float2(x[b].z, x[b].w), acc[a][b]);
-                        }
-                }
-                if (half) {
+                    for (int b = 0; b < 8; b++) x[b] = *reinterpret_cast<const float2*>(xb + 8 * b * TMP + r);
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int b = 0; b < 8; b++) CB[(a * 8 + b) * 128 + l7] = acc[a][b].x + acc[a][b].y;
+                        for (int b = 0; b < 8; b++) acc[a][b] = ffma2(g[a], x[b], acc[a][b]);
                 }
-                named_sync<2, 256>();
-                if (!half) {
+                stamp(1, 256);
+                // both halves park their partial sums; all 512 threads add and store them (coalesced) after the barrier
+                float* cb = CB + half * 64 * kS64CBLd + tj * kS64CBLd + tk;
 #pragma unroll
-                    for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int b = 0; b < 8; b++)
-                            put(net.w_off[1] + (tj + 16 * a) * 64 + tk + 8 * b, (acc[a][b].x + acc[a][b].y) + CB[(a * 8 + b) * 128 + l7]);
-                } else {
-                    // db1[j] = sum_r G2[j][r]: j = 16*(warp & 3) + (lane & 15), row half = lane >> 4
-                    const int j = 16 * (warp & 3) + (lane & 15), hh = lane >> 4;
-                    const float* gq = G2 + j * TMP + 64 * hh;
-                    float sb = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float4 gv = lds4(gq + 4 * i);
-                        sb += (gv.x + gv.y) + (gv.z + gv.w);
-                    }
-                    sb += __shfl_xor_sync(kFull, sb, 16);
-                    if (hh == 0) put(net.b_off[1] + j, sb);
-                }
+                    for (int b = 0; b < 8; b++) cb[16 * a * kS64CBLd + 8 * b] = acc[a][b].x + acc[a][b].y;
             }
-            __syncthreads();                                   // X0 / src_rows / CB are about to be refilled
+            __syncthreads();                                   // X0 / src_rows are about to be refilled; the dW1 partials are complete
             stamp(13);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int e = t + kS64Threads * i, j = e >> 6, k = e & 63;
+                put(net.w_off[1] + e, CB[j * kS64CBLd + k] + CB[64 * kS64CBLd + j * kS64CBLd + k]);
+            }
             if (have_next) {
                 if (t < TM) src_rows[t] = nxt_src;
                 __syncthreads();
