@@ -102,7 +102,7 @@ int main() {
     CFG(2, 1, 512, false, true, false); CFG(2, 1, 512, true, false, false); CFG(2, 1, 512, true, true, false); CFG(2, 1, 512, true, true, true);
     CFG(2, 2, 512, true, true, false); CFG(2, 2, 256, true, true, false); CFG(2, 2, 256, true, true, true); CFG(4, 1, 512, true, true, false);
     CFG(4, 1, 256, true, true, false); CFG(1, 2, 512, true, true, false); CFG(4, 2, 256, true, true, false); CFG(2, 1, 256, true, true, false);
-    CFG(2, 1, 384, true, true, false); CFG(2, 2, 384, true, true, false);
+    CFG(2, 1, 384, true, true, false); CFG(2, 2, 384, true, true, false); CFG(2, 2, 128, true, true, false); CFG(2, 2, 128, true, true, true);
     run<2, 1, 512, false, true, false>("8x4 tile, 512 thr, math only", out, cyc);
     run<2, 1, 512, true, false, false>("8x4 tile, 512 thr, loads only", out, cyc);
     run<2, 1, 512, true, true, false>("8x4 tile, 512 thr, loads + math", out, cyc);
@@ -113,6 +113,8 @@ int main() {
     run<2, 2, 384, true, true, false>("8x8 tile, 384 thr, loads + math", out, cyc);
     run<2, 2, 256, true, true, false>("8x8 tile, 256 thr, loads + math", out, cyc);
     run<2, 2, 256, true, true, true>("8x8 tile, 256 thr, loads + math, prefetch", out, cyc);
+    run<2, 2, 128, true, true, false>("8x8 tile, 128 thr, loads + math", out, cyc);
+    run<2, 2, 128, true, true, true>("8x8 tile, 128 thr, loads + math, prefetch", out, cyc);
     run<4, 1, 512, true, true, false>("16x4 tile, 512 thr, loads + math", out, cyc);
     run<4, 1, 256, true, true, false>("16x4 tile, 256 thr, loads + math", out, cyc);
     run<1, 2, 512, true, true, false>("4x8 tile, 512 thr, loads + math", out, cyc);
