@@ -176,7 +176,7 @@ class C1(Workload):
         it, nb = self.STEPS // self.CAP, self.CAP // self.MB
         sv = self.SIZES[:-1] + [1]
         flops = it * nb * (self.N_VAL * train_flops(sv, self.MB) + self.N_POL * train_flops(self.SIZES, self.MB))
-        return {"fused_phase_kernel": ("fp32", flops), "sample_action": ("fp32", 2.0 * self.STEPS * mlp_weights(self.SIZES))}
+        return {"fused_phase": ("fp32", flops), "sample_action": ("fp32", 2.0 * self.STEPS * mlp_weights(self.SIZES))}
 
     def teardown(self):
         self.L.free_ppo(self.ppo)
@@ -288,9 +288,9 @@ class C2(Workload):
         red_bytes = (self.N_VAL * nb * (ctas * slab_v * 4 + 32 * mlp_params(sv))
                      + self.N_POL * nb * (ctas * slab_p * 4 + 32 * mlp_params(self.SIZES)))
         roll_flops = 2 * B * mlp_weights(self.SIZES)
-        if any("fused_phase_kernel" in k for k in kernels):          # persistent path: the whole update is one kernel per phase
+        if any("fused_phase" in k for k in kernels):          # persistent path: the whole update is one kernel per phase
             gae_fwd = 2 * 2 * B * mlp_weights(sv)
-            return {"fused_phase_kernel": ("fp32", upd_flops - gae_fwd), "fused_tile64_kernel": ("fp32", gae_fwd),
+            return {"fused_phase": ("fp32", upd_flops - gae_fwd), "fused_tile64_kernel": ("fp32", gae_fwd),
                     "rollout64_kernel": ("fp32", roll_flops), "rollout_kernel": ("fp32", roll_flops),
                     "gae_scan": ("hbm", 22.0 * B), "gae_normalize_kernel": ("hbm", 8.0 * B)}
         return {"fused_tile64_kernel": ("fp32", upd_flops),

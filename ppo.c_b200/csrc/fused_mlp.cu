@@ -1215,20 +1215,24 @@ __global__ void __launch_bounds__(kPhaseMaxThreads, 1) fused_phase_kernel(const 
 // Same outer structure as fused_phase_kernel ([A] tiles, [B] barrier, [C] slice reduce + Adam, [D] barrier, [E] image re-stage)
 // and the same global weight image / slab / optimiser layout, but [A] is written for ONE 128-row tile per CTA with every
 // loop bound, stride and thread mapping a compile-time constant (the generic kernel spends 73 % of its issue slots on
-// address arithmetic, predicates and branches of runtime-shaped loops; ncu, profiles/r02_*):
-//   L0   (K = S)    512 threads x (4 rows x 4 units), weights warp-uniform
-//   L1   (64 x 64)  8 rows x 4 units per thread, split-K halves on the two 256-thread groups, register-prefetched fragments;
-//                   the epilogue also forms the partial dot products of the output layer (y = w2 . h2), so h2 is not re-read
+// address arithmetic, predicates and branches of runtime-shaped loops; ncu, profiles/r02_*), and with 8 x 8 register tiles:
+// measured on B200 (scripts/ubench/tile_loop.cu) an LDS.128 costs ~3.3 cycles of the SM's load/store unit inside such a loop,
+// so the 8 x 4 tile (3 loads per 16 FFMA2) is LSU-bound at 76 % of the FFMA2 rate while 8 x 8 (4 per 32) reaches 85 %.  The
+// 8 x 8 accumulators plus prefetched operands need ~200 registers, hence 256 threads (two warps per sub-partition) per CTA.
+//   L0   (K = S)    256 threads x (4 rows x 8 units), weights warp-uniform
+//   L1   (64 x 64)  8 rows x 8 units per thread, split-K halves on the two 128-thread groups; the epilogue also forms the
+//                   partial dot products of the output layer (y = w2 . h2), so h2 is not re-read
 //   head            128 threads (one per row): loss head on y, dLoss/dy -> gvec
-//   dPre2           512 threads: G2 = g w2 act'(h2), dW2 (warp sums over the 128 rows), db2
-//   bwd l=1         threads 0-255: dX1 -> G1 (8 rows x 4 inputs per thread), then dW0 / db0 from G1 and the input tile;
-//                   threads 256-511: dW1 (4 x 8 outputs per thread, two 64-row halves combined through shared memory), db1
+//   dPre2           G2 = g w2 act'(h2), dW2, db1, db2: eight lanes per hidden unit
+//   bwd l=1         warps 0-3: dX1 -> G1 (8 rows x 8 inputs per thread), then dW0 / db0 from G1 and the input tile, loss sums;
+//                   warps 4-7: dW1 (8 x 8 outputs per thread over a 64-row half; the halves are added by all threads afterwards)
 // One slab per CTA (the generic kernel writes one per 64-row tile slot).  Arithmetic per element is the generic kernel's
 // (fma.rn chains in fixed order, packed two per FFMA2), so results agree with it to rounding of the changed summation splits.
 // ===================================================================================================
-constexpr int kS64TM = 128, kS64TMP = 132, kS64LDW = 68, kS64Threads = 512;
+constexpr int kS64TM = 128, kS64TMP = 132, kS64LDW = 68, kS64Threads = 256;
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void sts4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 template <int ID, int N> __device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" :: "n"(ID), "n"(N) : "memory"); }
 
@@ -1239,7 +1243,7 @@ constexpr int kS64H2 = kS64H1 + 64 * kS64TMP;              // [64][TMP]  hidden 
 constexpr int kS64G2 = kS64H2 + 64 * kS64TMP;              // [64][TMP]  dLoss/d(pre-activation 2)
 constexpr int kS64G1 = kS64G2 + 64 * kS64TMP;              // [64][TMP]  dLoss/d(pre-activation 1); forward: split-K exchange
 constexpr int kS64CBLd = 72;                               // row stride of the dW1 partials: 8 * tj + tk hits 32 distinct banks
-constexpr int kS64CB = kS64G1 + 64 * kS64TMP;              // [2][64][72] dW1 partials of the two 64-row halves; forward: y partials [8][128]
+constexpr int kS64CB = kS64G1 + 64 * kS64TMP;              // [2][64][72] dW1 partials of the two 64-row halves; forward: y partials [4][128]
 constexpr int kS64Red = kS64CB + 2 * 64 * kS64CBLd;        // [2][128]   per-row loss terms | per-row log_std gradient terms
 constexpr int kS64Gv = kS64Red + 256;                      // [128]      dLoss/dy per row
 constexpr int kS64Src = kS64Gv + 128;                      // [128] int  source rows of the tile
@@ -1363,90 +1367,90 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
             const bool have_next = ns < p.n_steps;
             if (have_next && t < TM) nxt_src = src_of(ns, nt, t);
             stamp(3);
-            // ---- L0: H1[j][r] = act(sum_k X0[k][r] W0[k][j] + b0[j]);  rows 4*lane.., units 4*warp..
+            // ---- L0: H1[j][r] = act(sum_k X0[k][r] W0[k][j] + b0[j]);  rows 4*lane.., units 8*warp..
             {
-                float2 acc[2][4];
+                float2 acc[2][8];
 #pragma unroll
-                for (int c = 0; c < 4; c++) { acc[0][c] = make_float2(0.f, 0.f); acc[1][c] = make_float2(0.f, 0.f); }
+                for (int c = 0; c < 8; c++) { acc[0][c] = make_float2(0.f, 0.f); acc[1][c] = make_float2(0.f, 0.f); }
                 for (int k = 0; k < S; k++) {
                     const float4 x = lds4(X0 + k * TMP + 4 * lane);
-                    const float4 w = lds4(W0 + k * LDW + 4 * warp);
-                    const float wv[4] = {w.x, w.y, w.z, w.w};
+                    const float4 w0 = lds4(W0 + k * LDW + 8 * warp), w1 = lds4(W0 + k * LDW + 8 * warp + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
+                    for (int c = 0; c < 8; c++) {
                         acc[0][c] = ffma2(make_float2(x.x, x.y), bcast2(wv[c]), acc[0][c]);
                         acc[1][c] = ffma2(make_float2(x.z, x.w), bcast2(wv[c]), acc[1][c]);
                     }
                 }
-                const float4 b = lds4(B0 + 4 * warp);
-                const float bv[4] = {b.x, b.y, b.z, b.w};
+                const float4 b0 = lds4(B0 + 8 * warp), b1 = lds4(B0 + 8 * warp + 4);
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    sts4(H1 + (4 * warp + c) * TMP + 4 * lane, act_apply(acc[0][c].x + bv[c], ACT), act_apply(acc[0][c].y + bv[c], ACT),
+                for (int c = 0; c < 8; c++)
+                    sts4(H1 + (8 * warp + c) * TMP + 4 * lane, act_apply(acc[0][c].x + bv[c], ACT), act_apply(acc[0][c].y + bv[c], ACT),
                          act_apply(acc[1][c].x + bv[c], ACT), act_apply(acc[1][c].y + bv[c], ACT));
             }
             __syncthreads();
             stamp(8);
-            // ---- L1: split-K halves (group g: k in [32g, 32g + 32)), 8 rows x 4 units per thread
+            // ---- L1: 8 rows x 8 units per thread; split-K halves: group g = warp >> 2 accumulates k in [32g, 32g + 32);
+            // rows {4tr..} U {64+4tr..}, units {4tc..} U {32+4tc..}
             {
-                const int g = t >> 8, lt = t & 255, tr = lt & 15, tc = lt >> 4;
-                float2 acc[4][4];                   // row pairs (4tr, +1), (4tr+2, +3), (64+4tr, +1), (64+4tr+2, +3)
+                const int g = t >> 7, lt = t & 127, tr = lt & 15, tc = lt >> 4;
+                float2 acc[4][8];                   // row pairs (4tr, +1), (4tr+2, +3), (64+4tr, +1), (64+4tr+2, +3)
 #pragma unroll
                 for (int r = 0; r < 4; r++)
 #pragma unroll
-                    for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
+                    for (int c = 0; c < 8; c++) acc[r][c] = make_float2(0.f, 0.f);
                 const float* xp = H1 + 32 * g * TMP + 4 * tr;
                 const float* wp = W1 + 32 * g * LDW + 4 * tc;
-                float4 a0 = lds4(xp), a1 = lds4(xp + 64), w = lds4(wp);
 #pragma unroll 8
                 for (int k = 0; k < 32; k++) {
-                    const float4 c0 = a0, c1 = a1, cw = w;
-                    if (k + 1 < 32) { a0 = lds4(xp + (k + 1) * TMP); a1 = lds4(xp + (k + 1) * TMP + 64); w = lds4(wp + (k + 1) * LDW); }
+                    const float4 c0 = lds4(xp + k * TMP), c1 = lds4(xp + k * TMP + 64);
+                    const float4 w0 = lds4(wp + k * LDW), w1 = lds4(wp + k * LDW + 32);
                     const float2 ap[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
-                    const float wv[4] = {cw.x, cw.y, cw.z, cw.w};
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                     for (int r = 0; r < 4; r++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) acc[r][c] = ffma2(ap[r], bcast2(wv[c]), acc[r][c]);
+                        for (int c = 0; c < 8; c++) acc[r][c] = ffma2(ap[r], bcast2(wv[c]), acc[r][c]);
                 }
                 // group 0 finalises rows 4tr.. (pairs 0,1), group 1 rows 64+4tr.. (pairs 2,3): pass the other quad through G1
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    float* dst = G1 + (4 * tc + c) * TMP + 4 * tr + (g ? 0 : 64);
+                for (int c = 0; c < 8; c++) {
+                    const int col = (c < 4) ? 4 * tc + c : 28 + 4 * tc + c;
+                    float* dst = G1 + col * TMP + 4 * tr + (g ? 0 : 64);
                     if (g) sts4(dst, acc[0][c].x, acc[0][c].y, acc[1][c].x, acc[1][c].y);
                     else sts4(dst, acc[2][c].x, acc[2][c].y, acc[3][c].x, acc[3][c].y);
                 }
                 __syncthreads();
-                const float4 b = lds4(B1 + 4 * tc);
-                const float bv[4] = {b.x, b.y, b.z, b.w};
+                const float4 b0 = lds4(B1 + 4 * tc), b1 = lds4(B1 + 32 + 4 * tc);
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float yp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < 8; c++) {
+                    const int col = (c < 4) ? 4 * tc + c : 28 + 4 * tc + c;
                     const float2 lo = g ? acc[2][c] : acc[0][c], hi = g ? acc[3][c] : acc[1][c];
-                    const float4 q = lds4(G1 + (4 * tc + c) * TMP + 4 * tr + 64 * g);
+                    const float4 q = lds4(G1 + col * TMP + 4 * tr + 64 * g);
                     float o[4] = {lo.x, lo.y, hi.x, hi.y};
                     const float qv[4] = {q.x, q.y, q.z, q.w};
-                    const float w2 = W2[(4 * tc + c) * 8];
+                    const float w2 = W2[col * 8];
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         o[r] = g ? qv[r] + o[r] : o[r] + qv[r];            // lower-k partial + upper-k partial
                         o[r] = act_apply(o[r] + bv[c], ACT);
                         yp[r] = fmaf(o[r], w2, yp[r]);
                     }
-                    sts4(H2 + (4 * tc + c) * TMP + 4 * tr + 64 * g, o[0], o[1], o[2], o[3]);
+                    sts4(H2 + col * TMP + 4 * tr + 64 * g, o[0], o[1], o[2], o[3]);
                 }
-                // y partials: the two unit groups of a warp meet through one shuffle; the 8 warps of a group through CB[8][128]
+                // y partials: the two unit groups of a warp meet through one shuffle; the 4 warps of a group through CB[4][128]
 #pragma unroll
                 for (int r = 0; r < 4; r++) yp[r] += __shfl_xor_sync(kFull, yp[r], 16);
-                if (lane < 16) sts4(CB + ((warp & 7) * TM) + 64 * g + 4 * tr, yp[0], yp[1], yp[2], yp[3]);
+                if (lane < 16) sts4(CB + ((warp & 3) * TM) + 64 * g + 4 * tr, yp[0], yp[1], yp[2], yp[3]);
             }
             __syncthreads();
             stamp(9);
             // ---- head: one thread per row (src/loss.cu:5-23 | src/policy.cu:67-111 + src/ppo.cu:89-98)
             if (t < TM) {
-                float part = CB[t];
-#pragma unroll
-                for (int w8 = 1; w8 < 8; w8++) part += CB[w8 * TM + t];
+                const float part = (CB[t] + CB[TM + t]) + (CB[2 * TM + t] + CB[3 * TM + t]);
                 const float y = act_apply(part + B2[0], out_act);
                 float loss_term = 0.f, gout = 0.f, gls = 0.f;
                 if (my_src >= 0) {
@@ -1471,95 +1475,104 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                     }
                 }
                 gvec[t] = act_grad(y, gout, out_act);
-                red[t] = loss_term;                            // summed (fixed order) in the tail of the dX group, off this chain
+                red[t] = loss_term;                            // summed (fixed order) in the tail of the dX warps, off this chain
                 red[128 + t] = gls;
             }
             __syncthreads();
             stamp(10);
             // ---- dPre2: G2[k][r] = g_r w2[k] act'(H2[k][r]); dW2[k] = sum_r g_r H2[k][r]; db1[k] = sum_r G2[k][r]; db2 = sum_r g_r.
-            // Eight lanes per hidden unit k = t >> 3; lane l8 takes the row quads l8, l8 + 8, l8 + 16, l8 + 24 (a quarter-warp reads 128
-            // contiguous bytes); the eight partial sums of a unit meet through three shuffles.
+            // Eight lanes per hidden unit (k = (t >> 3) and 32 + (t >> 3)); lane l8 takes the row quads l8, l8 + 8, l8 + 16, l8 + 24
+            // (a quarter-warp reads 128 contiguous bytes); the eight partial sums of a unit meet through three shuffles.
             {
-                const int k = t >> 3, l8 = t & 7;
-                const float w2 = W2[k * 8];
-                float pw = 0.f, pb = 0.f, pg = 0.f;
+                const int l8 = t & 7;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int r0 = 4 * (l8 + 8 * i);
-                    const float4 h = lds4(H2 + k * TMP + r0);
-                    const float4 g4 = lds4(gvec + r0);
-                    const float d0 = act_grad(h.x, __fmul_rn(g4.x, w2), ACT), d1 = act_grad(h.y, __fmul_rn(g4.y, w2), ACT);
-                    const float d2 = act_grad(h.z, __fmul_rn(g4.z, w2), ACT), d3 = act_grad(h.w, __fmul_rn(g4.w, w2), ACT);
-                    sts4(G2 + k * TMP + r0, d0, d1, d2, d3);
-                    pw = fmaf(g4.w, h.w, fmaf(g4.z, h.z, fmaf(g4.y, h.y, fmaf(g4.x, h.x, pw))));
-                    pb += (d0 + d1) + (d2 + d3);
-                    pg += (g4.x + g4.y) + (g4.z + g4.w);
-                }
+                for (int h = 0; h < 2; h++) {
+                    const int k = (t >> 3) + 32 * h;
+                    const float w2 = W2[k * 8];
+                    float pw = 0.f, pb = 0.f, pg = 0.f;
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    pw += __shfl_xor_sync(kFull, pw, o);
-                    pb += __shfl_xor_sync(kFull, pb, o);
-                    pg += __shfl_xor_sync(kFull, pg, o);
-                }
-                if (l8 == 0) {
-                    put(net.w_off[2] + k, pw);
-                    put(net.b_off[1] + k, pb);
-                    if (k == 0) put(net.b_off[2], pg);
+                    for (int i = 0; i < 4; i++) {
+                        const int r0 = 4 * (l8 + 8 * i);
+                        const float4 hv = lds4(H2 + k * TMP + r0);
+                        const float4 g4 = lds4(gvec + r0);
+                        const float d0 = act_grad(hv.x, __fmul_rn(g4.x, w2), ACT), d1 = act_grad(hv.y, __fmul_rn(g4.y, w2), ACT);
+                        const float d2 = act_grad(hv.z, __fmul_rn(g4.z, w2), ACT), d3 = act_grad(hv.w, __fmul_rn(g4.w, w2), ACT);
+                        sts4(G2 + k * TMP + r0, d0, d1, d2, d3);
+                        pw = fmaf(g4.w, hv.w, fmaf(g4.z, hv.z, fmaf(g4.y, hv.y, fmaf(g4.x, hv.x, pw))));
+                        pb += (d0 + d1) + (d2 + d3);
+                        pg += (g4.x + g4.y) + (g4.z + g4.w);
+                    }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        pw += __shfl_xor_sync(kFull, pw, o);
+                        pb += __shfl_xor_sync(kFull, pb, o);
+                        pg += __shfl_xor_sync(kFull, pg, o);
+                    }
+                    if (l8 == 0) {
+                        put(net.w_off[2] + k, pw);
+                        put(net.b_off[1] + k, pb);
+                        if (k == 0) put(net.b_off[2], pg);
+                    }
                 }
             }
             __syncthreads();
             stamp(11);
             // ---- backward of layer 1 (and layer 0 behind it)
-            if (t < 256) {
-                // dX1: G1[k][r] = (sum_j G2[j][r] W1[k][j]) act'(H1[k][r]);  k = tc + 16c, rows 4tr.. and 64+4tr..
+            if (t < 128) {
+                // dX1: G1[k][r] = (sum_j G2[j][r] W1[k][j]) act'(H1[k][r]);  k = tc + 8c, rows 4tr.. and 64+4tr..
                 const int tr = t & 15, tc = t >> 4;
-                float2 acc[4][4];
+                {
+                    float2 acc[4][8];
 #pragma unroll
-                for (int r = 0; r < 4; r++)
+                    for (int r = 0; r < 4; r++)
 #pragma unroll
-                    for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
-                const float* wrow = W1 + tc * LDW;
-                const float* gp = G2 + 4 * tr;
-#pragma unroll 2
-                for (int j0 = 0; j0 < 64; j0 += 4) {
-                    float wv[4][4];
+                        for (int c = 0; c < 8; c++) acc[r][c] = make_float2(0.f, 0.f);
+                    const float* wrow = W1 + tc * LDW;
+                    const float* gp = G2 + 4 * tr;
+#pragma unroll 4
+                    for (int j0 = 0; j0 < 64; j0 += 2) {
+                        float2 wv[8];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const float4 w = lds4(wrow + 16 * c * LDW + j0);
-                        wv[c][0] = w.x; wv[c][1] = w.y; wv[c][2] = w.z; wv[c][3] = w.w;
+                        for (int c = 0; c < 8; c++) wv[c] = lds2(wrow + 8 * c * LDW + j0);
+                        {
+                            const float4 g0 = lds4(gp + j0 * TMP), g1 = lds4(gp + j0 * TMP + 64);
+                            const float2 gq[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+#pragma unroll
+                                for (int c = 0; c < 8; c++) acc[r][c] = ffma2(gq[r], bcast2(wv[c].x), acc[r][c]);
+                        }
+                        {
+                            const float4 g0 = lds4(gp + (j0 + 1) * TMP), g1 = lds4(gp + (j0 + 1) * TMP + 64);
+                            const float2 gq[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+#pragma unroll
+                                for (int c = 0; c < 8; c++) acc[r][c] = ffma2(gq[r], bcast2(wv[c].y), acc[r][c]);
+                        }
                     }
 #pragma unroll
-                    for (int jj = 0; jj < 4; jj++) {
-                        const float4 g0 = lds4(gp + (j0 + jj) * TMP);
-                        const float4 g1 = lds4(gp + (j0 + jj) * TMP + 64);
-                        const float2 gq[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
-#pragma unroll
-                        for (int r = 0; r < 4; r++)
-#pragma unroll
-                            for (int c = 0; c < 4; c++) acc[r][c] = ffma2(gq[r], bcast2(wv[c][jj]), acc[r][c]);
+                    for (int c = 0; c < 8; c++) {
+                        const int k = tc + 8 * c;
+                        const float4 h0 = lds4(H1 + k * TMP + 4 * tr), h1 = lds4(H1 + k * TMP + 4 * tr + 64);
+                        sts4(G1 + k * TMP + 4 * tr, act_grad(h0.x, acc[0][c].x, ACT), act_grad(h0.y, acc[0][c].y, ACT),
+                             act_grad(h0.z, acc[1][c].x, ACT), act_grad(h0.w, acc[1][c].y, ACT));
+                        sts4(G1 + k * TMP + 4 * tr + 64, act_grad(h1.x, acc[2][c].x, ACT), act_grad(h1.y, acc[2][c].y, ACT),
+                             act_grad(h1.z, acc[3][c].x, ACT), act_grad(h1.w, acc[3][c].y, ACT));
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int k = tc + 16 * c;
-                    const float4 h0 = lds4(H1 + k * TMP + 4 * tr), h1 = lds4(H1 + k * TMP + 4 * tr + 64);
-                    sts4(G1 + k * TMP + 4 * tr, act_grad(h0.x, acc[0][c].x, ACT), act_grad(h0.y, acc[0][c].y, ACT),
-                         act_grad(h0.z, acc[1][c].x, ACT), act_grad(h0.w, acc[1][c].y, ACT));
-                    sts4(G1 + k * TMP + 4 * tr + 64, act_grad(h1.x, acc[2][c].x, ACT), act_grad(h1.y, acc[2][c].y, ACT),
-                         act_grad(h1.z, acc[3][c].x, ACT), act_grad(h1.w, acc[3][c].y, ACT));
                 }
                 stamp(14);
-                named_sync<1, 256>();
-                // dW0[j][k] = sum_r G1[j][r] X0[k][r], db0[j] = sum_r G1[j][r]: j = 8*warp + (lane & 7), row quarter = lane >> 3
+                named_sync<1, 128>();
+                // dW0[j][k] = sum_r G1[j][r] X0[k][r], db0[j] = sum_r G1[j][r]: j = 16*warp + (lane & 15), row half = lane >> 4
                 {
-                    const int j = 8 * warp + (lane & 7), rq = lane >> 3;
+                    const int j = 16 * warp + (lane & 15), hh = lane >> 4;
                     float accw[8], accb = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; k++) accw[k] = 0.f;
-                    const float* gq = G1 + j * TMP + 32 * rq;
-                    const float* xq = X0 + 32 * rq;
-#pragma unroll 2
-                    for (int i = 0; i < 8; i++) {
+                    const float* gq = G1 + j * TMP + 64 * hh;
+                    const float* xq = X0 + 64 * hh;
+#pragma unroll 4
+                    for (int i = 0; i < 16; i++) {
                         const float4 gv = lds4(gq + 4 * i);
                         accb += (gv.x + gv.y) + (gv.z + gv.w);
 #pragma unroll
@@ -1569,15 +1582,11 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                                 accw[k] = fmaf(gv.w, xv.w, fmaf(gv.z, xv.z, fmaf(gv.y, xv.y, fmaf(gv.x, xv.x, accw[k]))));
                             }
                     }
-                    accb += __shfl_xor_sync(kFull, accb, 8);
                     accb += __shfl_xor_sync(kFull, accb, 16);
 #pragma unroll
                     for (int k = 0; k < 8; k++)
-                        if (k < S) {
-                            accw[k] += __shfl_xor_sync(kFull, accw[k], 8);
-                            accw[k] += __shfl_xor_sync(kFull, accw[k], 16);
-                        }
-                    if (rq == 0) {
+                        if (k < S) accw[k] += __shfl_xor_sync(kFull, accw[k], 16);
+                    if (hh == 0) {
                         put(net.b_off[0] + j, accb);
 #pragma unroll
                         for (int k = 0; k < 8; k++)
@@ -1592,39 +1601,39 @@ __global__ void __launch_bounds__(kS64Threads, 1) fused_phase_spec64_kernel(cons
                 }
                 stamp(15);
             } else {
-                // dW1[j][k] = sum_r G2[j][r] H1[k][r]: j = tj + 16a, k = tk + 8b, rows [64*half, 64*half + 64)
-                const int lt = t - 256, half = lt >> 7, l7 = lt & 127, tk = l7 & 7, tj = l7 >> 3;
-                float2 acc[4][8];
+                // dW1[j][k] = sum_r G2[j][r] H1[k][r]: j = tj + 8a, k = tk + 8b, rows [64*half, 64*half + 64); two rows per step
+                const int lt = t - 128, half = lt >> 6, l6 = lt & 63, tk = l6 & 7, tj = l6 >> 3;
+                float2 acc[8][8];                   // (sum over even rows, sum over odd rows)
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 8; a++)
 #pragma unroll
                     for (int b = 0; b < 8; b++) acc[a][b] = make_float2(0.f, 0.f);
                 const float* gb = G2 + tj * TMP + 64 * half;
                 const float* xb = H1 + tk * TMP + 64 * half;
-#pragma unroll 4
-                for (int r = 0; r < 64; r += 2) {          // two rows per step (LDS.64): operands fit beside the 64 accumulators,
-                    float2 g[4], x[8];                      // so the loads of the next steps can be hoisted above this step's math
+#pragma unroll 2
+                for (int r = 0; r < 64; r += 2) {
+                    float2 g[8], x[8];
 #pragma unroll
-                    for (int a = 0; a < 4; a++) g[a] = *reinterpret_cast<const float2*>(gb + 16 * a * TMP + r);
+                    for (int a = 0; a < 8; a++) g[a] = lds2(gb + 8 * a * TMP + r);
 #pragma unroll
-                    for (int b = 0; b < 8; b++) x[b] = *reinterpret_cast<const float2*>(xb + 8 * b * TMP + r);
+                    for (int b = 0; b < 8; b++) x[b] = lds2(xb + 8 * b * TMP + r);
 #pragma unroll
-                    for (int a = 0; a < 4; a++)
+                    for (int a = 0; a < 8; a++)
 #pragma unroll
                         for (int b = 0; b < 8; b++) acc[a][b] = ffma2(g[a], x[b], acc[a][b]);
                 }
-                stamp(1, 256);
-                // both halves park their partial sums; all 512 threads add and store them (coalesced) after the barrier
+                stamp(1, 128);
+                // both halves park their partial sums; all threads add and store them (coalesced) after the barrier
                 float* cb = CB + half * 64 * kS64CBLd + tj * kS64CBLd + tk;
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 8; a++)
 #pragma unroll
-                    for (int b = 0; b < 8; b++) cb[16 * a * kS64CBLd + 8 * b] = acc[a][b].x + acc[a][b].y;
+                    for (int b = 0; b < 8; b++) cb[8 * a * kS64CBLd + 8 * b] = acc[a][b].x + acc[a][b].y;
             }
             __syncthreads();                                   // X0 / src_rows are about to be refilled; the dW1 partials are complete
             stamp(13);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < 16; i++) {
                 const int e = t + kS64Threads * i, j = e >> 6, k = e & 63;
                 put(net.w_off[1] + e, CB[j * kS64CBLd + k] + CB[64 * kS64CBLd + j * kS64CBLd + k]);
             }

@@ -31,8 +31,9 @@ for name, a, b in [("  fwd L0", 8, 3), ("  fwd L1", 9, 8), ("  last layer + head
     d = us(a, b)
     print("%-34s median %.2f us  min %.2f  max %.2f" % (name, np.median(d), d.min(), d.max()))
 if t[:, 10].any():      # specialised kernel: finer stamps
-    for name, a, b in [("  spec64: head (128 thr)", 10, 9), ("  spec64: dPre2 + dW2", 11, 10), ("  spec64: dX1 loop + epilogue", 14, 11), ("  spec64: dW0/db0 + loss sums (dX group)", 15, 14),
-                       ("  spec64: dW1 loop", 1, 11), ("  spec64: bwd start -> end barrier", 13, 11), ("  spec64: dW1 add + store", 12, 13)]:
+    for name, a, b in [("  spec64: head (128 thr)", 10, 9), ("  spec64: dPre2 + dW2 + db1", 11, 10), ("  spec64: dX1 loop + epilogue (warps 0-3)", 14, 11),
+                       ("  spec64: dW0/db0 + loss sums (warps 0-3)", 15, 14), ("  spec64: dW1 loop (warps 4-7)", 1, 11),
+                       ("  spec64: bwd start -> end barrier", 13, 11), ("  spec64: dW1 add + store", 12, 13)]:
         d = us(a, b)
         print("%-34s median %.2f us  min %.2f  max %.2f" % (name, np.median(d), d.min(), d.max()))
 print("step period estimate (t6 last - t7 prev): median %.2f us" % np.median(us(6, 7)))
