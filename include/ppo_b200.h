@@ -409,12 +409,19 @@ void ppo_b200_set_permutation_mode(PPO* ppo, int mode, unsigned long long seed);
 void ppo_b200_set_kernel_path(int path);
 /* matmul precision of dense layers whose in/out widths are >= 64 and batch >= 128:
  * 0 = fp32 FFMA (default; 1e-5 tolerance), 1 = TF32 tcgen05 tensor cores with fp32 accumulation
- * (wide-MLP configs; tolerance ~1e-3, stated separately).  Env PPO_B200_TF32=1 sets the default. */
+ * (wide-MLP configs; tolerance ~1e-3, stated separately), 2 = BF16 operands (tcgen05 kind::f16, fp32 accumulation in TMEM;
+ * layers additionally need widths that are multiples of 8; tolerance ~1e-2, stated separately).  Parameters, gradients and
+ * the optimiser stay fp32 in every mode.  Env PPO_B200_TF32=1 / 2 sets the default. */
 void ppo_b200_set_matmul_precision(int mode);
 /* raw tensor-core layer kernels (tests/bench): mode 0 forward (aux = bias), 1 backward-input
  * (aux = post-activation input), 2 backward-weights (out = `splits` slabs of l*n floats). */
 void ppo_b200_tc_linear(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l,
                         int act, int splits);
+/* the same three contractions with BF16 operands: a / b are converted to bf16 scratch copies first (skip_convert: reuse the
+ * copies of the previous call; convert_only: stop after the conversion), out16 (may be NULL) receives the bf16 shadow of the
+ * fp32 output of modes 0 and 1. */
+void ppo_b200_tc_linear_bf16(int mode, float* out, void* out16, const float* a, const float* b, const float* aux, int m, int n, int l,
+                             int act, int splits, int convert_only, int skip_convert);
 /* Running observation normalisation for the device rollout (new capability; the reference only has the
  * Welford merge, include/welford_var.h:33-40,58-66, applied to advantages).  The rollout kernel keeps a
  * Welford triple of the RAW observations per lane, merges them per CTA, and a one-thread-per-feature kernel

@@ -597,7 +597,7 @@ int choose_splits(int m, size_t param_count) {
 
 static int g_matmul_precision = -1;
 int matmul_precision() {
-    if (g_matmul_precision < 0) { const char* e = getenv("PPO_B200_TF32"); g_matmul_precision = (e && e[0] == '1') ? 1 : 0; }
+    if (g_matmul_precision < 0) { const char* e = getenv("PPO_B200_TF32"); g_matmul_precision = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0; }
     return g_matmul_precision;
 }
 static bool use_tc(int m, int n, int l, const void* a, const void* b, int lda, int ldb) {
@@ -647,6 +647,14 @@ void linear_backward_input(float* gx, const float* g, const float* W, const floa
     }
     dim3 grid(div_up(n, kBN), div_up(m, kBM), 1);
     B200_LAUNCH(sgemm_kernel<kBwdInput>, grid, 256, 0, a);
+}
+
+// bias gradients of one layer as `splits` slabs: column sums of g over the rows of each split
+void launch_colsum(float* gb_part, size_t stride, int splits, const float* g, int m, int l) {
+    int rows = div_up(m, splits);
+    rows = div_up(rows, 32) * 32;
+    dim3 grid2(div_up(l, 32), splits, 1);
+    B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
 }
 
 void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int splits, const float* g,
@@ -717,7 +725,7 @@ using namespace b200;
 
 extern "C" {
 
-void ppo_b200_set_matmul_precision(int mode) { g_matmul_precision = mode ? 1 : 0; }
+void ppo_b200_set_matmul_precision(int mode) { g_matmul_precision = mode == 2 ? 2 : mode ? 1 : 0; }
 
 // include/mat_mul.h:19-20 (device pointers; handle ignored)
 void mat_mul_cuda(cublasHandle_t handle, float* out, float* x, float* weight, float* bias, int m, int n, int l) {

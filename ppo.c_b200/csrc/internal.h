@@ -76,7 +76,15 @@ void tc_linear_forward(float* y, const float* x, const float* W, const float* b,
 void tc_linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev);
 void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l);
 void tc_round_copy(const float* src, float* dst, size_t n);   // RNA-rounded TF32 shadow of a weight arena
-int matmul_precision();   // 0 fp32 FFMA (default), 1 TF32 tcgen05 for layers with n, l >= 64
+int matmul_precision();   // 0 fp32 FFMA (default), 1 TF32 tcgen05 for layers with n, l >= 64, 2 BF16 tcgen05 (widths % 8 == 0)
+// bf16 operand mode (tc_gemm.cu): shadows are __nv_bfloat16 arrays, passed as void* between translation units
+bool tc_bf16_shape_ok(int m, int n, int l);
+void tc_linear_forward_bf16_v(float* y, void* y16, const void* x16, const void* W16, const float* b, int m, int n, int l, int act);
+void tc_linear_backward_input_bf16_v(float* gx, void* gx16, const void* g16, const void* Wt16, const float* xin, int m, int n, int l, int act_prev);
+void tc_linear_backward_weights_bf16_v(float* gW_part, size_t stride, int splits, const void* g16, const void* x16, int m, int n, int l);
+void tc_to_bf16_v(const float* src, void* dst, size_t n);
+void tc_weights_bf16_v(const float* W, void* W16, void* Wt16, int l, int n);
+void launch_colsum(float* gb_part, size_t stride, int splits, const float* g, int m, int l);
 
 // ---- nn.cu ------------------------------------------------------------------------------------
 struct NetDev {               // device-side view of one NeuralNetwork (side table keyed by pointer)
@@ -100,6 +108,10 @@ struct NetDev {               // device-side view of one NeuralNetwork (side tab
     int last_splits = 1;
     int last_m = 0;
     float* params_tf32 = nullptr;   // RNA-rounded shadow of `params` read by the tensor-core layers
+    // bf16 operand mode: per-layer weight copies W16 [out][in] | Wt16 [in][out] and shadows of the activations / gradients
+    void* params_bf16 = nullptr;    // 2 * param_count bf16: [W16 of every layer at w_off | Wt16 of every layer at param_count + w_off]
+    std::vector<void*> a16, gx16;   // a16[i] : bf16 [cap][sizes[i]] (null until needed)
+    std::vector<int> a16_cap, gx16_cap;
     float* image = nullptr;      // pre-transposed weight image staged by the fused kernels (fused_mlp.cu)
     int image_floats = 0;
     bool image_dirty = true;     // set by every writer of `params` other than fused_reduce_adam_kernel

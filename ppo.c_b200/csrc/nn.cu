@@ -88,6 +88,24 @@ static void ensure_bwd_capacity(NeuralNetwork* nn, NetDev* nd, int m) {
     nd->cap_bwd = cap;
 }
 
+// ---- bf16 operand mode helpers ----------------------------------------------------------------------------
+static bool bf16_layer(const NetDev* nd, int i, int m) { return tc_bf16_shape_ok(m, nd->sizes[i], nd->sizes[i + 1]); }
+// element offset of layer i's W16 inside params_bf16 (16-byte aligned); Wt16 follows at + bf16_total(nd)
+static size_t bf16_w_off(const NetDev* nd, int i) {
+    size_t off = 0;
+    for (int j = 0; j < i; j++) off = ((off + 7) & ~size_t(7)) + (size_t)nd->sizes[j] * nd->sizes[j + 1];
+    return (off + 7) & ~size_t(7);
+}
+static size_t bf16_total(const NetDev* nd) { return (bf16_w_off(nd, nd->num_layers - 1) + 7) & ~size_t(7); }
+static void ensure_shadow(std::vector<void*>& v, std::vector<int>& cap, int i, int m, int width) {
+    if ((int)v.size() <= i) { v.resize(i + 1, nullptr); cap.resize(i + 1, 0); }
+    if (cap[i] >= m) return;
+    CUDA_CHECK(cudaStreamSynchronize(stream()));
+    if (v[i]) CUDA_CHECK(cudaFree(v[i]));
+    cap[i] = m + m / 8;
+    CUDA_CHECK(cudaMalloc(&v[i], (size_t)cap[i] * width * 2 + 64));
+}
+
 void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input) {
     NetDev* nd = net_dev(nn);
     ensure_fwd_capacity(nn, nd, m);
@@ -115,9 +133,35 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
         tc_round_copy(nd->params, nd->params_tf32, nd->param_count);
         wsrc = nd->params_tf32;
     }
-    for (int i = 0; i < L; i++)
-        linear_forward(nd->a[i + 1], nd->a[i], wsrc + nd->w_off[i], nd->params + nd->b_off[i], m,
-                       nd->sizes[i], nd->sizes[i + 1], nd->acts[i]);
+    if (matmul_precision() == 2) {
+        // BF16 mode: weight copies W16 | Wt16 refreshed per forward (= once per optimiser step); a tensor-core layer reads the
+        // bf16 shadow of its input (written by the previous tensor-core layer's epilogue, else converted here) and writes the
+        // shadow of its output when the next layer wants it
+        const size_t tot16 = bf16_total(nd);
+        if (!nd->params_bf16) CUDA_CHECK(cudaMalloc(&nd->params_bf16, 2 * tot16 * 2 + 64));
+        char* w16 = static_cast<char*>(nd->params_bf16);
+        bool have16 = false;          // a16[i] holds the shadow of a[i]
+        for (int i = 0; i < L; i++) {
+            const int n = nd->sizes[i], l = nd->sizes[i + 1];
+            if (bf16_layer(nd, i, m)) {
+                const size_t wo = bf16_w_off(nd, i);
+                tc_weights_bf16_v(nd->params + nd->w_off[i], w16 + 2 * wo, w16 + 2 * (tot16 + wo), l, n);
+                if (!have16) { ensure_shadow(nd->a16, nd->a16_cap, i, m, n); tc_to_bf16_v(nd->a[i], nd->a16[i], (size_t)m * n); }
+                const bool next16 = i + 1 < L && bf16_layer(nd, i + 1, m);
+                if (next16) ensure_shadow(nd->a16, nd->a16_cap, i + 1, m, l);
+                tc_linear_forward_bf16_v(nd->a[i + 1], next16 ? nd->a16[i + 1] : nullptr, nd->a16[i], w16 + 2 * wo,
+                                         nd->params + nd->b_off[i], m, n, l, nd->acts[i]);
+                have16 = next16;
+            } else {
+                linear_forward(nd->a[i + 1], nd->a[i], nd->params + nd->w_off[i], nd->params + nd->b_off[i], m, n, l, nd->acts[i]);
+                have16 = false;
+            }
+        }
+    } else {
+        for (int i = 0; i < L; i++)
+            linear_forward(nd->a[i + 1], nd->a[i], wsrc + nd->w_off[i], nd->params + nd->b_off[i], m,
+                           nd->sizes[i], nd->sizes[i + 1], nd->acts[i]);
+    }
     nn->cache_m_forward = m;
     nd->last_m = m;
     nn->d_output = nd->a[L];
@@ -129,7 +173,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
     ensure_bwd_capacity(nn, nd, m);
     const int L = nn->num_layers - 1;
     int splits = choose_splits(m, nd->param_count);
-    if (matmul_precision() == 1 && m >= 128) {
+    if (matmul_precision() >= 1 && m >= 128) {
         // tensor-core dW: one 128x256 tile per CTA, so split-K only until ~2 CTAs per SM exist for the widest
         // layer; more slabs would only add slab traffic (each slab is a full copy of the gradient).
         int tiles = 0;
@@ -152,6 +196,34 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         activation_grad_inplace(nd->a[L], nd->gx[L], (long long)m * nd->sizes[L], nd->acts[L - 1]);
         g = nd->gx[L];
     }
+    if (matmul_precision() == 2) {
+        char* w16 = static_cast<char*>(nd->params_bf16);
+        const size_t tot16 = bf16_total(nd);
+        bool have16 = false;          // gx16[i + 1] holds the shadow of g (the gradient wrt a[i + 1])
+        for (int i = L - 1; i >= 0; i--) {
+            const int n = nd->sizes[i], l = nd->sizes[i + 1];
+            if (w16 && bf16_layer(nd, i, m) && (int)nd->a16.size() > i && nd->a16[i]) {
+                if (!have16) { ensure_shadow(nd->gx16, nd->gx16_cap, i + 1, m, l); tc_to_bf16_v(g, nd->gx16[i + 1], (size_t)m * l); }
+                tc_linear_backward_weights_bf16_v(nd->partials + nd->w_off[i], nd->slab_stride(), splits, nd->gx16[i + 1], nd->a16[i], m, n, l);
+                launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
+                if (i > 0) {
+                    const bool next16 = bf16_layer(nd, i - 1, m) && (int)nd->a16.size() > i - 1 && nd->a16[i - 1];
+                    if (next16) ensure_shadow(nd->gx16, nd->gx16_cap, i, m, n);
+                    tc_linear_backward_input_bf16_v(nd->gx[i], next16 ? nd->gx16[i] : nullptr, nd->gx16[i + 1],
+                                                    w16 + 2 * (tot16 + bf16_w_off(nd, i)), nd->a[i], m, n, l, nd->acts[i - 1]);
+                    g = nd->gx[i];
+                    have16 = next16;
+                }
+            } else {
+                linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, nd->a[i], m, n, l);
+                if (i > 0) {
+                    linear_backward_input(nd->gx[i], g, nd->params + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
+                    g = nd->gx[i];
+                }
+                have16 = false;
+            }
+        }
+    } else
     for (int i = L - 1; i >= 0; i--) {
         const int n = nd->sizes[i], l = nd->sizes[i + 1];
         linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->slab_stride(), splits, g,
@@ -236,6 +308,9 @@ void free_neural_network(NeuralNetwork* nn) {
         if (nd->partials) CUDA_CHECK(cudaFree(nd->partials));
         if (nd->image) CUDA_CHECK(cudaFree(nd->image));
         if (nd->params_tf32) CUDA_CHECK(cudaFree(nd->params_tf32));
+        if (nd->params_bf16) CUDA_CHECK(cudaFree(nd->params_bf16));
+        for (void* q : nd->a16) if (q) CUDA_CHECK(cudaFree(q));
+        for (void* q : nd->gx16) if (q) CUDA_CHECK(cudaFree(q));
         delete nd;
         g_nets.erase(it);
     }

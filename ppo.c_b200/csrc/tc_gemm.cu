@@ -13,15 +13,22 @@
 // accumulation is fp32 in TMEM.  Tolerance for this path is stated separately from the fp32 kernels
 // (north-star): ~1e-3 norm-wise on layer outputs / gradients, measured in tests/test_gpu_tc.py.
 //
-// Kernel anatomy (Blackwell guide "canonical GEMM"): 192 threads =
+// BF16 operand mode (kind::f16, bf16 x bf16 -> fp32 in TMEM; PPO_B200_TF32=2 / ppo_b200_set_matmul_precision(2)): the same
+// kernel template with 2-byte operands.  Activations, gradients and weights keep their fp32 arrays (the rest of the library
+// and the optimiser read those); every tensor-core layer additionally writes a bf16 shadow of its output from the epilogue
+// and reads bf16 shadows of its inputs, so operand traffic halves and the MMA rate doubles.  dX reads a pre-transposed bf16
+// copy of the weights (K-major B), dW reads the bf16 shadows MN-major (SWIZZLE_128B, 64-element chunks, 8-row atoms).
+//
+// Kernel anatomy (Blackwell guide "canonical GEMM"): persistent CTAs (one per SM, clusters of 2), 64 + 32 * 8 threads =
 //   warp 0  TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage shared-memory ring,
-//                          mbarrier expect_tx / complete_tx
-//   warp 1  MMA issuer     one elected lane issues tcgen05.mma (M=128, N=BN, K=8) from shared-memory
-//                          descriptors; tcgen05.commit releases ring slots and publishes the accumulator
-//   warps 2-5 epilogue     tcgen05.ld 32x32b.x32 TMEM -> registers, fused bias+activation /
-//                          activation-derivative mask, 128-byte row stores
-// One 128 x BN output tile per CTA, fp32 accumulator = BN TMEM columns.
+//                          mbarrier expect_tx / complete_tx; the B tile of a cluster is loaded half-and-half and multicast
+//   warp 1  MMA issuer     one elected lane issues tcgen05.mma (M=128, N=256, K=8 tf32 / 16 bf16) from shared-memory
+//                          descriptors; tcgen05.commit releases ring slots (in both CTAs) and publishes the accumulator
+//   warps 2-9 epilogue     tcgen05.ld 32x32b.x32 TMEM -> registers, fused bias+activation / activation-derivative mask,
+//                          128-byte row stores (+ the packed bf16 shadow)
+// Two TMEM accumulator buffers (2 x 256 columns = all of TMEM): the epilogue of tile i overlaps the MMAs of tile i + 1.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -30,9 +37,17 @@ namespace b200 {
 
 constexpr int kTcBM = 128;
 constexpr int kTcBKBytes = 128;            // one 128B swizzle row per k-block
-constexpr int kTcBK = kTcBKBytes / 4;      // 32 tf32 elements
-constexpr int kTcUmmaK = 8;                // tf32: 32 bytes
 constexpr int kTcStages = 4;
+// element-type constants: BF = false -> tf32 operands read from fp32 words, BF = true -> bf16 operands
+template <bool BF> struct TcElem {
+    static constexpr int kSize = BF ? 2 : 4;
+    static constexpr int kBK = kTcBKBytes / kSize;             // elements per k-block: 32 tf32 / 64 bf16
+    static constexpr int kUmmaK = 32 / kSize;                  // one MMA consumes 32 bytes of K: 8 tf32 / 16 bf16
+    static constexpr int kMnChunk = kTcBKBytes / kSize;        // MN-major: elements per 128-byte chunk
+    static constexpr uint32_t kMnSbo = BF ? 1024u : 512u;      // MN-major atom: 8 k-rows (SWIZZLE_128B) / 4 k-rows (.._BASE32B)
+    static constexpr uint32_t kMnLayout = BF ? 2u : 1u;
+    static constexpr uint32_t kFormat = BF ? 1u : 2u;          // instruction descriptor a/b format: BF16 = 1, TF32 = 2
+};
 constexpr int kTcEpiWarps = 8;               // two warps per TMEM lane quadrant, each takes half of the columns
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 
@@ -40,6 +55,7 @@ enum TcEpilogue { kTcFwd = 0, kTcDx = 1, kTcDw = 2 };
 
 struct TcArgs {
     float* C;
+    __nv_bfloat16* C16;     // optional bf16 shadow of C (kTcFwd / kTcDx), same leading dimension
     int M, N, K;            // GEMM extents (output M x N, reduction K)
     int ldc;
     const float* bias;      // kTcFwd
@@ -89,12 +105,20 @@ __device__ __forceinline__ void tc_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tc_umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+template <bool BF>
+__device__ __forceinline__ void tc_umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (BF)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s_u32(bar)) : "memory");
@@ -141,14 +165,16 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict
 // shared memories, which halves the B traffic out of L2 (a 128x256 TF32 tile pulls 1.5 MB of operands through L2
 // per 67 MFLOP - the kernel is L2-bandwidth bound, not tensor bound).  A ring slot may be refilled only after BOTH
 // CTAs' MMAs released it, so tcgen05.commit arrives on the empty barrier of both CTAs (count = CL).
-template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+    using E = TcElem<BF>;
+    constexpr int kTcBK = E::kBK, kTcUmmaK = E::kUmmaK;
     constexpr uint32_t A_BYTES = kTcBM * kTcBKBytes;           // 16 KB per stage
     constexpr uint32_t B_BYTES = BN * kTcBKBytes;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+    // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32 or BF16, majors, N>>3, M>>4
+    constexpr uint32_t IDESC = (1u << 4) | (E::kFormat << 7) | (E::kFormat << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 
     extern __shared__ uint8_t tc_smem_raw[];
@@ -219,27 +245,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                         // box {32 k, 128 rows}
                     } else {
 #pragma unroll
-                        for (int i = 0; i < kTcBM / 32; i++)                                        // box {32 mn, 32 k-rows}
-                            tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + 32 * i, k0, &full_bar[s]);
+                        for (int i = 0; i < kTcBM / E::kMnChunk; i++)                               // box {one 128-byte mn chunk, BK k-rows}
+                            tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + E::kMnChunk * i, k0, &full_bar[s]);
                     }
                     if (CL == 1) {
                         if (!B_MN) {
                             tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < BN / 32; i++)
-                                tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * i, k0, &full_bar[s]);
+                            for (int i = 0; i < BN / E::kMnChunk; i++)
+                                tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + E::kMnChunk * i, k0, &full_bar[s]);
                         }
                     } else {                     // my half of the shared B tile, multicast to both CTAs of the cluster
                         if (!B_MN) {             // box {32 k, BN/CL rows}
                             constexpr int HR = BN / CL;
                             tc_tma_load_2d_mc(sb + crank * (HR * kTcBKBytes), &tmB, k0, n0 + (int)crank * HR, &full_bar[s], kMask);
                         } else {
-                            constexpr int HB = BN / 32 / CL;
+                            constexpr int HB = BN / E::kMnChunk / CL;
 #pragma unroll
                             for (int i = 0; i < HB; i++) {
                                 const int bi = (int)crank * HB + i;
-                                tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), &tmB, n0 + 32 * bi, k0, &full_bar[s], kMask);
+                                tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), &tmB, n0 + E::kMnChunk * bi, k0, &full_bar[s], kMask);
                             }
                         }
                     }
@@ -267,11 +293,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < kTcBK / kTcUmmaK; k++) {
                         // K-major: 8 rows x 128 B swizzle atoms, 1024 B apart; a k-step is 32 B inside the row.
-                        // MN-major: 32-element (128 B) MN chunks kTcBK*128 B apart (LBO), 4 k-rows = 512 B atoms (SBO);
-                        //           a k-step (8 k-rows) spans two atoms = 1024 B.
-                        const uint64_t da = A_MN ? tc_make_desc(sa + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sa + k * 32, 16, 1024, 2);
-                        const uint64_t db = B_MN ? tc_make_desc(sb + k * 1024, kTcBK * kTcBKBytes, 512, 1) : tc_make_desc(sb + k * 32, 16, 1024, 2);
-                        tc_umma_tf32(tmem_acc, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        // MN-major: 128-byte MN chunks kTcBK*128 B apart (LBO); tf32: 4 k-rows = 512 B atoms (SBO), bf16: 8 k-rows =
+                        //           1024 B atoms; a k-step (8 tf32 / 16 bf16 k-rows of 128 B) spans two atoms.
+                        constexpr uint32_t kMnStep = (uint32_t)kTcUmmaK * kTcBKBytes;
+                        const uint64_t da = A_MN ? tc_make_desc(sa + k * kMnStep, kTcBK * kTcBKBytes, E::kMnSbo, E::kMnLayout) : tc_make_desc(sa + k * 32, 16, 1024, 2);
+                        const uint64_t db = B_MN ? tc_make_desc(sb + k * kMnStep, kTcBK * kTcBKBytes, E::kMnSbo, E::kMnLayout) : tc_make_desc(sb + k * 32, 16, 1024, 2);
+                        tc_umma<BF>(tmem_acc, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                     }
                     if (CL == 1) tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
                     else tc_umma_commit_mc(&empty_bar[s], kMask);        // ... in both CTAs (each writes into the other's slot)
@@ -327,7 +354,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (EPI == kTcFwd) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            if (nb + j < p.N) v[j] = round_tf32(act_apply(v[j] + __ldg(p.bias + nb + j), p.act));
+                            if (nb + j < p.N) {
+                                const float y = act_apply(v[j] + __ldg(p.bias + nb + j), p.act);
+                                v[j] = BF ? y : round_tf32(y);
+                            }
                     } else if (EPI == kTcDx) {
                         if (need_h) {
                             if (full32 && (p.N & 3) == 0) {
@@ -345,8 +375,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
                             }
                         }
+                        if (!BF) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
+                            for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
+                        }
+                    }
+                    if (BF && EPI != kTcDw && p.C16) {          // bf16 shadow for the next tensor-core GEMM (round-to-nearest-even)
+                        __nv_bfloat16* Hrow = p.C16 + (size_t)row * p.ldc + nb;
+                        if (full32 && (p.ldc & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                                *reinterpret_cast<uint4*>(Hrow + j) = pk;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (nb + j < p.N) Hrow[j] = __float2bfloat16_rn(v[j]);
+                        }
                     }
                     if (full32 && (p.ldc & 3) == 0) {
 #pragma unroll
@@ -386,16 +436,18 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// Row-major fp32 matrix [rows][cols]; box = {box_cols (innermost, 128 B), box_rows}, 128B swizzle.
-static CUtensorMap make_map(const float* base, int rows, int cols, int box_cols, int box_rows, bool mn_major = false) {
+// Row-major matrix [rows][cols] of fp32 (tf32 operands) or bf16; box = {box_cols (innermost, 128 B), box_rows}, 128B swizzle.
+// MN-major tf32 operands need the 32-byte-atom flavour of the swizzle (SWIZZLE_128B_ATOM_32B <-> UMMA SWIZZLE_128B_BASE32B).
+static CUtensorMap make_map(const void* base, int rows, int cols, int box_cols, int box_rows, bool mn_major = false, bool bf16 = false) {
     CUtensorMap m;
+    const size_t esz = bf16 ? 2 : 4;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const CUtensorMapSwizzle sw = (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUresult r = encode_fn()(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) B200_FATAL("cuTensorMapEncodeTiled failed (%d) for %dx%d box %dx%d", (int)r, rows, cols, box_rows, box_cols);
     return m;
@@ -407,12 +459,12 @@ static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multi
     return cl;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF>
 static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 tiles /* (N tiles, M tiles, splits) */) {
     const size_t smem = (size_t)kTcStages * (kTcBM + BN) * kTcBKBytes + 1024 /*align*/ + 256 /*barriers*/;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     // persistent: one CTA per SM (190 KB of shared memory each), clusters of CL CTAs walk the work items
@@ -420,25 +472,26 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcA
     const int clusters = (int)std::min<long long>(items, num_sms() / CL);
     const dim3 grid(clusters * CL, 1, 1);
     if (CL == 1) {
-        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>), grid, kTcThreads, smem, ta, tb, a);
+        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>), grid, kTcThreads, smem, ta, tb, a);
         return;
     }
-    if (g_profiling) profile_mark("(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)", true);
+    const char* label = BF ? "(tc_gemm_kernel<bf16>)" : "(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)";
+    if (g_profiling) profile_mark(label, true);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>, ta, tb, a));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, ta, tb, a));
     ++g_launches;
-    if (g_profiling) profile_mark("(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)", false);
+    if (g_profiling) profile_mark(label, false);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool BF>
 static void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
-    if (tc_cluster() == 2) launch_tc_cl<BN, A_MN, B_MN, EPI, 2>(ta, tb, a, grid);
-    else launch_tc_cl<BN, A_MN, B_MN, EPI, 1>(ta, tb, a, grid);
+    if (tc_cluster() == 2) launch_tc_cl<BN, A_MN, B_MN, EPI, 2, BF>(ta, tb, a, grid);
+    else launch_tc_cl<BN, A_MN, B_MN, EPI, 1, BF>(ta, tb, a, grid);
 }
 
 // Shapes the tensor path accepts: TMA needs 16-byte row pitches and aligned bases.
@@ -453,31 +506,125 @@ void tc_round_copy(const float* src, float* dst, size_t n) {
 }
 
 constexpr int kTcBN = 256;
+constexpr int kTcBK32 = TcElem<false>::kBK, kTcBK16 = TcElem<true>::kBK;
 
 void tc_linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act) {
     TcArgs a{};
     a.C = y; a.M = m; a.N = l; a.K = n; a.ldc = l; a.bias = b; a.act = act;
-    const CUtensorMap ta = make_map(x, m, n, kTcBK, kTcBM);        // A K-major
-    const CUtensorMap tb = make_map(W, l, n, kTcBK, kTcBN / tc_cluster());   // B K-major (half tile per CTA under multicast)
-    launch_tc<kTcBN, false, false, kTcFwd>(ta, tb, a, dim3(div_up(l, kTcBN), div_up(m, kTcBM), 1));
+    const CUtensorMap ta = make_map(x, m, n, kTcBK32, kTcBM);        // A K-major
+    const CUtensorMap tb = make_map(W, l, n, kTcBK32, kTcBN / tc_cluster());   // B K-major (half tile per CTA under multicast)
+    launch_tc<kTcBN, false, false, kTcFwd, false>(ta, tb, a, dim3(div_up(l, kTcBN), div_up(m, kTcBM), 1));
 }
 
 void tc_linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev) {
     TcArgs a{};
     a.C = gx; a.M = m; a.N = n; a.K = l; a.ldc = n; a.xin = xin; a.act = act_prev;
-    const CUtensorMap ta = make_map(g, m, l, kTcBK, kTcBM);        // A K-major (k = out)
-    const CUtensorMap tb = make_map(W, l, n, 32, kTcBK, true);     // B MN-major: W[k=out][n=in], box {32 n, 32 k}
-    launch_tc<kTcBN, false, true, kTcDx>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(m, kTcBM), 1));
+    const CUtensorMap ta = make_map(g, m, l, kTcBK32, kTcBM);        // A K-major (k = out)
+    const CUtensorMap tb = make_map(W, l, n, 32, kTcBK32, true);     // B MN-major: W[k=out][n=in], box {32 n, 32 k}
+    launch_tc<kTcBN, false, true, kTcDx, false>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(m, kTcBM), 1));
 }
 
 void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l) {
     TcArgs a{};
     int rows = div_up(m, splits);
-    rows = div_up(rows, kTcBK) * kTcBK;
+    rows = div_up(rows, kTcBK32) * kTcBK32;
     a.C = gW_part; a.M = l; a.N = n; a.K = m; a.ldc = n; a.k_per_split = rows; a.c_split_stride = stride; a.splits = splits;
-    const CUtensorMap ta = make_map(g, m, l, 32, kTcBK, true);     // A MN-major: g[k=batch][m'=out]
-    const CUtensorMap tb = make_map(x, m, n, 32, kTcBK, true);     // B MN-major: x[k=batch][n=in]
-    launch_tc<kTcBN, true, true, kTcDw>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
+    const CUtensorMap ta = make_map(g, m, l, 32, kTcBK32, true);     // A MN-major: g[k=batch][m'=out]
+    const CUtensorMap tb = make_map(x, m, n, 32, kTcBK32, true);     // B MN-major: x[k=batch][n=in]
+    launch_tc<kTcBN, true, true, kTcDw, false>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
+}
+
+// ---- bf16 operand mode ---------------------------------------------------------------------------------
+// bf16 arrays need 16-byte row pitches: column counts that are multiples of 8
+bool tc_bf16_shape_ok(int m, int n, int l) { return m >= 128 && n >= 64 && l >= 64 && (n % 8) == 0 && (l % 8) == 0; }
+
+// y = act(x W^T + b): x16 [m][n], W16 [l][n] (both K-major); writes y (fp32) and, when y16 != null, its bf16 shadow
+void tc_linear_forward_bf16(float* y, __nv_bfloat16* y16, const __nv_bfloat16* x16, const __nv_bfloat16* W16, const float* b, int m, int n,
+                            int l, int act) {
+    TcArgs a{};
+    a.C = y; a.C16 = y16; a.M = m; a.N = l; a.K = n; a.ldc = l; a.bias = b; a.act = act;
+    const CUtensorMap ta = make_map(x16, m, n, kTcBK16, kTcBM, false, true);
+    const CUtensorMap tb = make_map(W16, l, n, kTcBK16, kTcBN / tc_cluster(), false, true);
+    launch_tc<kTcBN, false, false, kTcFwd, true>(ta, tb, a, dim3(div_up(l, kTcBN), div_up(m, kTcBM), 1));
+}
+
+// gx = (g W) act'(xin): g16 [m][l] K-major, Wt16 [n][l] = the TRANSPOSED weights (K-major B); xin fp32
+void tc_linear_backward_input_bf16(float* gx, __nv_bfloat16* gx16, const __nv_bfloat16* g16, const __nv_bfloat16* Wt16, const float* xin,
+                                   int m, int n, int l, int act_prev) {
+    TcArgs a{};
+    a.C = gx; a.C16 = gx16; a.M = m; a.N = n; a.K = l; a.ldc = n; a.xin = xin; a.act = act_prev;
+    const CUtensorMap ta = make_map(g16, m, l, kTcBK16, kTcBM, false, true);
+    const CUtensorMap tb = make_map(Wt16, n, l, kTcBK16, kTcBN / tc_cluster(), false, true);
+    launch_tc<kTcBN, false, false, kTcDx, true>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(m, kTcBM), 1));
+}
+
+// gW = g^T x (split-K slabs, fp32): g16 [m][l] and x16 [m][n] read MN-major (k = batch)
+void tc_linear_backward_weights_bf16(float* gW_part, size_t stride, int splits, const __nv_bfloat16* g16, const __nv_bfloat16* x16, int m,
+                                     int n, int l) {
+    TcArgs a{};
+    int rows = div_up(m, splits);
+    rows = div_up(rows, kTcBK16) * kTcBK16;
+    a.C = gW_part; a.M = l; a.N = n; a.K = m; a.ldc = n; a.k_per_split = rows; a.c_split_stride = stride; a.splits = splits;
+    const CUtensorMap ta = make_map(g16, m, l, 64, kTcBK16, true, true);     // box {64 m' (128 B), 64 k-rows}
+    const CUtensorMap tb = make_map(x16, m, n, 64, kTcBK16, true, true);
+    launch_tc<kTcBN, true, true, kTcDw, true>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
+}
+
+// fp32 -> bf16 (round to nearest even), 8 elements per thread; n must be a multiple of 8 and both pointers 16-byte aligned
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n8) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const float4 a = ld_stream4(src + 8 * i), b = ld_stream4(src + 8 * i + 4);
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(dst + 8 * i) = pk;
+    }
+}
+void tc_to_bf16(const float* src, __nv_bfloat16* dst, size_t n) {
+    if (n == 0) return;
+    if (n % 8) B200_FATAL("tc_to_bf16: %zu elements (must be a multiple of 8)", n);
+    const int blocks = (int)std::min<size_t>((n / 8 + 255) / 256, (size_t)num_sms() * 8);
+    B200_LAUNCH(to_bf16_kernel, blocks, 256, 0, src, dst, n / 8);
+}
+
+// W [l][n] fp32 -> W16 [l][n] and Wt16 [n][l] (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) weights_bf16_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ W16,
+                                                           __nv_bfloat16* __restrict__ Wt16, int l, int n) {
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, k = k0 + tx;
+        float v = 0.f;
+        if (j < l && k < n) { v = W[(size_t)j * n + k]; W16[(size_t)j * n + k] = __float2bfloat16_rn(v); }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, j = j0 + tx;
+        if (k < n && j < l) Wt16[(size_t)k * l + j] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+void tc_weights_bf16(const float* W, __nv_bfloat16* W16, __nv_bfloat16* Wt16, int l, int n) {
+    dim3 grid(div_up(n, 32), div_up(l, 32), 1);
+    B200_LAUNCH(weights_bf16_kernel, grid, 256, 0, W, W16, Wt16, l, n);
+}
+
+void tc_linear_forward_bf16_v(float* y, void* y16, const void* x16, const void* W16, const float* b, int m, int n, int l, int act) {
+    tc_linear_forward_bf16(y, static_cast<__nv_bfloat16*>(y16), static_cast<const __nv_bfloat16*>(x16), static_cast<const __nv_bfloat16*>(W16), b, m, n, l, act);
+}
+void tc_linear_backward_input_bf16_v(float* gx, void* gx16, const void* g16, const void* Wt16, const float* xin, int m, int n, int l, int act_prev) {
+    tc_linear_backward_input_bf16(gx, static_cast<__nv_bfloat16*>(gx16), static_cast<const __nv_bfloat16*>(g16), static_cast<const __nv_bfloat16*>(Wt16), xin, m, n, l, act_prev);
+}
+void tc_linear_backward_weights_bf16_v(float* gW_part, size_t stride, int splits, const void* g16, const void* x16, int m, int n, int l) {
+    tc_linear_backward_weights_bf16(gW_part, stride, splits, static_cast<const __nv_bfloat16*>(g16), static_cast<const __nv_bfloat16*>(x16), m, n, l);
+}
+void tc_to_bf16_v(const float* src, void* dst, size_t n) { tc_to_bf16(src, static_cast<__nv_bfloat16*>(dst), n); }
+void tc_weights_bf16_v(const float* W, void* W16, void* Wt16, int l, int n) {
+    tc_weights_bf16(W, static_cast<__nv_bfloat16*>(W16), static_cast<__nv_bfloat16*>(Wt16), l, n);
 }
 
 }  // namespace b200
@@ -490,4 +637,26 @@ extern "C" void ppo_b200_tc_linear(int mode, float* out, const float* a, const f
     if (mode == 0) tc_linear_forward(out, a, b, aux, m, n, l, act);
     else if (mode == 1) tc_linear_backward_input(out, a, b, aux, m, n, l, act);
     else tc_linear_backward_weights(out, (size_t)n * l, splits, a, b, m, n, l);
+}
+
+// Same contractions with bf16 operands: the fp32 inputs are converted into scratch bf16 arrays first (the conversion is
+// outside what a caller should time: the training path keeps bf16 shadows resident), `out16` (may be null) receives the
+// bf16 shadow of the output.  mode 0: a = x [m][n], b = W [l][n], aux = bias; 1: a = g [m][l], b = W [l][n], aux = xin [m][n];
+// 2: a = g [m][l], b = x [m][n].
+extern "C" void ppo_b200_tc_linear_bf16(int mode, float* out, void* out16, const float* a, const float* b, const float* aux, int m,
+                                        int n, int l, int act, int splits, int convert_only, int skip_convert) {
+    const size_t na = (size_t)m * (mode == 0 ? n : l), nw = (size_t)l * n, nb = mode == 2 ? (size_t)m * n : nw;
+    char* base = static_cast<char*>(scratch(kScratchStage3, (na + 2 * nb) * 2 + 1024));
+    __nv_bfloat16* a16 = reinterpret_cast<__nv_bfloat16*>(base);
+    __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(base + ((na * 2 + 255) & ~size_t(255)));
+    __nv_bfloat16* bt16 = reinterpret_cast<__nv_bfloat16*>(base + ((na * 2 + 255) & ~size_t(255)) + ((nb * 2 + 255) & ~size_t(255)));
+    if (!skip_convert) {
+        tc_to_bf16(a, a16, na);
+        if (mode == 2) tc_to_bf16(b, b16, nb);
+        else tc_weights_bf16(b, b16, bt16, l, n);
+    }
+    if (convert_only) return;
+    if (mode == 0) tc_linear_forward_bf16(out, static_cast<__nv_bfloat16*>(out16), a16, b16, aux, m, n, l, act);
+    else if (mode == 1) tc_linear_backward_input_bf16(out, static_cast<__nv_bfloat16*>(out16), a16, bt16, aux, m, n, l, act);
+    else tc_linear_backward_weights_bf16(out, (size_t)n * l, splits, a16, b16, m, n, l);
 }

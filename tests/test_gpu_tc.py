@@ -99,3 +99,98 @@ def test_wide_mlp_tf32_vs_fp32_oracle(L, hidden_act, tol):
           % (hidden_act, m, e_y, e_g, ["%.1e" % e for e in per]))
     assert e_y < 3e-3 and max(per) < tol
     L.free_neural_network(nn)
+
+
+# ---- BF16 operand mode (kind::f16, fp32 accumulation) -------------------------------------------------------------------
+# Stated tolerance: operands rounded to bf16 (8-bit mantissa, round-to-nearest-even: relative error <= 2^-9 each), products
+# and sums exact in fp32 -> norm-wise output error ~ 2^-9 * sqrt(2) / sqrt(K) * |row|-ish; measured 2e-3 .. 3e-3, bound 6e-3.
+# Against the SAME contraction evaluated in float64 on the bf16-rounded operands the kernel must agree to fp32 accumulation
+# error (1e-5): that separates "bf16 rounding" from "kernel bug".
+TOL_BF16 = 6e-3
+
+
+def bf16_round(a):
+    """Round-to-nearest-even fp32 -> bf16 -> fp32 in numpy."""
+    u = np.ascontiguousarray(a, dtype=f32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(f32)
+
+
+def bf16_view(dev16, shape):
+    """bf16 device array (stored in a uint16 DeviceArray) -> fp32 numpy."""
+    return (dev16.numpy().astype(np.uint32) << 16).view(f32).reshape(shape)
+
+
+@pytest.mark.parametrize("m,n,l", [(128, 64, 256), (256, 1024, 1024), (1000, 104, 296), (4096, 1024, 1024), (384, 64, 64), (130, 256, 1024)])
+def test_tc_bf16_forward(L, m, n, l):
+    rng = np.random.default_rng(m + n + l)
+    x, w, b = rng.standard_normal((m, n)).astype(f32), (rng.standard_normal((l, n)) / np.sqrt(n)).astype(f32), rng.standard_normal(l).astype(f32)
+    dx, dw, db, dy, dy16 = b200.dev(x), b200.dev(w), b200.dev(b), b200.dev_empty((m, l)), b200.dev_empty((m, l), np.uint16)
+    xr, wr = bf16_round(x).astype(np.float64), bf16_round(w).astype(np.float64)
+    for act, fn in ((0, lambda z: z), (1, lambda z: np.maximum(z, 0)), (2, np.tanh)):
+        L.ppo_b200_tc_linear_bf16(0, dy.ptr, dy16.ptr, dx.ptr, dw.ptr, db.ptr, m, n, l, act, 1, 0, 0)
+        got = dy.numpy()
+        assert nerr(got, fn(xr @ wr.T + b)) < 2e-5, act                       # same rounded operands: fp32 accumulation error only
+        assert nerr(got, fn(x.astype(np.float64) @ w.astype(np.float64).T + b)) < (TOL_BF16 if act != 2 else 1.5e-2), act
+        assert np.array_equal(bf16_view(dy16, (m, l)), bf16_round(got)), act     # the shadow is the RNE rounding of the fp32 output
+    for d in (dx, dw, db, dy, dy16):
+        d.free()
+
+
+@pytest.mark.parametrize("m,n,l", [(128, 64, 256), (256, 1024, 1024), (1000, 104, 296), (2048, 1024, 1024), (384, 64, 64)])
+def test_tc_bf16_backward_input(L, m, n, l):
+    rng = np.random.default_rng(m + n + l + 1)
+    g, w = rng.standard_normal((m, l)).astype(f32), rng.standard_normal((l, n)).astype(f32)
+    h = np.maximum(rng.standard_normal((m, n)), 0).astype(f32)
+    dg, dw, dh, dgx, d16 = b200.dev(g), b200.dev(w), b200.dev(h), b200.dev_empty((m, n)), b200.dev_empty((m, n), np.uint16)
+    L.ppo_b200_tc_linear_bf16(1, dgx.ptr, d16.ptr, dg.ptr, dw.ptr, dh.ptr, m, n, l, 1, 1, 0, 0)
+    gr, wr = bf16_round(g).astype(np.float64), bf16_round(w).astype(np.float64)
+    assert nerr(dgx.numpy(), (gr @ wr) * (h > 0)) < 2e-5
+    assert nerr(dgx.numpy(), (g.astype(np.float64) @ w.astype(np.float64)) * (h > 0)) < TOL_BF16
+    assert np.array_equal(bf16_view(d16, (m, n)), bf16_round(dgx.numpy()))
+    L.ppo_b200_tc_linear_bf16(1, dgx.ptr, None, dg.ptr, dw.ptr, dh.ptr, m, n, l, 0, 1, 0, 0)
+    assert nerr(dgx.numpy(), gr @ wr) < 2e-5
+
+
+@pytest.mark.parametrize("m,n,l,splits", [(128, 64, 256, 1), (4096, 1024, 1024, 4), (1000, 104, 296, 3), (65536, 256, 128, 16)])
+def test_tc_bf16_backward_weights(L, m, n, l, splits):
+    rng = np.random.default_rng(m + n + l + 2)
+    g, x = rng.standard_normal((m, l)).astype(f32), rng.standard_normal((m, n)).astype(f32)
+    dg, dx, dout = b200.dev(g), b200.dev(x), b200.dev_empty((splits, l, n))
+    L.ppo_b200_tc_linear_bf16(2, dout.ptr, None, dg.ptr, dx.ptr, None, m, n, l, 0, splits, 0, 0)
+    got = dout.numpy().astype(np.float64).sum(0)
+    assert nerr(got, bf16_round(g).astype(np.float64).T @ bf16_round(x).astype(np.float64)) < 2e-5
+    assert nerr(got, g.astype(np.float64).T @ x.astype(np.float64)) < TOL_BF16
+
+
+@pytest.mark.parametrize("hidden_act,tol", [("tanh", 2e-2), ("relu", 1.5e-1)])
+def test_wide_mlp_bf16_vs_fp32_oracle(L, hidden_act, tol):
+    """3x1024 net through the NeuralNetwork API with BF16 operands against the fp32 oracle; measured error printed.
+    relu: dominated by derivative-mask flips of units within bf16 rounding of zero (see the TF32 test above)."""
+    sizes, acts, m = [17, 1024, 1024, 1024, 6], [hidden_act] * 3 + ["none"], 512
+    cabi.srand(4)
+    nn = L.create_neural_network(cabi.int_array(sizes), cabi.cstr_array(acts), len(sizes))
+    p = b200.nn_get_params(L, nn)
+    rng = np.random.default_rng(0)
+    x, g = rng.standard_normal((m, 17)).astype(f32), rng.standard_normal((m, 6)).astype(f32)
+    dx, dg = b200.dev(x), b200.dev(g)
+    L.ppo_b200_set_matmul_precision(2)
+    try:
+        L.forward_propagation_cuda(nn, dx.fp(), m)
+        y = b200.d2h(L, nn.contents.d_output, (m, 6))
+        L.backward_propagation_cuda(nn, dg.fp(), m)
+        grads = b200.nn_get_device_grads(L, nn)
+    finally:
+        L.ppo_b200_set_matmul_precision(0)
+    y_o, cache = oracle.mlp_forward(p, sizes, acts, x)
+    g_o = oracle.mlp_backward(p, sizes, acts, cache, g)
+    per, o = [], 0
+    for i in range(len(sizes) - 1):
+        for cnt in (sizes[i] * sizes[i + 1], sizes[i + 1]):
+            a, b = grads[o:o + cnt].astype(np.float64), g_o[o:o + cnt].astype(np.float64)
+            per.append(np.linalg.norm(a - b) / np.linalg.norm(b))
+            o += cnt
+    print("BF16 wide MLP %s (m=%d): output err %.2e (max-norm), gradient max-norm err %.2e, per-tensor relative L2 %s"
+          % (hidden_act, m, nerr(y, y_o), nerr(grads, g_o), ["%.1e" % e for e in per]))
+    assert nerr(y, y_o) < 2e-2 and max(per) < tol
+    L.free_neural_network(nn)
