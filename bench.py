@@ -466,6 +466,25 @@ class C4(UpdateOnly):
                 "gae_scan": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
 
 
+class C4BF16(C4):
+    """c4 with BF16 operands (tcgen05 kind::f16, fp32 accumulation): the same shapes and data flow, peak = sustained cuBLAS bf16."""
+    name = "c4bf16"
+    dtype = "bf16"
+    TF32 = 2
+
+    def config(self):
+        c = self.base_config("c4bf16: wide actor-critic 3x1024 ReLU MLP (S=17, A=6), minibatch 65536/GPU, BF16-operand tcgen05 GEMMs with "
+                             "fp32 accumulation in TMEM (fp32 parameters, gradients and Adam), 262144-row synthetic buffer per GPU, PPO "
+                             "update only (BASELINE.json configs[3], bf16 variant)")
+        c["tolerance"] = "BF16 operands (round-to-nearest-even), stated separately from fp32: ~3e-3 norm-wise per GEMM (tests/test_gpu_tc.py)"
+        return c
+
+    def roofline_work(self, kernels):
+        w = dict(C4.roofline_work(self, kernels))
+        w["tc_gemm_kernel"] = ("tensor_bf16", w["tc_gemm_kernel"][1])
+        return w
+
+
 class C5(Workload):
     """GAE/returns-only sweep on synthetic rewards/values/dones (BASELINE.json configs[4])."""
     name = "c5"
@@ -700,7 +719,7 @@ class GatherStage(StageWorkload):
         return "oracle port of get_batch (src/trajectory_buffer.cu:202-220) over %d rows" % self.CPU_B
 
 
-WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c4": C4, "c5": C5, "adam": AdamStage, "gather": GatherStage}
+WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c4": C4, "c4bf16": C4BF16, "c5": C5, "adam": AdamStage, "gather": GatherStage}
 
 
 # ======================================================================================= CPU arm
@@ -836,6 +855,10 @@ def build_roofline(kernels, work, traffic_file=None):
         sec = agg[prefix]["total_ms"] * 1e-3
         if bound == "hbm":
             ach, peak, unit, psrc = amount / sec / 1e9, pk["hbm"], "GB/s", pk["src"] + ": HBM copy read+write"
+        elif bound == "tensor_bf16":
+            ach, peak, unit = amount / sec / 1e12, pk["bf16"], "TFLOP/s"
+            psrc = pk["src"] + ": sustained cuBLAS bf16"
+            bound = "tensor"
         elif bound == "tensor_tf32":
             ach, peak, unit = amount / sec / 1e12, pk["bf16"] / 2, "TFLOP/s"
             psrc = pk["src"] + ": sustained cuBLAS bf16 / 2 (TF32 dense rate is half of bf16)"
@@ -1037,7 +1060,7 @@ def run_secondary(L, rank, world, stream, barrier, torch, dist):
     """Short runs of the other BASELINE.json configs after the headline workload: value (device-resident, CUDA events, max over
     ranks) + the roofline of the dominant kernel from one profiled step.  c1 (host env, not collective) only at N = 1."""
     out = {}
-    for name, steps in (("c3", 2), ("c4", 2), ("c5", 5)):
+    for name, steps in (("c3", 2), ("c4", 2), ("c4bf16", 2), ("c5", 5)):
         wl = WORKLOADS[name](L, rank, world)
         wl.setup()
         wl.step_device(1)
@@ -1106,7 +1129,8 @@ def whole_step_fraction(wl, ms_per_step):
     flops = (wl.N_VAL * nb * train_flops(sv, wl.MB) + wl.N_POL * nb * train_flops(wl.SIZES, wl.MB) + 2 * 2 * wl.cap * mlp_weights(sv))
     tfs = flops / (ms_per_step * 1e-3) / 1e12
     pk = load_peaks()
-    peak = pk["bf16"] / 2 if getattr(wl, "TF32", 0) else (FP32_MEASURED.get("ffma_const_operands") or FP32_PEAK_TFLOPS)
+    prec = getattr(wl, "TF32", 0)
+    peak = pk["bf16"] if prec == 2 else pk["bf16"] / 2 if prec else (FP32_MEASURED.get("ffma_const_operands") or FP32_PEAK_TFLOPS)
     return {"tflops": tfs, "peak": peak, "frac": tfs / peak}
 
 

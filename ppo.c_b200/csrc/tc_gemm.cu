@@ -37,7 +37,8 @@ namespace b200 {
 
 constexpr int kTcBM = 128;
 constexpr int kTcBKBytes = 128;            // one 128B swizzle row per k-block
-constexpr int kTcStages = 4;
+constexpr int kTcStagesMax = 4;            // ring depth: 4 for the split-K dW kernels, 3 where the epilogue stages its tiles for TMA stores
+constexpr int kTcStgBytes = 8192;          // per epilogue warp: [32 rows][32 fp32] + [32 rows][64 bf16], both 128-byte rows, swizzled
 // element-type constants: BF = false -> tf32 operands read from fp32 words, BF = true -> bf16 operands
 template <bool BF> struct TcElem {
     static constexpr int kSize = BF ? 2 : 4;
@@ -64,6 +65,7 @@ struct TcArgs {
     int k_per_split;        // kTcDw: reduction rows per split
     int splits;             // kTcDw: number of split-K slabs
     size_t c_split_stride;
+    int tma_store;          // kTcFwd / kTcDx: the epilogue writes C (and C16) with TMA bulk tensor stores from swizzled staging tiles
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -91,6 +93,10 @@ __device__ __forceinline__ void tc_tma_load_2d(void* dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
                  :: "r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(s_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -167,8 +173,10 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict
 // CTAs' MMAs released it, so tcgen05.commit arrives on the empty barrier of both CTAs (count = CL).
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmC16, const TcArgs p) {
     using E = TcElem<BF>;
+    constexpr int kTcStages = (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
     constexpr int kTcBK = E::kBK, kTcUmmaK = E::kUmmaK;
     constexpr uint32_t A_BYTES = kTcBM * kTcBKBytes;           // 16 KB per stage
     constexpr uint32_t B_BYTES = BN * kTcBKBytes;
@@ -179,7 +187,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTcStages * STAGE_BYTES);
+    uint8_t* stg_base = smem + kTcStages * STAGE_BYTES;                        // staging tiles of the epilogue warps (1024-byte aligned)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (EPI == kTcDw ? 0 : kTcEpiWarps * kTcStgBytes));
     uint64_t* empty_bar = full_bar + kTcStages;
     uint64_t* tmem_full_bar = empty_bar + kTcStages;      // [2] accumulator buffer b holds a finished tile
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2] the epilogue warps have drained buffer b
@@ -323,6 +332,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* Crow = p.C + (EPI == kTcDw ? (size_t)z * p.c_split_stride : 0) + (size_t)row * p.ldc;
             const bool rows_ok = row < p.M;
             constexpr int CPW = BN / (kTcEpiWarps / 4);          // columns per warp
+            const bool use_tma = EPI != kTcDw && p.tma_store;
+            float* stg32 = reinterpret_cast<float*>(stg_base + (warp - 2) * kTcStgBytes);
+            uint4* stg16 = reinterpret_cast<uint4*>(stg_base + (warp - 2) * kTcStgBytes + 4096);
 #pragma unroll 1
             for (int c0 = half * CPW; c0 < (half + 1) * CPW; c0 += 32) {
                 const int nb = n0 + c0;
@@ -347,7 +359,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_u32(&tmem_empty_bar[buf])) : "memory");
                 }
-                if (rows_ok) {
+                if (rows_ok || use_tma) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -380,6 +392,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
                         }
                     }
+                    if (use_tma) {
+                        // Stage the 32 x 32 chunk (thread = row) in the 128B-swizzled layout the store tensor map expects (16-byte piece
+                        // j of row r sits at piece j ^ (r & 7): conflict-free per quarter-warp), then one lane issues the bulk tensor
+                        // store: full 128-byte lines leave through the TMA unit instead of 32 partial lines per st.v4 (the st.v4
+                        // epilogue kept the load/store unit as busy as the tensor pipe).  Rows / columns past M / N are clipped by TMA.
+                        const int cidx = (c0 - half * CPW) >> 5;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // previous stores have read the staging tiles
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            *reinterpret_cast<float4*>(stg32 + lane * 32 + 4 * (j ^ (lane & 7))) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        const bool shadow = BF && p.C16 != nullptr;
+                        if (shadow) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                uint4 pk;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), t1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), t3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                                stg16[lane * 8 + (((cidx & 1) * 4 + j) ^ (lane & 7))] = pk;
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tc_tma_store_2d(&tmC, stg32, nb, m0 + q * 32);
+                            if (shadow && (cidx & 1)) tc_tma_store_2d(&tmC16, stg16, nb - 32, m0 + q * 32);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        continue;
+                    }
                     if (BF && EPI != kTcDw && p.C16) {          // bf16 shadow for the next tensor-core GEMM (round-to-nearest-even)
                         __nv_bfloat16* Hrow = p.C16 + (size_t)row * p.ldc + nb;
                         if (full32 && (p.ldc & 7) == 0) {
@@ -411,6 +455,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     }
+    if (EPI != kTcDw && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // my bulk stores have completed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -453,6 +498,11 @@ static CUtensorMap make_map(const void* base, int rows, int cols, int box_cols, 
     return m;
 }
 
+static bool tc_tma_store_enabled() {      // PPO_B200_TC_TMA_STORE=0 keeps the per-lane st.v4 epilogue (A/B runs)
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("PPO_B200_TC_TMA_STORE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
 static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multicast clusters (A/B runs)
     static int cl = -1;
     if (cl < 0) { const char* e = getenv("PPO_B200_TC_CLUSTER"); cl = (e && e[0] == '1') ? 1 : 2; }
@@ -460,8 +510,19 @@ static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multi
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF>
-static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 tiles /* (N tiles, M tiles, splits) */) {
-    const size_t smem = (size_t)kTcStages * (kTcBM + BN) * kTcBKBytes + 1024 /*align*/ + 256 /*barriers*/;
+static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a_in, dim3 tiles /* (N tiles, M tiles, splits) */) {
+    constexpr int kStages = (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
+    const size_t smem = (size_t)kStages * (kTcBM + BN) * kTcBKBytes + (EPI == kTcDw ? 0 : kTcEpiWarps * kTcStgBytes) + 1024 /*align*/ + 256 /*barriers*/;
+    // output tensor maps of the TMA-store epilogue (forward / dX): fp32 boxes {32 columns, 32 rows}, bf16 shadow boxes {64, 32}
+    TcArgs a = a_in;
+    CUtensorMap tc = ta, tc16 = ta;        // placeholders when the store path is off
+    a.tma_store = 0;
+    if (EPI != kTcDw && tc_tma_store_enabled() && (a.ldc % 4) == 0 && a.ldc == a.N && ((uintptr_t)a.C & 15) == 0 &&
+        (!a.C16 || ((a.ldc % 8) == 0 && ((uintptr_t)a.C16 & 15) == 0))) {
+        a.tma_store = 1;
+        tc = make_map(a.C, a.M, a.N, 32, 32, false, false);
+        if (a.C16) tc16 = make_map(a.C16, a.M, a.N, 64, 32, false, true);
+    }
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -472,7 +533,7 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcA
     const int clusters = (int)std::min<long long>(items, num_sms() / CL);
     const dim3 grid(clusters * CL, 1, 1);
     if (CL == 1) {
-        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>), grid, kTcThreads, smem, ta, tb, a);
+        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>), grid, kTcThreads, smem, ta, tb, tc, tc16, a);
         return;
     }
     const char* label = BF ? "(tc_gemm_kernel<bf16>)" : "(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)";
@@ -483,7 +544,7 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcA
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, ta, tb, a));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, ta, tb, tc, tc16, a));
     ++g_launches;
     if (g_profiling) profile_mark(label, false);
 }
