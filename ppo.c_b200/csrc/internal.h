@@ -85,6 +85,9 @@ void tc_linear_backward_weights_bf16_v(float* gW_part, size_t stride, int splits
 void tc_to_bf16_v(const float* src, void* dst, size_t n);
 void tc_weights_bf16_v(const float* W, void* W16, void* Wt16, int l, int n);
 void launch_colsum(float* gb_part, size_t stride, int splits, const float* g, int m, int l);
+void tc_colsum_bf16_v(float* gb_part, size_t stride, int splits, const void* g16, int m, int l);
+void tc_pad_bf16_v(const float* src, void* dst, size_t rows, int n, int npad);
+void tc_unpad_slabs(const float* src, float* gW_part, size_t stride, int splits, int l, int n, int npad);
 
 // ---- nn.cu ------------------------------------------------------------------------------------
 struct NetDev {               // device-side view of one NeuralNetwork (side table keyed by pointer)
@@ -110,7 +113,8 @@ struct NetDev {               // device-side view of one NeuralNetwork (side tab
     float* params_tf32 = nullptr;   // RNA-rounded shadow of `params` read by the tensor-core layers
     // bf16 operand mode: per-layer weight copies W16 [out][in] | Wt16 [in][out] and shadows of the activations / gradients
     void* params_bf16 = nullptr;    // 2 * param_count bf16: [W16 of every layer at w_off | Wt16 of every layer at param_count + w_off]
-    std::vector<void*> a16, gx16;   // a16[i] : bf16 [cap][sizes[i]] (null until needed)
+    void* w0pad_bf16 = nullptr;     // first layer with fewer than 64 inputs: W16 [out][64] zero padded (K padded to one k-block)
+    std::vector<void*> a16, gx16;   // a16[i] : bf16 [cap][sizes[i]] (null until needed); a16[0] is [cap][64] when layer 0 is K-padded
     std::vector<int> a16_cap, gx16_cap;
     float* image = nullptr;      // pre-transposed weight image staged by the fused kernels (fused_mlp.cu)
     int image_floats = 0;

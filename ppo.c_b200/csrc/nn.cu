@@ -90,6 +90,12 @@ static void ensure_bwd_capacity(NeuralNetwork* nn, NetDev* nd, int m) {
 
 // ---- bf16 operand mode helpers ----------------------------------------------------------------------------
 static bool bf16_layer(const NetDev* nd, int i, int m) { return tc_bf16_shape_ok(m, nd->sizes[i], nd->sizes[i + 1]); }
+// first layer of a low-dimensional env (n < 64): its K is padded to one 64-element k-block so that forward and dW run on the
+// tensor cores too (dX of layer 0 is never needed)
+constexpr int kPadK = 64;
+static bool bf16_layer0_padk(const NetDev* nd, int m) {
+    return nd->num_layers >= 3 && nd->sizes[0] < 64 && m >= 128 && nd->sizes[1] >= 64 && (nd->sizes[1] % 8) == 0;
+}
 // element offset of layer i's W16 inside params_bf16 (16-byte aligned); Wt16 follows at + bf16_total(nd)
 static size_t bf16_w_off(const NetDev* nd, int i) {
     size_t off = 0;
@@ -143,7 +149,16 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
         bool have16 = false;          // a16[i] holds the shadow of a[i]
         for (int i = 0; i < L; i++) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
-            if (bf16_layer(nd, i, m)) {
+            if (i == 0 && bf16_layer0_padk(nd, m)) {
+                if (!nd->w0pad_bf16) CUDA_CHECK(cudaMalloc(&nd->w0pad_bf16, (size_t)l * kPadK * 2 + 64));
+                tc_pad_bf16_v(nd->params + nd->w_off[0], nd->w0pad_bf16, (size_t)l, n, kPadK);
+                ensure_shadow(nd->a16, nd->a16_cap, 0, m, kPadK);
+                tc_pad_bf16_v(nd->a[0], nd->a16[0], (size_t)m, n, kPadK);
+                const bool next16 = L > 1 && bf16_layer(nd, 1, m);
+                if (next16) ensure_shadow(nd->a16, nd->a16_cap, 1, m, l);
+                tc_linear_forward_bf16_v(nd->a[1], next16 ? nd->a16[1] : nullptr, nd->a16[0], nd->w0pad_bf16, nd->params + nd->b_off[0], m, kPadK, l, nd->acts[0]);
+                have16 = next16;
+            } else if (bf16_layer(nd, i, m)) {
                 const size_t wo = bf16_w_off(nd, i);
                 tc_weights_bf16_v(nd->params + nd->w_off[i], w16 + 2 * wo, w16 + 2 * (tot16 + wo), l, n);
                 if (!have16) { ensure_shadow(nd->a16, nd->a16_cap, i, m, n); tc_to_bf16_v(nd->a[i], nd->a16[i], (size_t)m * n); }
@@ -202,12 +217,19 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         bool have16 = false;          // gx16[i + 1] holds the shadow of g (the gradient wrt a[i + 1])
         for (int i = L - 1; i >= 0; i--) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
-            if (w16 && bf16_layer(nd, i, m) && (int)nd->a16.size() > i && nd->a16[i]) {
+            if (i == 0 && w16 && bf16_layer0_padk(nd, m) && nd->w0pad_bf16 && !nd->a16.empty() && nd->a16[0]) {
+                // K-padded first layer: dW through the tensor cores into [splits][l][64] staging slabs, columns < n copied out
+                if (!have16) { ensure_shadow(nd->gx16, nd->gx16_cap, 1, m, l); tc_to_bf16_v(g, nd->gx16[1], (size_t)m * l); }
+                float* tmp = static_cast<float*>(scratch(kScratchSkinny, (size_t)splits * l * kPadK * sizeof(float)));
+                tc_linear_backward_weights_bf16_v(tmp, (size_t)l * kPadK, splits, nd->gx16[1], nd->a16[0], m, kPadK, l);
+                tc_unpad_slabs(tmp, nd->partials + nd->w_off[0], nd->slab_stride(), splits, l, n, kPadK);
+                tc_colsum_bf16_v(nd->partials + nd->b_off[0], nd->slab_stride(), splits, nd->gx16[1], m, l);
+            } else if (w16 && bf16_layer(nd, i, m) && (int)nd->a16.size() > i && nd->a16[i]) {
                 if (!have16) { ensure_shadow(nd->gx16, nd->gx16_cap, i + 1, m, l); tc_to_bf16_v(g, nd->gx16[i + 1], (size_t)m * l); }
                 tc_linear_backward_weights_bf16_v(nd->partials + nd->w_off[i], nd->slab_stride(), splits, nd->gx16[i + 1], nd->a16[i], m, n, l);
-                launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
+                tc_colsum_bf16_v(nd->partials + nd->b_off[i], nd->slab_stride(), splits, nd->gx16[i + 1], m, l);
                 if (i > 0) {
-                    const bool next16 = bf16_layer(nd, i - 1, m) && (int)nd->a16.size() > i - 1 && nd->a16[i - 1];
+                    const bool next16 = (bf16_layer(nd, i - 1, m) || (i == 1 && bf16_layer0_padk(nd, m))) && (int)nd->a16.size() > i - 1 && nd->a16[i - 1];
                     if (next16) ensure_shadow(nd->gx16, nd->gx16_cap, i, m, n);
                     tc_linear_backward_input_bf16_v(nd->gx[i], next16 ? nd->gx16[i] : nullptr, nd->gx16[i + 1],
                                                     w16 + 2 * (tot16 + bf16_w_off(nd, i)), nd->a[i], m, n, l, nd->acts[i - 1]);
@@ -309,6 +331,7 @@ void free_neural_network(NeuralNetwork* nn) {
         if (nd->image) CUDA_CHECK(cudaFree(nd->image));
         if (nd->params_tf32) CUDA_CHECK(cudaFree(nd->params_tf32));
         if (nd->params_bf16) CUDA_CHECK(cudaFree(nd->params_bf16));
+        if (nd->w0pad_bf16) CUDA_CHECK(cudaFree(nd->w0pad_bf16));
         for (void* q : nd->a16) if (q) CUDA_CHECK(cudaFree(q));
         for (void* q : nd->gx16) if (q) CUDA_CHECK(cudaFree(q));
         delete nd;

@@ -674,6 +674,80 @@ void tc_weights_bf16(const float* W, __nv_bfloat16* W16, __nv_bfloat16* Wt16, in
     B200_LAUNCH(weights_bf16_kernel, grid, 256, 0, W, W16, Wt16, l, n);
 }
 
+// db slabs from the bf16 shadow of g: gb_part[s][col] = sum over the rows of split s of g16[row][col].  Thread = (8-column group,
+// row lane): 4 groups x 64 row lanes per CTA (32 columns), eight independent 128-bit loads in flight per thread (the grid is only
+// (l / 32) x splits CTAs, so bytes in flight per CTA set the bandwidth); fixed-order combine of the row lanes.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(float* __restrict__ gb_part, size_t stride, const __nv_bfloat16* __restrict__ g, int m, int l, int rows_per_split) {
+    __shared__ float red[64][4][9];
+    const int cx = threadIdx.x & 3, ry = threadIdx.x >> 2;
+    const int col = blockIdx.x * 32 + 8 * cx;
+    const int r0 = blockIdx.y * rows_per_split, r1 = min(m, r0 + rows_per_split);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] = 0.f;
+    auto add = [&](const uint4& t) {
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) { s[2 * j] += __uint_as_float(w[j] << 16); s[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u); }
+    };
+    if (col < l) {            // l is a multiple of 8 (bf16 layers)
+        int r = r0 + ry;
+        for (; r + 7 * 64 < r1; r += 8 * 64) {
+            uint4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = __ldg(reinterpret_cast<const uint4*>(g + (size_t)(r + 64 * u) * l + col));
+#pragma unroll
+            for (int u = 0; u < 8; u++) add(t[u]);
+        }
+        for (; r < r1; r += 64) add(__ldg(reinterpret_cast<const uint4*>(g + (size_t)r * l + col)));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[ry][cx][j] = s[j];
+    __syncthreads();
+    if (threadIdx.x < 32 && blockIdx.x * 32 + (int)threadIdx.x < l) {      // thread = column: folds the 64 row lanes in order
+        const int c = threadIdx.x >> 3, j = threadIdx.x & 7;
+        float t = red[0][c][j];
+#pragma unroll 8
+        for (int k = 1; k < 64; k++) t += red[k][c][j];
+        gb_part[(size_t)blockIdx.y * stride + blockIdx.x * 32 + threadIdx.x] = t;
+    }
+}
+void tc_colsum_bf16_v(float* gb_part, size_t stride, int splits, const void* g16, int m, int l) {
+    int rows = div_up(m, splits);
+    rows = div_up(rows, 32) * 32;
+    dim3 grid(div_up(l, 32), splits, 1);
+    B200_LAUNCH(colsum_bf16_kernel, grid, 256, 0, gb_part, stride, static_cast<const __nv_bfloat16*>(g16), m, l, rows);
+}
+
+// [rows][n] fp32 -> [rows][npad] bf16, zero padded columns (first layer of a low-dimensional env: K padded to one 64-wide k-block)
+__global__ void __launch_bounds__(256) pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t rows, int n, int npad) {
+    const size_t total = rows * (size_t)npad, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const size_t r = e / npad;
+        const int k = (int)(e - r * npad);
+        dst[e] = __float2bfloat16_rn(k < n ? src[r * n + k] : 0.f);
+    }
+}
+void tc_pad_bf16_v(const float* src, void* dst, size_t rows, int n, int npad) {
+    const int blocks = (int)std::min<size_t>((rows * npad + 255) / 256, (size_t)num_sms() * 8);
+    B200_LAUNCH(pad_bf16_kernel, blocks, 256, 0, src, static_cast<__nv_bfloat16*>(dst), rows, n, npad);
+}
+// slabs [splits][l][npad] (tensor-core dW of a K-padded layer) -> gW slabs [l][n] at gW_part + s * stride
+__global__ void __launch_bounds__(256) unpad_slabs_kernel(const float* __restrict__ src, float* __restrict__ gW_part, size_t stride, int l, int n, int npad) {
+    const int total = l * n;
+    const float* s = src + (size_t)blockIdx.y * l * npad;
+    float* d = gW_part + (size_t)blockIdx.y * stride;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int j = e / n, k = e - j * n;
+        d[e] = s[(size_t)j * npad + k];
+    }
+}
+void tc_unpad_slabs(const float* src, float* gW_part, size_t stride, int splits, int l, int n, int npad) {
+    dim3 grid(std::max(1, std::min(64, div_up(l * n, 256))), splits, 1);
+    B200_LAUNCH(unpad_slabs_kernel, grid, 256, 0, src, gW_part, stride, l, n, npad);
+}
+
 void tc_linear_forward_bf16_v(float* y, void* y16, const void* x16, const void* W16, const float* b, int m, int n, int l, int act) {
     tc_linear_forward_bf16(y, static_cast<__nv_bfloat16*>(y16), static_cast<const __nv_bfloat16*>(x16), static_cast<const __nv_bfloat16*>(W16), b, m, n, l, act);
 }
