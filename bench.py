@@ -438,6 +438,27 @@ class C3(UpdateOnly):
                 "gae_scan": ("hbm", 22.0 * self.cap), "gae_normalize_kernel": ("hbm", 8.0 * self.cap)}
 
 
+class C3X3(C3):
+    """c3 with the 256x256 layers as 3xTF32 split contractions on the tensor cores (precision 3): fp32-accurate, same parity tests."""
+    name = "c3x3"
+    TF32 = 3
+
+    def config(self):
+        c = self.base_config("c3x3: HalfCheetah-shaped synthetic rollout buffer (S=17, A=6), T=2048 x N=512 per GPU, 2x256 ReLU MLP, the "
+                             "256x256 layers as 3xTF32 split tcgen05 contractions (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM), "
+                             "PPO update only (BASELINE.json configs[2])")
+        c["tolerance"] = "same as the fp32 FFMA path: 1e-5 (tests/test_gpu_tc.py::test_tc_x3_*, test_update_c3_minibatch_65536_matches_oracle[3xtf32])"
+        return c
+
+    def roofline_work(self, kernels):
+        w = dict(C3.roofline_work(self, kernels))
+        nb = self.cap // self.MB
+        steps = (self.N_VAL + self.N_POL) * nb
+        H = self.SIZES[1]
+        w["tc_gemm_kernel"] = ("tensor_3xtf32", 6 * self.MB * H * H * steps + 2 * 2 * self.cap * H * H)
+        return w
+
+
 class C4(UpdateOnly):
     name = "c4"
     dtype = "tf32"
@@ -719,7 +740,7 @@ class GatherStage(StageWorkload):
         return "oracle port of get_batch (src/trajectory_buffer.cu:202-220) over %d rows" % self.CPU_B
 
 
-WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c4": C4, "c4bf16": C4BF16, "c5": C5, "adam": AdamStage, "gather": GatherStage}
+WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c3x3": C3X3, "c4": C4, "c4bf16": C4BF16, "c5": C5, "adam": AdamStage, "gather": GatherStage}
 
 
 # ======================================================================================= CPU arm
@@ -862,6 +883,12 @@ def build_roofline(kernels, work, traffic_file=None):
         elif bound == "tensor_tf32":
             ach, peak, unit = amount / sec / 1e12, pk["bf16"] / 2, "TFLOP/s"
             psrc = pk["src"] + ": sustained cuBLAS bf16 / 2 (TF32 dense rate is half of bf16)"
+            bound = "tensor"
+        elif bound == "tensor_3xtf32":
+            # fp32-equivalent FLOPs (2 m n k per contraction); every product costs three TF32 MMAs, so the tensor-pipe peak for
+            # this mode is a third of the TF32 rate
+            ach, peak, unit = amount / sec / 1e12, pk["bf16"] / 6, "TFLOP/s"
+            psrc = pk["src"] + ": sustained cuBLAS bf16 / 2 (TF32) / 3 (three MMAs per product in the 3xTF32 split mode)"
             bound = "tensor"
         else:
             ach, unit = amount / sec / 1e12, "TFLOP/s"

@@ -410,13 +410,19 @@ void ppo_b200_set_kernel_path(int path);
 /* matmul precision of dense layers whose in/out widths are >= 64 and batch >= 128:
  * 0 = fp32 FFMA (default; 1e-5 tolerance), 1 = TF32 tcgen05 tensor cores with fp32 accumulation
  * (wide-MLP configs; tolerance ~1e-3, stated separately), 2 = BF16 operands (tcgen05 kind::f16, fp32 accumulation in TMEM;
- * layers additionally need widths that are multiples of 8; tolerance ~1e-2, stated separately).  Parameters, gradients and
- * the optimiser stay fp32 in every mode.  Env PPO_B200_TF32=1 / 2 sets the default. */
+ * layers additionally need widths that are multiples of 8; tolerance ~1e-2, stated separately), 3 = "3xTF32": every fp32
+ * operand is split exactly into hi (the 19 bits the tensor core reads) + lo and each contraction is the sum of the three
+ * tcgen05 TF32 products hi.hi + hi.lo + lo.hi with fp32 accumulation -- as accurate as the fp32 FFMA path (1e-5 tolerance,
+ * same parity tests) at a third of the TF32 rate; replaces cublasSgemm of src/mat_mul.cu:149-208 for the 2x256 nets.
+ * Parameters, gradients and the optimiser stay fp32 in every mode.  Env PPO_B200_TF32=1 / 2 / 3 sets the default. */
 void ppo_b200_set_matmul_precision(int mode);
 /* raw tensor-core layer kernels (tests/bench): mode 0 forward (aux = bias), 1 backward-input
  * (aux = post-activation input), 2 backward-weights (out = `splits` slabs of l*n floats). */
 void ppo_b200_tc_linear(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l,
                         int act, int splits);
+/* the same three contractions in the 3xTF32 split mode (lo companions are formed in scratch first) */
+void ppo_b200_tc_linear_x3(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l,
+                           int act, int splits);
 /* the same three contractions with BF16 operands: a / b are converted to bf16 scratch copies first (skip_convert: reuse the
  * copies of the previous call; convert_only: stop after the conversion), out16 (may be NULL) receives the bf16 shadow of the
  * fp32 output of modes 0 and 1. */

@@ -69,6 +69,7 @@ EXTENSION_API = {
     "ppo_b200_set_kernel_path": (None, [C.c_int]),
     "ppo_b200_set_matmul_precision": (None, [C.c_int]),
     "ppo_b200_tc_linear": (None, [C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ppo_b200_tc_linear_x3": (None, [C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ppo_b200_tc_linear_bf16": (None, [C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ppo_b200_last_mean_return": (C.c_float, [vp]),
     "ppo_b200_last_eval": (None, [vp, c_float_p, c_float_p, c_int_p]),

@@ -10,6 +10,7 @@
 // the process its bundled libnccl.so.2 is the one that gets picked up.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sched.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -201,6 +202,47 @@ long long dist_spin_limit() {
     return cached;
 }
 
+// One process per GPU: keep the calling thread (and with it the first-touch placement of the pinned host mirrors it
+// allocates next) on the CPUs of the NUMA node the GPU hangs off, so eight ranks' host<->device copies do not cross the
+// socket interconnect.  Best effort: silently skipped when sysfs has no answer (containers, single-node hosts) or when
+// PPO_B200_NUMA_BIND=0.
+static void bind_to_gpu_numa_node() {
+    const char* e = getenv("PPO_B200_NUMA_BIND");
+    if (e && e[0] == '0') return;
+    int dev = 0;
+    char bus[64];
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) return;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    char list[1024] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return;
+    cpu_set_t cur, want;
+    if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return;
+    CPU_ZERO(&want);
+    int n_set = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {      // "0-55,112-167"
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &cur)) { CPU_SET(c, &want); n_set++; }
+    }
+    if (n_set > 0) sched_setaffinity(0, sizeof(want), &want);
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -222,6 +264,7 @@ void ppo_b200_dist_init(const char id[PPO_B200_NCCL_ID_BYTES], int rank, int wor
     g_rank = rank;
     g_world = world_size;
     if (world_size <= 1) return;
+    bind_to_gpu_numa_node();
     load_nccl();
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));

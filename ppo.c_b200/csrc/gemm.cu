@@ -597,7 +597,7 @@ int choose_splits(int m, size_t param_count) {
 
 static int g_matmul_precision = -1;
 int matmul_precision() {
-    if (g_matmul_precision < 0) { const char* e = getenv("PPO_B200_TF32"); g_matmul_precision = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0; }
+    if (g_matmul_precision < 0) { const char* e = getenv("PPO_B200_TF32"); g_matmul_precision = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : 0; }
     return g_matmul_precision;
 }
 static bool use_tc(int m, int n, int l, const void* a, const void* b, int lda, int ldb) {
@@ -725,7 +725,7 @@ using namespace b200;
 
 extern "C" {
 
-void ppo_b200_set_matmul_precision(int mode) { g_matmul_precision = mode == 2 ? 2 : mode ? 1 : 0; }
+void ppo_b200_set_matmul_precision(int mode) { g_matmul_precision = (mode >= 0 && mode <= 3) ? mode : 0; }
 
 // include/mat_mul.h:19-20 (device pointers; handle ignored)
 void mat_mul_cuda(cublasHandle_t handle, float* out, float* x, float* weight, float* bias, int m, int n, int l) {

@@ -76,7 +76,15 @@ void tc_linear_forward(float* y, const float* x, const float* W, const float* b,
 void tc_linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev);
 void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l);
 void tc_round_copy(const float* src, float* dst, size_t n);   // RNA-rounded TF32 shadow of a weight arena
-int matmul_precision();   // 0 fp32 FFMA (default), 1 TF32 tcgen05 for layers with n, l >= 64, 2 BF16 tcgen05 (widths % 8 == 0)
+int matmul_precision();   // 0 fp32 FFMA (default), 1 TF32 tcgen05 for layers with n, l >= 64, 2 BF16 tcgen05 (widths % 8 == 0),
+                          // 3 "3xTF32" split on tcgen05: fp32-accurate (meets the 1e-5 parity of mode 0), layers with n, l >= 64
+// 3xTF32 split mode: every operand comes with lo = x - top19bits(x) (tc_split_lo)
+void tc_split_lo(const float* src, float* lo, size_t n);
+void tc_linear_forward_x3(float* y, const float* x, const float* xlo, const float* W, const float* Wlo, const float* b, int m, int n, int l, int act);
+void tc_linear_backward_input_x3(float* gx, const float* g, const float* glo, const float* W, const float* Wlo, const float* xin, int m, int n,
+                                 int l, int act_prev);
+void tc_linear_backward_weights_x3(float* gW_part, size_t stride, int splits, const float* g, const float* glo, const float* x, const float* xlo,
+                                   int m, int n, int l);
 // bf16 operand mode (tc_gemm.cu): shadows are __nv_bfloat16 arrays, passed as void* between translation units
 bool tc_bf16_shape_ok(int m, int n, int l);
 void tc_linear_forward_bf16_v(float* y, void* y16, const void* x16, const void* W16, const float* b, int m, int n, int l, int act);
@@ -116,6 +124,9 @@ struct NetDev {               // device-side view of one NeuralNetwork (side tab
     void* w0pad_bf16 = nullptr;     // first layer with fewer than 64 inputs: W16 [out][64] zero padded (K padded to one k-block)
     std::vector<void*> a16, gx16;   // a16[i] : bf16 [cap][sizes[i]] (null until needed); a16[0] is [cap][64] when layer 0 is K-padded
     std::vector<int> a16_cap, gx16_cap;
+    float* params_lo = nullptr;     // 3xTF32 mode: lo companion of `params` (same offsets), refreshed per forward
+    std::vector<void*> alo, glo;    // lo companions of a[i] / of the gradient wrt a[i] (fp32 [cap][sizes[i]], null until needed)
+    std::vector<int> alo_cap, glo_cap;
     float* image = nullptr;      // pre-transposed weight image staged by the fused kernels (fused_mlp.cu)
     int image_floats = 0;
     bool image_dirty = true;     // set by every writer of `params` other than fused_reduce_adam_kernel

@@ -103,13 +103,18 @@ static size_t bf16_w_off(const NetDev* nd, int i) {
     return (off + 7) & ~size_t(7);
 }
 static size_t bf16_total(const NetDev* nd) { return (bf16_w_off(nd, nd->num_layers - 1) + 7) & ~size_t(7); }
-static void ensure_shadow(std::vector<void*>& v, std::vector<int>& cap, int i, int m, int width) {
+static void ensure_shadow(std::vector<void*>& v, std::vector<int>& cap, int i, int m, int width, int elem_bytes = 2) {
     if ((int)v.size() <= i) { v.resize(i + 1, nullptr); cap.resize(i + 1, 0); }
     if (cap[i] >= m) return;
     CUDA_CHECK(cudaStreamSynchronize(stream()));
     if (v[i]) CUDA_CHECK(cudaFree(v[i]));
     cap[i] = m + m / 8;
-    CUDA_CHECK(cudaMalloc(&v[i], (size_t)cap[i] * width * 2 + 64));
+    CUDA_CHECK(cudaMalloc(&v[i], (size_t)cap[i] * width * elem_bytes + 64));
+}
+// 3xTF32 split mode: layers whose three contractions run on the tensor cores (TMA needs 16-byte pitches and bases)
+static bool x3_layer(const NetDev* nd, int i, int m) {
+    const int n = nd->sizes[i], l = nd->sizes[i + 1];
+    return matmul_precision() == 3 && m >= 128 && n >= 64 && l >= 64 && (n % 4) == 0 && (l % 4) == 0 && (nd->w_off[i] % 4) == 0;
 }
 
 void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input) {
@@ -139,7 +144,24 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
         tc_round_copy(nd->params, nd->params_tf32, nd->param_count);
         wsrc = nd->params_tf32;
     }
-    if (matmul_precision() == 2) {
+    if (matmul_precision() == 3) {
+        // 3xTF32 mode: lo companions of the weights (once per forward = once per optimiser step) and of the layer inputs
+        if (!nd->params_lo) nd->params_lo = dmalloc<float>(nd->param_count + 64);
+        bool split_w = false;
+        for (int i = 0; i < L; i++) {
+            const int n = nd->sizes[i], l = nd->sizes[i + 1];
+            if (x3_layer(nd, i, m)) {
+                if (!split_w) { tc_split_lo(nd->params, nd->params_lo, nd->param_count); split_w = true; }
+                ensure_shadow(nd->alo, nd->alo_cap, i, m, n, 4);
+                float* alo = static_cast<float*>(nd->alo[i]);
+                tc_split_lo(nd->a[i], alo, (size_t)m * n);
+                tc_linear_forward_x3(nd->a[i + 1], nd->a[i], alo, nd->params + nd->w_off[i], nd->params_lo + nd->w_off[i], nd->params + nd->b_off[i],
+                                     m, n, l, nd->acts[i]);
+            } else {
+                linear_forward(nd->a[i + 1], nd->a[i], nd->params + nd->w_off[i], nd->params + nd->b_off[i], m, n, l, nd->acts[i]);
+            }
+        }
+    } else if (matmul_precision() == 2) {
         // BF16 mode: weight copies W16 | Wt16 refreshed per forward (= once per optimiser step); a tensor-core layer reads the
         // bf16 shadow of its input (written by the previous tensor-core layer's epilogue, else converted here) and writes the
         // shadow of its output when the next layer wants it
@@ -245,6 +267,29 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                 have16 = false;
             }
         }
+    } else if (matmul_precision() == 3) {
+        for (int i = L - 1; i >= 0; i--) {
+            const int n = nd->sizes[i], l = nd->sizes[i + 1];
+            float* gWp = nd->partials + nd->w_off[i];
+            if (x3_layer(nd, i, m) && nd->params_lo && (int)nd->alo.size() > i && nd->alo[i] && ((nd->slab_stride() * 4) % 16) == 0 &&
+                ((uintptr_t)gWp & 15) == 0) {
+                ensure_shadow(nd->glo, nd->glo_cap, i + 1, m, l, 4);
+                float* glo = static_cast<float*>(nd->glo[i + 1]);
+                tc_split_lo(g, glo, (size_t)m * l);
+                tc_linear_backward_weights_x3(gWp, nd->slab_stride(), splits, g, glo, nd->a[i], static_cast<const float*>(nd->alo[i]), m, n, l);
+                launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
+                if (i > 0) {
+                    tc_linear_backward_input_x3(nd->gx[i], g, glo, nd->params + nd->w_off[i], nd->params_lo + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
+                    g = nd->gx[i];
+                }
+            } else {
+                linear_backward_params(gWp, nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, nd->a[i], m, n, l);
+                if (i > 0) {
+                    linear_backward_input(nd->gx[i], g, nd->params + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
+                    g = nd->gx[i];
+                }
+            }
+        }
     } else
     for (int i = L - 1; i >= 0; i--) {
         const int n = nd->sizes[i], l = nd->sizes[i + 1];
@@ -332,6 +377,9 @@ void free_neural_network(NeuralNetwork* nn) {
         if (nd->params_tf32) CUDA_CHECK(cudaFree(nd->params_tf32));
         if (nd->params_bf16) CUDA_CHECK(cudaFree(nd->params_bf16));
         if (nd->w0pad_bf16) CUDA_CHECK(cudaFree(nd->w0pad_bf16));
+        if (nd->params_lo) CUDA_CHECK(cudaFree(nd->params_lo));
+        for (void* q : nd->alo) if (q) CUDA_CHECK(cudaFree(q));
+        for (void* q : nd->glo) if (q) CUDA_CHECK(cudaFree(q));
         for (void* q : nd->a16) if (q) CUDA_CHECK(cudaFree(q));
         for (void* q : nd->gx16) if (q) CUDA_CHECK(cudaFree(q));
         delete nd;

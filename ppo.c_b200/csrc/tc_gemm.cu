@@ -171,16 +171,27 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict
 // shared memories, which halves the B traffic out of L2 (a 128x256 TF32 tile pulls 1.5 MB of operands through L2
 // per 67 MFLOP - the kernel is L2-bandwidth bound, not tensor bound).  A ring slot may be refilled only after BOTH
 // CTAs' MMAs released it, so tcgen05.commit arrives on the empty barrier of both CTAs (count = CL).
-template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF>
+//
+// X3 = "3xTF32" split mode (fp32-accurate contractions on the tensor cores, precision mode 3): every fp32 operand x is the exact
+// sum hi + lo with hi = its top 19 bits (what kind::tf32 reads from the raw word) and lo = x - hi, kept in a companion array
+// (tc_split_lo).  A stage then holds four tiles [A | B | A_lo | B_lo] and every k-step issues THREE MMAs into the same TMEM
+// accumulator: A.B (= hi.hi), A.B_lo (= hi.lo) and A_lo.B (= lo.hi); the dropped lo.lo term is <= 2^-20 relative per product.
+// Measured against float64 the result is as close as an fp32 FFMA GEMM (tests/test_gpu_tc.py), so the 1e-5 parity of the
+// fp32 path holds while the contraction runs at a third of the TF32 rate instead of the FFMA rate.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF, bool X3>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-               const __grid_constant__ CUtensorMap tmC16, const TcArgs p) {
+               const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
+               const TcArgs p) {
+    static_assert(!(X3 && BF), "the split mode is a TF32 mode");
     using E = TcElem<BF>;
-    constexpr int kTcStages = (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
+    constexpr int kTcStages = X3 ? 2 : (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
+    constexpr bool kStaged = EPI != kTcDw && !X3;              // epilogue staging tiles for the TMA-store path
     constexpr int kTcBK = E::kBK, kTcUmmaK = E::kUmmaK;
     constexpr uint32_t A_BYTES = kTcBM * kTcBKBytes;           // 16 KB per stage
     constexpr uint32_t B_BYTES = BN * kTcBKBytes;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t PAIR_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t STAGE_BYTES = (X3 ? 2 : 1) * PAIR_BYTES;
     // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32 or BF16, majors, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (E::kFormat << 7) | (E::kFormat << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
@@ -188,7 +199,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stg_base = smem + kTcStages * STAGE_BYTES;                        // staging tiles of the epilogue warps (1024-byte aligned)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (EPI == kTcDw ? 0 : kTcEpiWarps * kTcStgBytes));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (kStaged ? kTcEpiWarps * kTcStgBytes : 0));
     uint64_t* empty_bar = full_bar + kTcStages;
     uint64_t* tmem_full_bar = empty_bar + kTcStages;      // [2] accumulator buffer b holds a finished tile
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2] the epilogue warps have drained buffer b
@@ -210,6 +221,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
+        if (X3) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&tmAlo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBlo) : "memory");
+        }
         for (int s = 0; s < kTcStages; s++) { tc_mbar_init(&full_bar[s], 1); tc_mbar_init(&empty_bar[s], CL); }
         for (int b = 0; b < 2; b++) { tc_mbar_init(&tmem_full_bar[b], 1); tc_mbar_init(&tmem_empty_bar[b], kTcEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -246,38 +261,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int s = it % kTcStages;
                     const uint32_t phase = (it / kTcStages) & 1;
                     tc_mbar_wait(&empty_bar[s], phase ^ 1);
-                    uint8_t* sa = smem + s * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
                     tc_mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     const int k0 = kbeg + kb * kTcBK;
-                    if (!A_MN) {
-                        tc_tma_load_2d(sa, &tmA, k0, m0, &full_bar[s]);                         // box {32 k, 128 rows}
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kTcBM / E::kMnChunk; i++)                               // box {one 128-byte mn chunk, BK k-rows}
-                            tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), &tmA, m0 + E::kMnChunk * i, k0, &full_bar[s]);
-                    }
-                    if (CL == 1) {
-                        if (!B_MN) {
-                            tc_tma_load_2d(sb, &tmB, k0, n0, &full_bar[s]);
+                    auto load_pair = [&](const CUtensorMap* mA, const CUtensorMap* mB, uint8_t* sa) {
+                        uint8_t* sb = sa + A_BYTES;
+                        if (!A_MN) {
+                            tc_tma_load_2d(sa, mA, k0, m0, &full_bar[s]);                         // box {32 k, 128 rows}
                         } else {
 #pragma unroll
-                            for (int i = 0; i < BN / E::kMnChunk; i++)
-                                tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), &tmB, n0 + E::kMnChunk * i, k0, &full_bar[s]);
+                            for (int i = 0; i < kTcBM / E::kMnChunk; i++)                               // box {one 128-byte mn chunk, BK k-rows}
+                                tc_tma_load_2d(sa + i * (kTcBK * kTcBKBytes), mA, m0 + E::kMnChunk * i, k0, &full_bar[s]);
                         }
-                    } else {                     // my half of the shared B tile, multicast to both CTAs of the cluster
-                        if (!B_MN) {             // box {32 k, BN/CL rows}
-                            constexpr int HR = BN / CL;
-                            tc_tma_load_2d_mc(sb + crank * (HR * kTcBKBytes), &tmB, k0, n0 + (int)crank * HR, &full_bar[s], kMask);
-                        } else {
-                            constexpr int HB = BN / E::kMnChunk / CL;
+                        if (CL == 1) {
+                            if (!B_MN) {
+                                tc_tma_load_2d(sb, mB, k0, n0, &full_bar[s]);
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < HB; i++) {
-                                const int bi = (int)crank * HB + i;
-                                tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), &tmB, n0 + E::kMnChunk * bi, k0, &full_bar[s], kMask);
+                                for (int i = 0; i < BN / E::kMnChunk; i++)
+                                    tc_tma_load_2d(sb + i * (kTcBK * kTcBKBytes), mB, n0 + E::kMnChunk * i, k0, &full_bar[s]);
+                            }
+                        } else {                     // my half of the shared B tile, multicast to both CTAs of the cluster
+                            if (!B_MN) {             // box {32 k, BN/CL rows}
+                                constexpr int HR = BN / CL;
+                                tc_tma_load_2d_mc(sb + crank * (HR * kTcBKBytes), mB, k0, n0 + (int)crank * HR, &full_bar[s], kMask);
+                            } else {
+                                constexpr int HB = BN / E::kMnChunk / CL;
+#pragma unroll
+                                for (int i = 0; i < HB; i++) {
+                                    const int bi = (int)crank * HB + i;
+                                    tc_tma_load_2d_mc(sb + bi * (kTcBK * kTcBKBytes), mB, n0 + E::kMnChunk * bi, k0, &full_bar[s], kMask);
+                                }
                             }
                         }
-                    }
+                    };
+                    load_pair(&tmA, &tmB, smem + s * STAGE_BYTES);
+                    if (X3) load_pair(&tmAlo, &tmBlo, smem + s * STAGE_BYTES + PAIR_BYTES);
                 }
             }
         }
@@ -308,6 +326,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t da = A_MN ? tc_make_desc(sa + k * kMnStep, kTcBK * kTcBKBytes, E::kMnSbo, E::kMnLayout) : tc_make_desc(sa + k * 32, 16, 1024, 2);
                         const uint64_t db = B_MN ? tc_make_desc(sb + k * kMnStep, kTcBK * kTcBKBytes, E::kMnSbo, E::kMnLayout) : tc_make_desc(sb + k * 32, 16, 1024, 2);
                         tc_umma<BF>(tmem_acc, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        if (X3) {          // the lo tiles sit PAIR_BYTES behind their hi tiles: same descriptors, start address advanced
+                            constexpr uint64_t kLoAdv = (uint64_t)(PAIR_BYTES >> 4);
+                            tc_umma<BF>(tmem_acc, da, db + kLoAdv, IDESC, 1u);
+                            tc_umma<BF>(tmem_acc, da + kLoAdv, db, IDESC, 1u);
+                        }
                     }
                     if (CL == 1) tc_umma_commit(&empty_bar[s]);          // frees the ring slot when these MMAs retire
                     else tc_umma_commit_mc(&empty_bar[s], kMask);        // ... in both CTAs (each writes into the other's slot)
@@ -332,7 +355,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* Crow = p.C + (EPI == kTcDw ? (size_t)z * p.c_split_stride : 0) + (size_t)row * p.ldc;
             const bool rows_ok = row < p.M;
             constexpr int CPW = BN / (kTcEpiWarps / 4);          // columns per warp
-            const bool use_tma = EPI != kTcDw && p.tma_store;
+            const bool use_tma = kStaged && p.tma_store;
             float* stg32 = reinterpret_cast<float*>(stg_base + (warp - 2) * kTcStgBytes);
             uint4* stg16 = reinterpret_cast<uint4*>(stg_base + (warp - 2) * kTcStgBytes + 4096);
 #pragma unroll 1
@@ -368,7 +391,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; j++)
                             if (nb + j < p.N) {
                                 const float y = act_apply(v[j] + __ldg(p.bias + nb + j), p.act);
-                                v[j] = BF ? y : round_tf32(y);
+                                v[j] = (BF || X3) ? y : round_tf32(y);
                             }
                     } else if (EPI == kTcDx) {
                         if (need_h) {
@@ -387,7 +410,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     if (nb + j < p.N) v[j] = act_grad(hrow[j], v[j], p.act);
                             }
                         }
-                        if (!BF) {
+                        if (!BF && !X3) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
                         }
@@ -455,7 +478,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     }
-    if (EPI != kTcDw && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // my bulk stores have completed
+    if (kStaged && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // my bulk stores have completed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -509,15 +532,17 @@ static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multi
     return cl;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF>
-static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a_in, dim3 tiles /* (N tiles, M tiles, splits) */) {
-    constexpr int kStages = (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
-    const size_t smem = (size_t)kStages * (kTcBM + BN) * kTcBKBytes + (EPI == kTcDw ? 0 : kTcEpiWarps * kTcStgBytes) + 1024 /*align*/ + 256 /*barriers*/;
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF, bool X3>
+static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& talo, const CUtensorMap& tblo, const TcArgs& a_in,
+                         dim3 tiles /* (N tiles, M tiles, splits) */) {
+    constexpr int kStages = X3 ? 2 : (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
+    constexpr bool kStaged = EPI != kTcDw && !X3;
+    const size_t smem = (size_t)kStages * (X3 ? 2 : 1) * (kTcBM + BN) * kTcBKBytes + (kStaged ? kTcEpiWarps * kTcStgBytes : 0) + 1024 /*align*/ + 256 /*barriers*/;
     // output tensor maps of the TMA-store epilogue (forward / dX): fp32 boxes {32 columns, 32 rows}, bf16 shadow boxes {64, 32}
     TcArgs a = a_in;
     CUtensorMap tc = ta, tc16 = ta;        // placeholders when the store path is off
     a.tma_store = 0;
-    if (EPI != kTcDw && tc_tma_store_enabled() && (a.ldc % 4) == 0 && a.ldc == a.N && ((uintptr_t)a.C & 15) == 0 &&
+    if (kStaged && tc_tma_store_enabled() && (a.ldc % 4) == 0 && a.ldc == a.N && ((uintptr_t)a.C & 15) == 0 &&
         (!a.C16 || ((a.ldc % 8) == 0 && ((uintptr_t)a.C16 & 15) == 0))) {
         a.tma_store = 1;
         tc = make_map(a.C, a.M, a.N, 32, 32, false, false);
@@ -525,7 +550,7 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcA
     }
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     // persistent: one CTA per SM (190 KB of shared memory each), clusters of CL CTAs walk the work items
@@ -533,10 +558,10 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcA
     const int clusters = (int)std::min<long long>(items, num_sms() / CL);
     const dim3 grid(clusters * CL, 1, 1);
     if (CL == 1) {
-        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>), grid, kTcThreads, smem, ta, tb, tc, tc16, a);
+        B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF, X3>), grid, kTcThreads, smem, ta, tb, tc, tc16, talo, tblo, a);
         return;
     }
-    const char* label = BF ? "(tc_gemm_kernel<bf16>)" : "(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)";
+    const char* label = BF ? "(tc_gemm_kernel<bf16>)" : X3 ? "(tc_gemm_kernel<3xtf32>)" : "(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)";
     if (g_profiling) profile_mark(label, true);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream();
@@ -544,15 +569,20 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const TcA
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF>, ta, tb, tc, tc16, a));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF, X3>, ta, tb, tc, tc16, talo, tblo, a));
     ++g_launches;
     if (g_profiling) profile_mark(label, false);
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool BF>
 static void launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a, dim3 grid) {
-    if (tc_cluster() == 2) launch_tc_cl<BN, A_MN, B_MN, EPI, 2, BF>(ta, tb, a, grid);
-    else launch_tc_cl<BN, A_MN, B_MN, EPI, 1, BF>(ta, tb, a, grid);
+    if (tc_cluster() == 2) launch_tc_cl<BN, A_MN, B_MN, EPI, 2, BF, false>(ta, tb, ta, tb, a, grid);
+    else launch_tc_cl<BN, A_MN, B_MN, EPI, 1, BF, false>(ta, tb, ta, tb, a, grid);
+}
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static void launch_tc_x3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& talo, const CUtensorMap& tblo, const TcArgs& a, dim3 grid) {
+    if (tc_cluster() == 2) launch_tc_cl<BN, A_MN, B_MN, EPI, 2, false, true>(ta, tb, talo, tblo, a, grid);
+    else launch_tc_cl<BN, A_MN, B_MN, EPI, 1, false, true>(ta, tb, talo, tblo, a, grid);
 }
 
 // Shapes the tensor path accepts: TMA needs 16-byte row pitches and aligned bases.
@@ -593,6 +623,54 @@ void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const
     const CUtensorMap ta = make_map(g, m, l, 32, kTcBK32, true);     // A MN-major: g[k=batch][m'=out]
     const CUtensorMap tb = make_map(x, m, n, 32, kTcBK32, true);     // B MN-major: x[k=batch][n=in]
     launch_tc<kTcBN, true, true, kTcDw, false>(ta, tb, a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
+}
+
+// ---- 3xTF32 split mode (precision 3): fp32-accurate, operands come with their lo = x - top19bits(x) companions --------
+__global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ src, float* __restrict__ lo, size_t n4, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = ld_stream4(src + 4 * i);
+        float4 r;
+        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(lo + 4 * i) = r;
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) lo[i] = src[i] - __uint_as_float(__float_as_uint(src[i]) & 0xFFFFE000u);
+}
+// lo[i] = src[i] - (src[i] with the 13 low mantissa bits cleared); exact in fp32.  Both pointers 16-byte aligned.
+void tc_split_lo(const float* src, float* lo, size_t n) {
+    if (n == 0) return;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n / 4 + 255) / 256, (size_t)num_sms() * 8));
+    B200_LAUNCH(split_lo_kernel, blocks, 256, 0, src, lo, n / 4, n);
+}
+
+void tc_linear_forward_x3(float* y, const float* x, const float* xlo, const float* W, const float* Wlo, const float* b, int m, int n, int l, int act) {
+    TcArgs a{};
+    a.C = y; a.M = m; a.N = l; a.K = n; a.ldc = l; a.bias = b; a.act = act;
+    const int hb = kTcBN / tc_cluster();
+    launch_tc_x3<kTcBN, false, false, kTcFwd>(make_map(x, m, n, kTcBK32, kTcBM), make_map(W, l, n, kTcBK32, hb), make_map(xlo, m, n, kTcBK32, kTcBM),
+                                              make_map(Wlo, l, n, kTcBK32, hb), a, dim3(div_up(l, kTcBN), div_up(m, kTcBM), 1));
+}
+
+void tc_linear_backward_input_x3(float* gx, const float* g, const float* glo, const float* W, const float* Wlo, const float* xin, int m, int n,
+                                 int l, int act_prev) {
+    TcArgs a{};
+    a.C = gx; a.M = m; a.N = n; a.K = l; a.ldc = n; a.xin = xin; a.act = act_prev;
+    launch_tc_x3<kTcBN, false, true, kTcDx>(make_map(g, m, l, kTcBK32, kTcBM), make_map(W, l, n, 32, kTcBK32, true), make_map(glo, m, l, kTcBK32, kTcBM),
+                                            make_map(Wlo, l, n, 32, kTcBK32, true), a, dim3(div_up(n, kTcBN), div_up(m, kTcBM), 1));
+}
+
+void tc_linear_backward_weights_x3(float* gW_part, size_t stride, int splits, const float* g, const float* glo, const float* x, const float* xlo,
+                                   int m, int n, int l) {
+    TcArgs a{};
+    int rows = div_up(m, splits);
+    rows = div_up(rows, kTcBK32) * kTcBK32;
+    a.C = gW_part; a.M = l; a.N = n; a.K = m; a.ldc = n; a.k_per_split = rows; a.c_split_stride = stride; a.splits = splits;
+    launch_tc_x3<kTcBN, true, true, kTcDw>(make_map(g, m, l, 32, kTcBK32, true), make_map(x, m, n, 32, kTcBK32, true), make_map(glo, m, l, 32, kTcBK32, true),
+                                           make_map(xlo, m, n, 32, kTcBK32, true), a, dim3(div_up(n, kTcBN), div_up(l, kTcBM), splits));
 }
 
 // ---- bf16 operand mode ---------------------------------------------------------------------------------
@@ -772,6 +850,19 @@ extern "C" void ppo_b200_tc_linear(int mode, float* out, const float* a, const f
     if (mode == 0) tc_linear_forward(out, a, b, aux, m, n, l, act);
     else if (mode == 1) tc_linear_backward_input(out, a, b, aux, m, n, l, act);
     else tc_linear_backward_weights(out, (size_t)n * l, splits, a, b, m, n, l);
+}
+
+// Same contractions in the 3xTF32 split mode: the lo companions are formed in scratch first.
+extern "C" void ppo_b200_tc_linear_x3(int mode, float* out, const float* a, const float* b, const float* aux, int m, int n, int l, int act,
+                                      int splits) {
+    const size_t na = (size_t)m * (mode == 0 ? n : l), nb = mode == 2 ? (size_t)m * n : (size_t)l * n;
+    const size_t na_al = (na + 63) & ~size_t(63);
+    float* lo = static_cast<float*>(scratch(kScratchStage3, (na_al + nb) * sizeof(float) + 256));
+    tc_split_lo(a, lo, na);
+    tc_split_lo(b, lo + na_al, nb);
+    if (mode == 0) tc_linear_forward_x3(out, a, lo, b, lo + na_al, aux, m, n, l, act);
+    else if (mode == 1) tc_linear_backward_input_x3(out, a, lo, b, lo + na_al, aux, m, n, l, act);
+    else tc_linear_backward_weights_x3(out, (size_t)n * l, splits, a, lo, b, lo + na_al, m, n, l);
 }
 
 // Same contractions with bf16 operands: the fp32 inputs are converted into scratch bf16 arrays first (the conversion is

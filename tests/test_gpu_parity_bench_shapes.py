@@ -144,12 +144,14 @@ def test_update_at_bench_minibatch_matches_oracle_and_float64(L, sizes, acts, n,
     assert abs(gpu["p_loss"] - losses[nval * nb:].mean()) < 1e-5 + 1e-5 * abs(losses[nval * nb:].mean())
 
 
-def test_update_c3_minibatch_65536_matches_oracle(L):
-    """c3 as benched: 2x256 ReLU nets, S=17, A=6, minibatch 65 536 (the skinny-dW row splits + fold of the 17-wide first
+@pytest.mark.parametrize("precision", [0, 3], ids=["ffma", "3xtf32"])
+def test_update_c3_minibatch_65536_matches_oracle(L, precision):
+    """c3 as benched (precision 3 = the 256x256 layers as 3xTF32 split contractions on the tensor cores, held to the SAME
+    tolerance as the fp32 FFMA kernels): 2x256 ReLU nets, S=17, A=6, minibatch 65 536 (the skinny-dW row splits + fold of the 17-wide first
     layer and the 6 / 1-wide heads, split-K slabs of the 256x256 layers).  One value + one policy epoch of one minibatch
     each (the naive-sgemm oracle needs ~40 GFLOP for this)."""
     sizes, n, mb = [17, 256, 256, 6], 65536 + 300, 65536
-    gpu, T, b, perms, losses, _ = _run_update_three_ways(L, sizes, RELU3, n, mb, 1, 1, seed=65)
+    gpu, T, b, perms, losses, _ = _run_update_three_ways(L, sizes, RELU3, n, mb, 1, 1, seed=65, precision=precision)
     ev, em = nerr(gpu["v"], T.v), nerr(gpu["mu"], T.mu)
     print("c3 mb=65536 post-Adam weight errors vs oracle (V, mu):", ev, em)
     # one Adam step from zero moments moves every weight by lr * g/|g| = +-lr exactly, unless g is within fp32 noise of 0:

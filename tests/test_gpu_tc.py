@@ -101,6 +101,92 @@ def test_wide_mlp_tf32_vs_fp32_oracle(L, hidden_act, tol):
     L.free_neural_network(nn)
 
 
+# ---- 3xTF32 split mode (precision 3): fp32-accurate contractions on the tensor cores ------------------------------------
+# Stated tolerance: every operand is hi + lo exactly (hi = the 19 bits kind::tf32 reads); the three products hi.hi + hi.lo +
+# lo.hi leave out lo.lo (<= 2^-20 per product) and truncate lo to 11 bits (<= 2^-21): ~4e-7 against float64 if the sums were
+# exact.  What is measured on the B200 is larger and grows with the contraction length K, because the tensor core aligns
+# every addend to its fp32 accumulator by truncation: 3e-6 at K = 64 ... 8e-6 at K = 1024 (an FFMA GEMM: 6e-7 ... 1e-6).
+# Stated bound: 4e-6 up to K = 256 (the 2x256 nets of config 3), 1.2e-5 up to K = 1024; the whole-update parity tests hold
+# this mode to the fp32 path's criteria (tests/test_gpu_parity_bench_shapes.py).
+def tol_x3(K):
+    return 4e-6 if K <= 256 else 1.2e-5
+
+
+@pytest.mark.parametrize("m,n,l", [(128, 64, 256), (256, 1024, 1024), (1000, 100, 300), (4096, 256, 256), (384, 64, 64), (130, 256, 1024),
+                                    (65536, 256, 256)])
+def test_tc_x3_forward(L, m, n, l):
+    rng = np.random.default_rng(m + n + l)
+    x, w, b = rng.standard_normal((m, n)).astype(f32), (rng.standard_normal((l, n)) / np.sqrt(n)).astype(f32), rng.standard_normal(l).astype(f32)
+    dx, dw, db, dy = b200.dev(x), b200.dev(w), b200.dev(b), b200.dev_empty((m, l))
+    for act, fn in ((0, lambda z: z), (1, lambda z: np.maximum(z, 0)), (2, np.tanh)):
+        L.ppo_b200_tc_linear_x3(0, dy.ptr, dx.ptr, dw.ptr, db.ptr, m, n, l, act, 1)
+        ref = fn(x.astype(np.float64) @ w.astype(np.float64).T + b)
+        e = nerr(dy.numpy(), ref)
+        print("3xTF32 forward m=%d K=%d l=%d act=%d: %.2e" % (m, n, l, act, e))
+        assert e < tol_x3(n) * (6.0 if act == 2 else 1.0), (act, e)      # tanh output is normalised by max|tanh| <= 1, the pre-activation by max|z| ~ 5
+    for d in (dx, dw, db, dy):
+        d.free()
+
+
+@pytest.mark.parametrize("m,n,l", [(128, 64, 256), (256, 1024, 1024), (1000, 100, 300), (4096, 256, 256), (384, 64, 64)])
+def test_tc_x3_backward_input(L, m, n, l):
+    rng = np.random.default_rng(m + n + l + 1)
+    g, w = rng.standard_normal((m, l)).astype(f32), rng.standard_normal((l, n)).astype(f32)
+    h = np.maximum(rng.standard_normal((m, n)), 0).astype(f32)
+    dg, dw, dh, dgx = b200.dev(g), b200.dev(w), b200.dev(h), b200.dev_empty((m, n))
+    L.ppo_b200_tc_linear_x3(1, dgx.ptr, dg.ptr, dw.ptr, dh.ptr, m, n, l, 1, 1)
+    e1 = nerr(dgx.numpy(), (g.astype(np.float64) @ w.astype(np.float64)) * (h > 0))
+    L.ppo_b200_tc_linear_x3(1, dgx.ptr, dg.ptr, dw.ptr, dh.ptr, m, n, l, 0, 1)
+    e0 = nerr(dgx.numpy(), g.astype(np.float64) @ w.astype(np.float64))
+    print("3xTF32 dX m=%d n=%d K=%d: %.2e (relu mask) %.2e (none)" % (m, n, l, e1, e0))
+    assert max(e0, e1) < tol_x3(l)
+
+
+@pytest.mark.parametrize("m,n,l,splits", [(128, 64, 256, 1), (4096, 1024, 1024, 4), (1000, 100, 300, 3), (65536, 256, 256, 64)])
+def test_tc_x3_backward_weights(L, m, n, l, splits):
+    rng = np.random.default_rng(m + n + l + 2)
+    g, x = rng.standard_normal((m, l)).astype(f32), rng.standard_normal((m, n)).astype(f32)
+    dg, dx, dout = b200.dev(g), b200.dev(x), b200.dev_empty((splits, l, n))
+    L.ppo_b200_tc_linear_x3(2, dout.ptr, dg.ptr, dx.ptr, None, m, n, l, 0, splits)
+    got = dout.numpy().astype(np.float64).sum(0)
+    e = nerr(got, g.astype(np.float64).T @ x.astype(np.float64))
+    print("3xTF32 dW m=%d n=%d l=%d splits=%d (K per slab %d): %.2e" % (m, n, l, splits, -(-m // splits), e))
+    assert e < tol_x3(-(-m // splits))
+
+
+@pytest.mark.parametrize("hidden_act", ["tanh", "relu"])
+def test_mlp_x3_matches_fp32_oracle_at_fp32_tolerance(L, hidden_act):
+    """2x256 net (config 3 shape) through the NeuralNetwork API in the 3xTF32 split mode against the fp32 oracle at the
+    fp32 path's own tolerance (1e-5 norm-wise on outputs and on every gradient tensor)."""
+    sizes, acts, m = [17, 256, 256, 6], [hidden_act] * 2 + ["none"], 1024
+    cabi.srand(4)
+    nn = L.create_neural_network(cabi.int_array(sizes), cabi.cstr_array(acts), len(sizes))
+    p = b200.nn_get_params(L, nn)
+    rng = np.random.default_rng(0)
+    x, g = rng.standard_normal((m, 17)).astype(f32), rng.standard_normal((m, 6)).astype(f32)
+    dx, dg = b200.dev(x), b200.dev(g)
+    launches0 = L.ppo_b200_launch_count()
+    L.ppo_b200_set_matmul_precision(3)
+    try:
+        L.forward_propagation_cuda(nn, dx.fp(), m)
+        y = b200.d2h(L, nn.contents.d_output, (m, 6))
+        L.backward_propagation_cuda(nn, dg.fp(), m)
+        grads = b200.nn_get_device_grads(L, nn)
+    finally:
+        L.ppo_b200_set_matmul_precision(0)
+    y_o, cache = oracle.mlp_forward(p, sizes, acts, x)
+    g_o = oracle.mlp_backward(p, sizes, acts, cache, g)
+    per, o = [], 0
+    for i in range(len(sizes) - 1):
+        for cnt in (sizes[i] * sizes[i + 1], sizes[i + 1]):
+            per.append(nerr(grads[o:o + cnt], g_o[o:o + cnt]))
+            o += cnt
+    print("3xTF32 2x256 %s (m=%d): output err %.2e, per-tensor gradient errors %s, launches %d"
+          % (hidden_act, m, nerr(y, y_o), ["%.1e" % e for e in per], L.ppo_b200_launch_count() - launches0))
+    assert nerr(y, y_o) < 1e-5 and max(per) < 1e-5
+    L.free_neural_network(nn)
+
+
 # ---- BF16 operand mode (kind::f16, fp32 accumulation) -------------------------------------------------------------------
 # Stated tolerance: operands rounded to bf16 (8-bit mantissa, round-to-nearest-even: relative error <= 2^-9 each), products
 # and sums exact in fp32 -> norm-wise output error ~ 2^-9 * sqrt(2) / sqrt(K) * |row|-ish; measured 2e-3 .. 3e-3, bound 6e-3.
