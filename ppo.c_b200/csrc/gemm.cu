@@ -607,6 +607,8 @@ static bool use_tc(int m, int n, int l, const void* a, const void* b, int lda, i
 void linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act) {
     if (m <= 0) return;
     if (use_tc(m, n, l, x, W, n, n) && (l % 4) == 0) { tc_linear_forward(y, x, W, b, m, n, l, act); return; }
+    if (l <= 8 && narrow_head_forward(y, x, W, b, m, n, l, act)) return;
+    if (n <= 32 && l >= 64 && narrow_first_forward(y, nullptr, x, W, b, m, n, l, act)) return;
     if (l <= 8) {
         const int blocks = std::min(div_up(m, 8), num_sms() * 8);
         B200_LAUNCH(linear_forward_skinny_kernel, blocks, 256, 0, y, x, W, b, m, n, l, act);
@@ -670,6 +672,13 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
     }
     const bool narrow_in = m >= 1024 && n <= 32 && l >= 64;      // first layer of a low-dimensional env: wide side = l (+ db)
     const bool narrow_out = m >= 1024 && l <= 8 && n >= 64;      // value / action heads: wide side = n
+    // streaming kernels of narrow.cu (one cp.async-pipelined pass over the wide array); the kernels below stay for shapes they
+    // do not take (wide side not a multiple of 4, unaligned bases) and for PPO_B200_NARROW=0 A/B runs
+    if (narrow_in && narrow_first_layer_backward(gW_part, gb_part, stride, splits, g, x, m, n, l)) return;
+    if (narrow_out && narrow_head_backward(gW_part, stride, splits, nullptr, nullptr, g, x, nullptr, m, n, l, kActNone)) {
+        launch_colsum(gb_part, stride, splits, g, m, l);
+        return;
+    }
     if (narrow_in || narrow_out) {
         const int wide_n = narrow_in ? l : n, small_n = narrow_in ? n : l;
         const int sp = narrow_in ? (n <= 8 ? 8 : n <= 16 ? 16 : n <= 24 ? 24 : 32) : 8;
@@ -706,6 +715,12 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
     }
     dim3 grid2(div_up(l, 32), splits, 1);
     B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+}
+
+void skinny_fold(float* gW_part, float* gb_part, size_t stride, const float* part, int splits, int R, int wide_n, int small_n, int sp1, int n,
+                 int wide_is_l) {
+    dim3 gf(std::max(1, std::min(32, div_up(wide_n * sp1, 256))), splits, 1);
+    B200_LAUNCH(skinny_dw_fold_kernel, gf, 256, 0, gW_part, gb_part, stride, part, R, wide_n, small_n, sp1, n, wide_is_l);
 }
 
 void activation_inplace(float* x, long long count, int act) {

@@ -70,6 +70,16 @@ int choose_splits(int m, size_t param_count);
 void activation_inplace(float* x, long long count, int act);
 void activation_grad_inplace(const float* y, float* grad, long long count, int act);
 
+// ---- narrow.cu (streaming kernels for layers with one side <= 32 columns) ---------------------------
+bool narrow_first_layer_backward(float* gW_part, float* gb_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l);
+// dW slabs of an l <= 8 wide head and, when gx != null, gx = (g W) act'(h) (+ its lo companion when gx_lo != null) in one pass over h
+bool narrow_head_backward(float* gW_part, size_t stride, int splits, float* gx, float* gx_lo, const float* g, const float* h, const float* W,
+                          int m, int n, int l, int act_prev);
+
+bool narrow_head_forward(float* y, const float* h, const float* W, const float* b, int m, int n, int l, int act);
+// first layer (n <= 32 inputs); y_lo != null additionally receives the 3xTF32 lo companion of y
+bool narrow_first_forward(float* y, float* y_lo, const float* x, const float* W, const float* b, int m, int n, int l, int act);
+
 // ---- tc_gemm.cu (tcgen05 TF32 tensor-core path for wide layers) --------------------------------
 bool tc_shape_ok(const void* a, const void* b, int lda_cols, int ldb_cols);
 void tc_linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act);

@@ -147,17 +147,24 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
     if (matmul_precision() == 3) {
         // 3xTF32 mode: lo companions of the weights (once per forward = once per optimiser step) and of the layer inputs
         if (!nd->params_lo) nd->params_lo = dmalloc<float>(nd->param_count + 64);
-        bool split_w = false;
+        bool split_w = false, lo_ready = false;     // lo_ready: alo[i] already holds the lo companion of a[i]
         for (int i = 0; i < L; i++) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
             if (x3_layer(nd, i, m)) {
                 if (!split_w) { tc_split_lo(nd->params, nd->params_lo, nd->param_count); split_w = true; }
                 ensure_shadow(nd->alo, nd->alo_cap, i, m, n, 4);
                 float* alo = static_cast<float*>(nd->alo[i]);
-                tc_split_lo(nd->a[i], alo, (size_t)m * n);
+                if (!lo_ready) tc_split_lo(nd->a[i], alo, (size_t)m * n);
+                lo_ready = false;
                 tc_linear_forward_x3(nd->a[i + 1], nd->a[i], alo, nd->params + nd->w_off[i], nd->params_lo + nd->w_off[i], nd->params + nd->b_off[i],
                                      m, n, l, nd->acts[i]);
             } else {
+                // a narrow first layer feeding a split layer writes the lo companion of its output itself
+                if (i + 1 < L && n <= 32 && x3_layer(nd, i + 1, m)) {
+                    ensure_shadow(nd->alo, nd->alo_cap, i + 1, m, l, 4);
+                    if (narrow_first_forward(nd->a[i + 1], static_cast<float*>(nd->alo[i + 1]), nd->a[i], nd->params + nd->w_off[i],
+                                             nd->params + nd->b_off[i], m, n, l, nd->acts[i])) { lo_ready = true; continue; }
+                }
                 linear_forward(nd->a[i + 1], nd->a[i], nd->params + nd->w_off[i], nd->params + nd->b_off[i], m, n, l, nd->acts[i]);
             }
         }
@@ -204,6 +211,17 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
     nn->d_output = nd->a[L];
 }
 
+// Narrow head layer (<= 8 outputs) above a wide layer: dW slabs and dX from ONE pass over the layer input (narrow.cu); db from
+// the m x l gradient.  `W` = the weights the forward pass used; gx_lo (3xTF32 mode) receives the lo companion of dX.
+static bool head_backward_fused(NetDev* nd, int i, int m, int splits, const float* g, const float* W, float* gx_lo) {
+    const int n = nd->sizes[i], l = nd->sizes[i + 1];
+    if (i == 0 || l > 8 || n < 64) return false;
+    if (!narrow_head_backward(nd->partials + nd->w_off[i], nd->slab_stride(), splits, nd->gx[i], gx_lo, g, nd->a[i], W, m, n, l, nd->acts[i - 1]))
+        return false;
+    launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
+    return true;
+}
+
 void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
     NetDev* nd = net_dev(nn);
     if (m != nd->last_m) B200_FATAL("backward with m=%d after forward with m=%d", m, nd->last_m);
@@ -239,6 +257,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         bool have16 = false;          // gx16[i + 1] holds the shadow of g (the gradient wrt a[i + 1])
         for (int i = L - 1; i >= 0; i--) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
+            if (head_backward_fused(nd, i, m, splits, g, nd->params + nd->w_off[i], nullptr)) { g = nd->gx[i]; have16 = false; continue; }
             if (i == 0 && w16 && bf16_layer0_padk(nd, m) && nd->w0pad_bf16 && !nd->a16.empty() && nd->a16[0]) {
                 // K-padded first layer: dW through the tensor cores into [splits][l][64] staging slabs, columns < n copied out
                 if (!have16) { ensure_shadow(nd->gx16, nd->gx16_cap, 1, m, l); tc_to_bf16_v(g, nd->gx16[1], (size_t)m * l); }
@@ -268,14 +287,21 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
             }
         }
     } else if (matmul_precision() == 3) {
+        bool lo_ready = false;        // glo[i + 1] already holds the lo companion of g (written by the fused head kernel)
         for (int i = L - 1; i >= 0; i--) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
             float* gWp = nd->partials + nd->w_off[i];
+            {
+                float* next_lo = nullptr;
+                if (i > 0 && x3_layer(nd, i - 1, m)) { ensure_shadow(nd->glo, nd->glo_cap, i, m, n, 4); next_lo = static_cast<float*>(nd->glo[i]); }
+                if (head_backward_fused(nd, i, m, splits, g, nd->params + nd->w_off[i], next_lo)) { g = nd->gx[i]; lo_ready = next_lo != nullptr; continue; }
+            }
             if (x3_layer(nd, i, m) && nd->params_lo && (int)nd->alo.size() > i && nd->alo[i] && ((nd->slab_stride() * 4) % 16) == 0 &&
                 ((uintptr_t)gWp & 15) == 0) {
                 ensure_shadow(nd->glo, nd->glo_cap, i + 1, m, l, 4);
                 float* glo = static_cast<float*>(nd->glo[i + 1]);
-                tc_split_lo(g, glo, (size_t)m * l);
+                if (!lo_ready) tc_split_lo(g, glo, (size_t)m * l);
+                lo_ready = false;
                 tc_linear_backward_weights_x3(gWp, nd->slab_stride(), splits, g, glo, nd->a[i], static_cast<const float*>(nd->alo[i]), m, n, l);
                 launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
                 if (i > 0) {
@@ -288,11 +314,16 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                     linear_backward_input(nd->gx[i], g, nd->params + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
                     g = nd->gx[i];
                 }
+                lo_ready = false;
             }
         }
     } else
     for (int i = L - 1; i >= 0; i--) {
         const int n = nd->sizes[i], l = nd->sizes[i + 1];
+        {
+            const float* wfwd = (matmul_precision() == 1 && nd->params_tf32) ? nd->params_tf32 : nd->params;
+            if (head_backward_fused(nd, i, m, splits, g, wfwd + nd->w_off[i], nullptr)) { g = nd->gx[i]; continue; }
+        }
         linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->slab_stride(), splits, g,
                                nd->a[i], m, n, l);
         if (i > 0) {  // dX of layer 0 is unused by every caller (the reference computes it anyway)

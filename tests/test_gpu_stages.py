@@ -393,6 +393,47 @@ def test_mat_mul_backwards_cuda_narrow_layers_large_m(L, shapes):
             d.free()
 
 
+@pytest.mark.parametrize("m,n,l", [(4096, 17, 256), (20000, 3, 64), (5000, 32, 1024), (4096, 256, 6), (20000, 1024, 1), (3000, 64, 8), (2050, 24, 264)])
+def test_mat_mul_cuda_narrow_layers_forward(L, m, n, l):
+    """Forward of the narrow layers of a wide net at large m (csrc/narrow.cu: first layer with <= 32 inputs, heads with <= 8
+    outputs) through the reference entry point, against float64."""
+    rng = np.random.default_rng(m + n + l)
+    x, w, b = (rng.standard_normal(s).astype(f32) for s in [(m, n), (l, n), (l,)])
+    dx, dw, db, dout = b200.dev(x), b200.dev(w), b200.dev(b), b200.dev_empty((m, l))
+    L.mat_mul_cuda(None, dout.fp(), dx.fp(), dw.fp(), db.fp(), m, n, l)
+    assert nerr(dout.numpy(), x.astype(np.float64) @ w.astype(np.float64).T + b) < TOL
+    for d in (dx, dw, db, dout):
+        d.free()
+
+
+@pytest.mark.parametrize("sizes,act,m", [([17, 256, 256, 6], "relu", 4096), ([17, 256, 256, 1], "tanh", 3000), ([3, 128, 1024, 8], "tanh", 2048)])
+def test_wide_net_with_narrow_ends_vs_oracle(L, sizes, act, m):
+    """Nets with a low-dimensional input and a <= 8 wide head above wide layers at m >= 1024: the first layer and the head run
+    in the streaming kernels of csrc/narrow.cu (the head's dW and dX in ONE pass over its input); outputs and every gradient
+    tensor against the oracle at the fp32 tolerance."""
+    acts = [act] * (len(sizes) - 2) + ["none"]
+    cabi.srand(9)
+    nn = L.create_neural_network(cabi.int_array(sizes), cabi.cstr_array(acts), len(sizes))
+    p = b200.nn_get_params(L, nn)
+    rng = np.random.default_rng(m)
+    x, g = rng.standard_normal((m, sizes[0])).astype(f32), rng.standard_normal((m, sizes[-1])).astype(f32)
+    dx, dg = b200.dev(x), b200.dev(g)
+    L.forward_propagation_cuda(nn, dx.fp(), m)
+    y = b200.d2h(L, nn.contents.d_output, (m, sizes[-1]))
+    L.backward_propagation_cuda(nn, dg.fp(), m)
+    grads = b200.nn_get_device_grads(L, nn)
+    y_o, cache = oracle.mlp_forward(p, sizes, acts, x)
+    g_o = oracle.mlp_backward(p, sizes, acts, cache, g)
+    assert nerr(y, y_o) < TOL
+    o = 0
+    for i in range(len(sizes) - 1):
+        for cnt in (sizes[i] * sizes[i + 1], sizes[i + 1]):
+            assert nerr(grads[o:o + cnt], g_o[o:o + cnt]) < TOL, (i, cnt)
+            o += cnt
+    L.free_neural_network(nn)
+    dx.free(); dg.free()
+
+
 # ------------------------------------------------------------------------------------------ policy
 def _policy(L, sizes, params, log_std):
     pol = L.create_gaussian_policy(cabi.int_array(sizes), cabi.cstr_array(RELU3), len(sizes), 1.0)
