@@ -679,10 +679,14 @@ class AdamStage(StageWorkload):
 
 
 class GatherStage(StageWorkload):
-    """Minibatch gather by permutation on the C3-shaped buffer (src/trajectory_buffer.cu:168-220): 212 B/sample."""
+    """Minibatch gather by permutation on the C3-shaped buffer (src/trajectory_buffer.cu:168-220): 212 B/sample.
+    One step = what one PPO iteration of the layer-wise update path does: ONE streaming pass that builds the row-packed mirror
+    (csrc/buffer.cu) + one gather of every row per epoch, 14 epochs (10 value + 4 policy, src/main.c:36-37)."""
     name = "gather"
     metric, unit = "gather_samples_per_s", "samples/s"
     S, A, B = 17, 6, 2048 * 512
+    EPOCHS = 14
+    PACKED = True
     CPU_B = 1 << 18
 
     def setup(self):
@@ -691,12 +695,21 @@ class GatherStage(StageWorkload):
         S, A, B = self.S, self.A, self.B
         self.src = [self._mk((B, S), rng=rng)[0], self._mk((B, A), rng=rng)[0]] + [self._mk(B, rng=rng)[0] for _ in range(3)]
         self.dst = [self._mk((B, S))[0], self._mk((B, A))[0]] + [self._mk(B)[0] for _ in range(3)]
-        self.idx = b200.dev_empty(B, np.int32)
-        self.L.ppo_b200_permutation(self.idx.ptr, B, 17, 0)
-        self.devs = self.src + self.dst + [self.idx]
+        self.idx = [b200.dev_empty(B, np.int32) for _ in range(self.EPOCHS)]
+        for e, d in enumerate(self.idx):
+            self.L.ppo_b200_permutation(d.ptr, B, 17, e)
+        self.packed = b200.dev_empty((B, self.L.ppo_b200_packed_row_floats(S, A)))
+        self.devs = self.src + self.dst + self.idx + [self.packed]
 
     def _call(self):
-        self.L.ppo_b200_gather(self.idx.ptr, 0, self.B, self.B, self.S, self.A, *[d.ptr for d in self.src], *[d.ptr for d in self.dst])
+        L = self.L
+        if self.PACKED:
+            L.ppo_b200_pack_rows(self.packed.ptr, self.B, self.S, self.A, *[d.ptr for d in self.src])
+        for e in range(self.EPOCHS):
+            if self.PACKED:
+                L.ppo_b200_gather_packed(self.idx[e].ptr, 0, self.B, self.B, self.S, self.A, self.packed.ptr, *[d.ptr for d in self.dst])
+            else:
+                L.ppo_b200_gather(self.idx[e].ptr, 0, self.B, self.B, self.S, self.A, *[d.ptr for d in self.src], *[d.ptr for d in self.dst])
 
     def step_e2e(self, k):
         out = [np.empty(d.shape, f32) for d in self.dst]
@@ -706,19 +719,23 @@ class GatherStage(StageWorkload):
                 self.L.ppo_b200_d2h(o.ctypes.data, d.ptr, o.nbytes)
 
     def units_per_step(self):
-        return self.B
+        return self.B * self.EPOCHS
 
     def e2e_bytes(self):
         return 0, 4 * self.B * (self.S + self.A + 3)
 
     def config(self):
-        return {"workload": "gather: all %d rows of a HalfCheetah-shaped buffer (S=17, A=6) gathered by a device permutation in one "
-                            "launch (states, actions, logprob, advantage, adv_target)" % self.B,
-                "parallelism": "replicated x%d" % self.world, "l2": "buffer 109 MB + 109 MB output; random 68-byte rows",
-                "e2e_call": "ppo_b200_gather on the resident buffer + download of the gathered minibatch"}
+        how = ("from the row-packed mirror (one contiguous 128-byte row per sample; the mirror is rebuilt once per step)" if self.PACKED
+               else "from the five SoA arrays (random 68-byte state rows, 24-byte action rows, three 4-byte scalars)")
+        return {"workload": "%s: all %d rows of a HalfCheetah-shaped buffer (S=17, A=6) gathered by %d device permutations %s"
+                            % (self.name, self.B, self.EPOCHS, how),
+                "parallelism": "replicated x%d" % self.world, "l2": "buffer 109 MB (+ 134 MB mirror) + 109 MB output; random rows",
+                "e2e_call": "pack + %d gathers on the resident buffer + download of the last gathered minibatch" % self.EPOCHS}
 
     def roofline_work(self, kernels):
-        return {"gather_kernel": ("hbm", float(self.B) * (4 + 2 * 4 * (self.S + self.A + 3)))}
+        per = float(self.B) * (4 + 2 * 4 * (self.S + self.A + 3))
+        return {"gather_packed_kernel": ("hbm", self.EPOCHS * per), "gather_kernel": ("hbm", self.EPOCHS * per),
+                "pack_rows_kernel": ("hbm", float(self.B) * 4 * ((self.S + self.A + 3) + 32))}
 
     def cpu_sample(self, n_iters, seed=1):
         import oracle
@@ -740,7 +757,13 @@ class GatherStage(StageWorkload):
         return "oracle port of get_batch (src/trajectory_buffer.cu:202-220) over %d rows" % self.CPU_B
 
 
-WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c3x3": C3X3, "c4": C4, "c4bf16": C4BF16, "c5": C5, "adam": AdamStage, "gather": GatherStage}
+class GatherSoA(GatherStage):
+    """The same gathers straight from the SoA arrays (the reference's layout; get_batch_cuda / ppo_b200_gather)."""
+    name = "gather_soa"
+    PACKED = False
+
+
+WORKLOADS = {"c1": C1, "c2": C2, "c3": C3, "c3x3": C3X3, "c4": C4, "c4bf16": C4BF16, "c5": C5, "adam": AdamStage, "gather": GatherStage, "gather_soa": GatherSoA}
 
 
 # ======================================================================================= CPU arm

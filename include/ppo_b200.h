@@ -380,6 +380,15 @@ void ppo_b200_gather(const int* idx, int offset, int limit, int batch_size, int 
                      const float* state, const float* action, const float* logprob,
                      const float* advantage, const float* adv_target, float* states, float* actions,
                      float* logprobs, float* advantages, float* adv_targets);
+/* Row-packed mirror of the gathered fields (new): packed[row][PW] = state | action | logprob | advantage | adv_target | pad
+ * with PW = ppo_b200_packed_row_floats(S, A) (the row rounded up to whole 32-byte sectors).  Built by ONE streaming pass
+ * after GAE; ppo_b200_gather_packed then reads one contiguous, sector-aligned row per sample instead of five scattered
+ * pieces (same outputs as ppo_b200_gather, bit for bit; src/trajectory_buffer.cu:168-200). */
+int ppo_b200_packed_row_floats(int S, int A);
+void ppo_b200_pack_rows(float* packed, long long rows, int S, int A, const float* state, const float* action,
+                        const float* logprob, const float* advantage, const float* adv_target);
+void ppo_b200_gather_packed(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* packed,
+                            float* states, float* actions, float* logprobs, float* advantages, float* adv_targets);
 /* Device permutation (new): writes a uniformly random permutation of [0,n) from a counter-based
  * generator keyed by (seed, epoch).  NOT the reference's rand() chain — see shuffle_buffer_cuda. */
 void ppo_b200_permutation(int* idx, int n, unsigned long long seed, unsigned long long epoch);

@@ -56,6 +56,9 @@ EXTENSION_API = {
     "ppo_b200_gae": (None, [vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, vp]),
     "ppo_b200_adam_flat": (None, [vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]),
     "ppo_b200_gather": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 10),
+    "ppo_b200_packed_row_floats": (C.c_int, [C.c_int, C.c_int]),
+    "ppo_b200_pack_rows": (None, [vp, C.c_longlong, C.c_int, C.c_int] + [vp] * 5),
+    "ppo_b200_gather_packed": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 6),
     "ppo_b200_permutation": (None, [vp, C.c_int, C.c_ulonglong, C.c_ulonglong]),
     "ppo_b200_pendulum_step": (None, [vp, vp, vp, vp, vp, C.c_int]),
     "ppo_b200_update": (None, [vp, C.c_float, C.c_int, C.c_int, C.c_int]),

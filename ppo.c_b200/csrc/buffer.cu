@@ -69,6 +69,99 @@ void launch_gather(const int* idx, int offset, int limit, int batch_size, int S,
                 advantage, adv_target, states, actions, logprobs, advantages, adv_targets);
 }
 
+// ---- row-packed mirror for the layer-wise update path ------------------------------------------------------------------
+// A gather from the SoA buffer touches five arrays per sample: a 68-byte state row straddles 3-4 32-byte DRAM sectors, a
+// 24-byte action row 1-2, each of the three scalars pulls a whole sector for 4 bytes -- ~250 bytes fetched for 104 wanted
+// (ncu: gather_kernel at 35 % of HBM peak with the memory pipe saturated).  The update phase gathers every row once per epoch,
+// 14 epochs per iteration, from arrays that do not change after GAE, so ONE streaming pass builds a row-packed mirror
+// [row][PW] = state | action | logprob | advantage | adv_target | pad, PW = the row rounded up to whole sectors (8 floats), and
+// every epoch's gather then reads exactly PW * 4 contiguous, sector-aligned bytes per sample.
+int packed_row_floats(int S, int A) { return ((S + A + 3) + 7) & ~7; }
+
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(float* __restrict__ packed, long long rows, int S, int A, int PW, const float* __restrict__ state, const float* __restrict__ action,
+                 const float* __restrict__ logprob, const float* __restrict__ advantage, const float* __restrict__ adv_target) {
+    const long long total = rows * PW, stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long r = e / PW;
+        const int c = (int)(e - r * PW);
+        float v = 0.f;
+        if (c < S) v = state[r * S + c];
+        else if (c < S + A) v = action[r * A + (c - S)];
+        else if (c == S + A) v = logprob[r];
+        else if (c == S + A + 1) v = advantage[r];
+        else if (c == S + A + 2) v = adv_target[r];
+        packed[e] = v;
+    }
+}
+
+// A packed row is PW / 4 float4 words: that many lanes take one row, a warp 32 / (PW / 4) rows per load instruction and U
+// independent loads per lane.  The rows land in a per-warp shared-memory tile; from there every output array is written as
+// ONE dense run of consecutive floats (the RW output rows of a warp iteration are adjacent in each of the reference's five
+// arrays), so each store instruction fills whole sectors -- scattering 4-byte pieces straight from the loaded float4 words
+// cost four partial-sector writes per sector and held the kernel at 41 % of HBM peak.  Bit-exact copy.
+constexpr int kPackedU = 4;
+__global__ void __launch_bounds__(256)
+gather_packed_kernel(const int* __restrict__ idx, int offset, int limit, int batch_size, int S, int A, int PW, const float* __restrict__ packed,
+                     float* __restrict__ states, float* __restrict__ actions, float* __restrict__ logprobs, float* __restrict__ advantages,
+                     float* __restrict__ adv_targets) {
+    extern __shared__ __align__(16) float gsm[];   // [warps][RW][PW]
+    const int lpr = PW >> 2;                       // lanes per row: 2, 4, 8, ... (PW is a multiple of 8)
+    const int lane = threadIdx.x & 31;
+    const int rpw = 32 / lpr;                      // rows per warp per load
+    const int RW = rpw * kPackedU;                 // rows per warp iteration
+    const int li = lane % lpr, lr = lane / lpr;
+    float* tile = gsm + (size_t)(threadIdx.x >> 5) * RW * PW;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int row0 = warp * RW; row0 < batch_size; row0 += n_warps * RW) {
+        const int nrows = min(RW, batch_size - row0);
+        int src[kPackedU];
+#pragma unroll
+        for (int u = 0; u < kPackedU; u++) {
+            const int r = u * rpw + lr;
+            src[u] = r < nrows ? __ldg(idx + (offset + row0 + r) % limit) : -1;      // src/trajectory_buffer.cu:171-173
+        }
+        float4 v[kPackedU];
+#pragma unroll
+        for (int u = 0; u < kPackedU; u++)
+            if (src[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(packed + (size_t)src[u] * PW) + li);
+        __syncwarp();                              // the previous iteration's reads of the tile are done
+#pragma unroll
+        for (int u = 0; u < kPackedU; u++)
+            if (src[u] >= 0) *reinterpret_cast<float4*>(tile + (u * rpw + lr) * PW + 4 * li) = v[u];
+        __syncwarp();
+        float* so = states + (size_t)row0 * S;
+        for (int e = lane; e < nrows * S; e += 32) { const int r = e / S; so[e] = tile[r * PW + (e - r * S)]; }
+        float* ao = actions + (size_t)row0 * A;
+        for (int e = lane; e < nrows * A; e += 32) { const int r = e / A; ao[e] = tile[r * PW + S + (e - r * A)]; }
+        for (int e = lane; e < 3 * nrows; e += 32) {
+            const int which = e / nrows, r = e - which * nrows;
+            float* dst = which == 0 ? logprobs : which == 1 ? advantages : adv_targets;
+            dst[row0 + r] = tile[r * PW + S + A + which];
+        }
+    }
+}
+
+void launch_pack_rows(float* packed, long long rows, int S, int A, const float* state, const float* action, const float* logprob,
+                      const float* advantage, const float* adv_target) {
+    if (rows <= 0) return;
+    const int PW = packed_row_floats(S, A);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((rows * PW + 255) / 256, (long long)num_sms() * 16));
+    B200_LAUNCH(pack_rows_kernel, blocks, 256, 0, packed, rows, S, A, PW, state, action, logprob, advantage, adv_target);
+}
+
+void launch_gather_packed(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* packed, float* states, float* actions,
+                          float* logprobs, float* advantages, float* adv_targets) {
+    if (batch_size <= 0) return;
+    const int PW = packed_row_floats(S, A);
+    if (PW > 128) B200_FATAL("packed gather: rows of %d floats are not supported (S + A + 3 <= 128)", PW);
+    const int rows_per_warp = (32 / (PW >> 2)) * kPackedU;
+    const size_t smem = (size_t)8 * rows_per_warp * PW * sizeof(float);        // 8 warps x 512 floats = 16 KB whatever PW is
+    const int blocks = std::max(1, std::min(div_up(div_up(batch_size, rows_per_warp), 8), num_sms() * 8));
+    B200_LAUNCH(gather_packed_kernel, blocks, 256, smem, idx, offset, limit, batch_size, S, A, PW, packed, states, actions, logprobs, advantages,
+                adv_targets);
+}
+
 void host_shuffle(int* idx, int limit) {
     for (int i = 0; i < limit; i++) idx[i] = i;
     for (int i = 0; i < limit; i++) {
@@ -152,6 +245,18 @@ void ppo_b200_gather(const int* idx, int offset, int limit, int batch_size, int 
                      float* states, float* actions, float* logprobs, float* advantages, float* adv_targets) {
     launch_gather(idx, offset, limit, batch_size, S, A, state, action, logprob, advantage, adv_target, states,
                   actions, logprobs, advantages, adv_targets);
+}
+
+int ppo_b200_packed_row_floats(int S, int A) { return packed_row_floats(S, A); }
+
+void ppo_b200_pack_rows(float* packed, long long rows, int S, int A, const float* state, const float* action, const float* logprob,
+                        const float* advantage, const float* adv_target) {
+    launch_pack_rows(packed, rows, S, A, state, action, logprob, advantage, adv_target);
+}
+
+void ppo_b200_gather_packed(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* packed, float* states,
+                            float* actions, float* logprobs, float* advantages, float* adv_targets) {
+    launch_gather_packed(idx, offset, limit, batch_size, S, A, packed, states, actions, logprobs, advantages, adv_targets);
 }
 
 void ppo_b200_permutation(int* idx, int n, unsigned long long seed, unsigned long long epoch) {

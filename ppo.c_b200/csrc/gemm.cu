@@ -569,10 +569,12 @@ skinny_dw_fold_kernel(float* __restrict__ gW_part, float* __restrict__ gb_part, 
         const int col = e / sp1, k = e - col * sp1;
         float t = 0.f;
         for (int z = 0; z < R; z++) t += part[((size_t)(slab * R + z) * wide_n + col) * sp1 + k];
+        // wide_is_l: 1 = first layer (wide = g columns; the last entry is this layer's db), 0 = head (wide = input columns),
+        // 2 = head whose last entry holds the column sums of its dX = the db of the layer below (gb_part points there)
         if (k < small_n) {
-            if (wide_is_l) gW_part[(size_t)slab * stride + (size_t)col * n + k] = t;    // gW[j = col][k]
-            else gW_part[(size_t)slab * stride + (size_t)k * n + col] = t;              // gW[j = k][col]
-        } else if (k == sp1 - 1 && wide_is_l) {
+            if (wide_is_l == 1) gW_part[(size_t)slab * stride + (size_t)col * n + k] = t;    // gW[j = col][k]
+            else gW_part[(size_t)slab * stride + (size_t)k * n + col] = t;                   // gW[j = k][col]
+        } else if (k == sp1 - 1 && wide_is_l != 0) {
             gb_part[(size_t)slab * stride + col] = t;
         }
     }
@@ -675,7 +677,7 @@ void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int s
     // streaming kernels of narrow.cu (one cp.async-pipelined pass over the wide array); the kernels below stay for shapes they
     // do not take (wide side not a multiple of 4, unaligned bases) and for PPO_B200_NARROW=0 A/B runs
     if (narrow_in && narrow_first_layer_backward(gW_part, gb_part, stride, splits, g, x, m, n, l)) return;
-    if (narrow_out && narrow_head_backward(gW_part, stride, splits, nullptr, nullptr, g, x, nullptr, m, n, l, kActNone)) {
+    if (narrow_out && narrow_head_backward(gW_part, stride, splits, nullptr, nullptr, nullptr, g, x, nullptr, m, n, l, kActNone)) {
         launch_colsum(gb_part, stride, splits, g, m, l);
         return;
     }

@@ -73,8 +73,9 @@ void activation_grad_inplace(const float* y, float* grad, long long count, int a
 // ---- narrow.cu (streaming kernels for layers with one side <= 32 columns) ---------------------------
 bool narrow_first_layer_backward(float* gW_part, float* gb_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l);
 // dW slabs of an l <= 8 wide head and, when gx != null, gx = (g W) act'(h) (+ its lo companion when gx_lo != null) in one pass over h
-bool narrow_head_backward(float* gW_part, size_t stride, int splits, float* gx, float* gx_lo, const float* g, const float* h, const float* W,
-                          int m, int n, int l, int act_prev);
+// (+ the column sums of gx = db slabs of the layer below when gb_below != null)
+bool narrow_head_backward(float* gW_part, size_t stride, int splits, float* gx, float* gx_lo, float* gb_below, const float* g, const float* h,
+                          const float* W, int m, int n, int l, int act_prev);
 
 bool narrow_head_forward(float* y, const float* h, const float* W, const float* b, int m, int n, int l, int act);
 // first layer (n <= 32 inputs); y_lo != null additionally receives the 3xTF32 lo companion of y
@@ -191,6 +192,11 @@ void launch_policy_head(const float* mu, const float* log_std, const float* acti
                         float* logp_out, float* grad_mu, float* grad_log_std, float* loss_slot);
 
 // ---- buffer.cu --------------------------------------------------------------------------------
+int packed_row_floats(int S, int A);
+void launch_pack_rows(float* packed, long long rows, int S, int A, const float* state, const float* action, const float* logprob,
+                      const float* advantage, const float* adv_target);
+void launch_gather_packed(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* packed, float* states, float* actions,
+                          float* logprobs, float* advantages, float* adv_targets);
 void launch_gather(const int* idx, int offset, int limit, int batch_size, int S, int A, const float* state,
                    const float* action, const float* logprob, const float* advantage, const float* adv_target,
                    float* states, float* actions, float* logprobs, float* advantages, float* adv_targets);

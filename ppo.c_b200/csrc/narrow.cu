@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(256, 2) narrow_bwd_kernel(const NarrowArgs p) 
                     o.z = act_grad(w4[2], t23.x, p.act_prev); o.w = act_grad(w4[3], t23.y, p.act_prev);
                     const size_t off = (size_t)(c0 + r) * p.wide_n + col;
                     *reinterpret_cast<float4*>(p.gx + off) = o;
+                    bsum[0] += o.x; bsum[1] += o.y; bsum[2] += o.z; bsum[3] += o.w;      // column sums of dX = db of the layer below
                     if (p.gx_lo) {
                         float4 lo;
                         lo.x = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
@@ -237,9 +238,10 @@ bool narrow_first_layer_backward(float* gW_part, float* gb_part, size_t stride, 
 }
 
 // Head (l <= 8 outputs, n >= 64 inputs): dW slabs and gx = (g W) act'(h) (+ optional lo companion) from ONE pass over h.
-// db (column sums of the m x l array g) stays with the caller.
-bool narrow_head_backward(float* gW_part, size_t stride, int splits, float* gx, float* gx_lo, const float* g, const float* h, const float* W,
-                          int m, int n, int l, int act_prev) {
+// db (column sums of the m x l array g) stays with the caller; gb_below != null receives the column sums of gx (the db slabs of
+// the layer below, same slab stride).
+bool narrow_head_backward(float* gW_part, size_t stride, int splits, float* gx, float* gx_lo, float* gb_below, const float* g, const float* h,
+                          const float* W, int m, int n, int l, int act_prev) {
     if (!narrow_enabled() || m < 1024 || l > 8 || n < 64 || (n & 3) || ((uintptr_t)h & 15) || (gx && (((uintptr_t)W & 15) || ((uintptr_t)gx & 15))) ||
         (gx_lo && ((uintptr_t)gx_lo & 15)))
         return false;
@@ -252,7 +254,7 @@ bool narrow_head_backward(float* gW_part, size_t stride, int splits, float* gx, 
     a.part = static_cast<float*>(scratch(kScratchSkinny, (size_t)splits * R * n * 9 * sizeof(float)));
     a.W = W; a.gx = gx; a.gx_lo = gx_lo; a.act_prev = act_prev;
     launch_narrow_bwd<8, true>(a, dim3(gxb, splits, R));
-    skinny_fold(gW_part, nullptr, stride, a.part, splits, R, n, l, 9, n, 0);
+    skinny_fold(gW_part, gb_below, stride, a.part, splits, R, n, l, 9, n, (gx && gb_below) ? 2 : 0);
     return true;
 }
 
@@ -420,7 +422,12 @@ bool narrow_first_forward(float* y, float* y_lo, const float* x, const float* W,
     const int gx = div_up(l, kNrwCols);
     const int tiles = div_up(m, kNffRows);
     const dim3 grid(gx, std::max(1, std::min(tiles, (2 * num_sms()) / gx)), 1);
-    const size_t smem = (size_t)n * ((kNrwCols + 8) + 2 * (kNffRows + 4)) * sizeof(float);      // <= 47 KB at n = 32
+    const size_t smem = (size_t)n * ((kNrwCols + 8) + 2 * (kNffRows + 4)) * sizeof(float);      // 51 KB at n = 32
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(narrow_first_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+    }
     B200_LAUNCH(narrow_first_forward_kernel, grid, 256, smem, y, y_lo, x, W, b, m, n, l, act);
     return true;
 }

@@ -213,10 +213,12 @@ void net_forward(NeuralNetwork* nn, const float* input, int m, bool borrow_input
 
 // Narrow head layer (<= 8 outputs) above a wide layer: dW slabs and dX from ONE pass over the layer input (narrow.cu); db from
 // the m x l gradient.  `W` = the weights the forward pass used; gx_lo (3xTF32 mode) receives the lo companion of dX.
-static bool head_backward_fused(NetDev* nd, int i, int m, int splits, const float* g, const float* W, float* gx_lo) {
+// db_below: also emit the db slabs of layer i - 1 (column sums of dX), for callers that would otherwise run a column-sum pass.
+static bool head_backward_fused(NetDev* nd, int i, int m, int splits, const float* g, const float* W, float* gx_lo, bool db_below = false) {
     const int n = nd->sizes[i], l = nd->sizes[i + 1];
     if (i == 0 || l > 8 || n < 64) return false;
-    if (!narrow_head_backward(nd->partials + nd->w_off[i], nd->slab_stride(), splits, nd->gx[i], gx_lo, g, nd->a[i], W, m, n, l, nd->acts[i - 1]))
+    if (!narrow_head_backward(nd->partials + nd->w_off[i], nd->slab_stride(), splits, nd->gx[i], gx_lo,
+                              db_below ? nd->partials + nd->b_off[i - 1] : nullptr, g, nd->a[i], W, m, n, l, nd->acts[i - 1]))
         return false;
     launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
     return true;
@@ -288,13 +290,16 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         }
     } else if (matmul_precision() == 3) {
         bool lo_ready = false;        // glo[i + 1] already holds the lo companion of g (written by the fused head kernel)
+        bool db_ready = false;        // ... and the db slabs of layer i are written too
         for (int i = L - 1; i >= 0; i--) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
             float* gWp = nd->partials + nd->w_off[i];
             {
                 float* next_lo = nullptr;
                 if (i > 0 && x3_layer(nd, i - 1, m)) { ensure_shadow(nd->glo, nd->glo_cap, i, m, n, 4); next_lo = static_cast<float*>(nd->glo[i]); }
-                if (head_backward_fused(nd, i, m, splits, g, nd->params + nd->w_off[i], next_lo)) { g = nd->gx[i]; lo_ready = next_lo != nullptr; continue; }
+                if (head_backward_fused(nd, i, m, splits, g, nd->params + nd->w_off[i], next_lo, next_lo != nullptr)) {
+                    g = nd->gx[i]; lo_ready = db_ready = next_lo != nullptr; continue;
+                }
             }
             if (x3_layer(nd, i, m) && nd->params_lo && (int)nd->alo.size() > i && nd->alo[i] && ((nd->slab_stride() * 4) % 16) == 0 &&
                 ((uintptr_t)gWp & 15) == 0) {
@@ -303,7 +308,8 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                 if (!lo_ready) tc_split_lo(g, glo, (size_t)m * l);
                 lo_ready = false;
                 tc_linear_backward_weights_x3(gWp, nd->slab_stride(), splits, g, glo, nd->a[i], static_cast<const float*>(nd->alo[i]), m, n, l);
-                launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
+                if (!db_ready) launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
+                db_ready = false;
                 if (i > 0) {
                     tc_linear_backward_input_x3(nd->gx[i], g, glo, nd->params + nd->w_off[i], nd->params_lo + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
                     g = nd->gx[i];
@@ -314,7 +320,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                     linear_backward_input(nd->gx[i], g, nd->params + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
                     g = nd->gx[i];
                 }
-                lo_ready = false;
+                lo_ready = db_ready = false;
             }
         }
     } else

@@ -40,6 +40,8 @@ struct Trainer {
     int n_v_steps = 0, n_p_steps = 0;
     bool obs_norm = false;
     double* d_dist_triples = nullptr;
+    float* packed = nullptr;     // row-packed mirror of the gathered fields (layer-wise update path), [packed_cap][PW]
+    size_t packed_cap = 0;
     float eval_J = 0.f, eval_R = 0.f;   // what the last eval_ppo printed (src/ppo.cu:581)
     int eval_episodes = 0;
 };
@@ -161,6 +163,11 @@ static bool use_fused_env() {
     if (cached < 0) { const char* e = getenv("PPO_B200_FUSED"); cached = (e && e[0] == '0') ? 0 : 1; }
     return cached == 1;
 }
+static bool packed_gather_enabled() {      // PPO_B200_PACKED_GATHER=0 gathers from the SoA arrays (A/B runs)
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("PPO_B200_PACKED_GATHER"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
 static int g_force_path = -1;   // tests: -1 env default, 0 layer-wise, 1 fused
 static bool use_fused() { return g_force_path < 0 ? use_fused_env() : g_force_path == 1; }
 
@@ -228,6 +235,18 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
         if (!t->d_align) { t->d_align = dmalloc<float>(1); CUDA_CHECK(cudaMemsetAsync(t->d_align, 0, sizeof(float), stream())); }
         dist_allreduce_sum(t->d_align, 1);
     }
+    // layer-wise nets gather every row once per epoch from arrays that are final after GAE: build the row-packed mirror once
+    const bool packed = (!fusedV || !fusedP) && num_batches > 0 && packed_gather_enabled() && packed_row_floats(S, A) <= 128;
+    if (packed) {
+        const size_t need = (size_t)limit * packed_row_floats(S, A);
+        if (need > t->packed_cap) {
+            CUDA_CHECK(cudaStreamSynchronize(stream()));
+            if (t->packed) CUDA_CHECK(cudaFree(t->packed));
+            t->packed = dmalloc<float>(need);
+            t->packed_cap = need;
+        }
+        launch_pack_rows(t->packed, limit, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p, b->d_advantage_p, b->d_adv_target_p);
+    }
     CUDA_CHECK(cudaMemsetAsync(t->d_scalars, 0, 2 * sizeof(float), stream()));
     t->n_v_steps = n_epochs_value * num_batches;
     t->n_p_steps = n_epochs_policy * num_batches;
@@ -255,8 +274,9 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
                 continue;
             }
             ndV->image_dirty = true;
-            launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
-                          b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
+            if (packed) launch_gather_packed(perm, k * batch_size + row0, limit, mb_local, S, A, t->packed, t->states, t->actions, t->lp_old, t->adv, t->advt);
+            else launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
+                               b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
             net_forward(ppo->V, t->states, mb_local, true);
             launch_value_head(ppo->V->d_output, t->advt, t->gl, mb_local, mb_total, t->d_scalars + 0);
             net_backward_partials(ppo->V, t->gl, mb_local);
@@ -300,8 +320,9 @@ static void update_device(PPO* ppo, float gamma, int batch_size, int n_epochs_po
                 continue;
             }
             ndP->image_dirty = true;
-            launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
-                          b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
+            if (packed) launch_gather_packed(perm, k * batch_size + row0, limit, mb_local, S, A, t->packed, t->states, t->actions, t->lp_old, t->adv, t->advt);
+            else launch_gather(perm, k * batch_size + row0, limit, mb_local, S, A, b->d_state_p, b->d_action_p, b->d_logprob_p,
+                               b->d_advantage_p, b->d_adv_target_p, t->states, t->actions, t->lp_old, t->adv, t->advt);
             net_forward(pol->mu, t->states, mb_local, true);
             launch_policy_head(pol->mu->d_output, pol->d_log_std, t->actions, t->lp_old, t->adv, mb_local, A, mb_total,
                                ppo->epsilon, ppo->ent_coeff, t->lp, t->gmu, pol->d_log_std_grad, t->d_scalars + 1);
@@ -388,6 +409,7 @@ void free_ppo(PPO* ppo) {
         if (t->h_perm_all) CUDA_CHECK(cudaFreeHost(t->h_perm_all));
         if (t->d_perm_all) CUDA_CHECK(cudaFree(t->d_perm_all));
         if (t->d_align) CUDA_CHECK(cudaFree(t->d_align));
+        if (t->packed) CUDA_CHECK(cudaFree(t->packed));
         CUDA_CHECK(cudaEventDestroy(t->perm_all_evt));
         for (int s = 0; s < 2; s++) {
             if (t->h_perm[s]) CUDA_CHECK(cudaFreeHost(t->h_perm[s]));

@@ -276,6 +276,29 @@ def test_gather_wide_rows_and_odd_batches(L, S, A, n, mb):
             assert np.array_equal(got.numpy(), want)
 
 
+@pytest.mark.parametrize("S,A,n,mb", [(17, 6, 5000, 1237), (3, 1, 4099, 4096), (40, 9, 3001, 1000), (1, 1, 700, 333), (100, 25, 600, 599)])
+def test_packed_gather_is_bit_exact(L, S, A, n, mb):
+    """Row-packed mirror + gather from it (csrc/buffer.cu) against numpy fancy indexing: same five output arrays as the SoA
+    gather, bit for bit, for rows of 1 .. 16 sectors, odd minibatches and the (offset + i) % limit wrap-around."""
+    rng = np.random.default_rng(n + mb)
+    st, ac = rng.standard_normal((n, S)).astype(f32), rng.standard_normal((n, A)).astype(f32)
+    lp, ad, at = (rng.standard_normal(n).astype(f32) for _ in range(3))
+    idx = rng.permutation(n).astype(i32)
+    d = [b200.dev(x) for x in (idx, st, ac, lp, ad, at)]
+    pw = L.ppo_b200_packed_row_floats(S, A)
+    assert pw % 8 == 0 and pw >= S + A + 3
+    packed = b200.dev_empty((n, pw))
+    L.ppo_b200_pack_rows(packed.ptr, n, S, A, *[x.ptr for x in d[1:]])
+    pk = packed.numpy()
+    assert np.array_equal(pk[:, :S], st) and np.array_equal(pk[:, S:S + A], ac) and np.array_equal(pk[:, S + A + 2], at)
+    for offset in [0, n - mb // 2 - 1]:
+        o = [b200.dev_empty((mb, S)), b200.dev_empty((mb, A)), b200.dev_empty(mb), b200.dev_empty(mb), b200.dev_empty(mb)]
+        L.ppo_b200_gather_packed(d[0].ptr, offset, n, mb, S, A, packed.ptr, *[x.ptr for x in o])
+        rows = idx[(offset + np.arange(mb)) % n]
+        for got, want in zip(o, (st[rows], ac[rows], lp[rows], ad[rows], at[rows])):
+            assert np.array_equal(got.numpy(), want)
+
+
 def test_empty_inputs_are_noops(L):
     """n = 0 / batch 0 calls must return without launching on garbage (the reference would index out of bounds)."""
     z = b200.dev_empty(4)
