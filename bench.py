@@ -1110,7 +1110,7 @@ def run_secondary(L, rank, world, stream, barrier, torch, dist):
     """Short runs of the other BASELINE.json configs after the headline workload: value (device-resident, CUDA events, max over
     ranks) + the roofline of the dominant kernel from one profiled step.  c1 (host env, not collective) only at N = 1."""
     out = {}
-    for name, steps in (("c3", 2), ("c4", 2), ("c4bf16", 2), ("c5", 5)):
+    for name, steps in (("c3", 2), ("c3x3", 2), ("c4", 2), ("c4bf16", 2), ("c5", 5), ("gather", 3)):
         wl = WORKLOADS[name](L, rank, world)
         wl.setup()
         wl.step_device(1)
@@ -1180,7 +1180,8 @@ def whole_step_fraction(wl, ms_per_step):
     tfs = flops / (ms_per_step * 1e-3) / 1e12
     pk = load_peaks()
     prec = getattr(wl, "TF32", 0)
-    peak = pk["bf16"] if prec == 2 else pk["bf16"] / 2 if prec else (FP32_MEASURED.get("ffma_const_operands") or FP32_PEAK_TFLOPS)
+    peak = (pk["bf16"] if prec == 2 else pk["bf16"] / 6 if prec == 3 else pk["bf16"] / 2 if prec
+            else (FP32_MEASURED.get("ffma_const_operands") or FP32_PEAK_TFLOPS))
     return {"tflops": tfs, "peak": peak, "frac": tfs / peak}
 
 

@@ -112,6 +112,7 @@ gather_packed_kernel(const int* __restrict__ idx, int offset, int limit, int bat
     const int RW = rpw * kPackedU;                 // rows per warp iteration
     const int li = lane % lpr, lr = lane / lpr;
     float* tile = gsm + (size_t)(threadIdx.x >> 5) * RW * PW;
+    const int s_dr = 32 / S, s_dc = 32 % S, a_dr = 32 / A, a_dc = 32 % A;      // 32 elements further = this many rows + columns
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int row0 = warp * RW; row0 < batch_size; row0 += n_warps * RW) {
         const int nrows = min(RW, batch_size - row0);
@@ -130,14 +131,24 @@ gather_packed_kernel(const int* __restrict__ idx, int offset, int limit, int bat
         for (int u = 0; u < kPackedU; u++)
             if (src[u] >= 0) *reinterpret_cast<float4*>(tile + (u * rpw + lr) * PW + 4 * li) = v[u];
         __syncwarp();
+        // (row, column) of element e advance without a division: + 32 columns, then carry whole rows
         float* so = states + (size_t)row0 * S;
-        for (int e = lane; e < nrows * S; e += 32) { const int r = e / S; so[e] = tile[r * PW + (e - r * S)]; }
+        for (int e = lane, r = lane / S, c = lane - (lane / S) * S; e < nrows * S; e += 32) {
+            so[e] = tile[r * PW + c];
+            r += s_dr; c += s_dc;
+            if (c >= S) { c -= S; r++; }
+        }
         float* ao = actions + (size_t)row0 * A;
-        for (int e = lane; e < nrows * A; e += 32) { const int r = e / A; ao[e] = tile[r * PW + S + (e - r * A)]; }
-        for (int e = lane; e < 3 * nrows; e += 32) {
-            const int which = e / nrows, r = e - which * nrows;
-            float* dst = which == 0 ? logprobs : which == 1 ? advantages : adv_targets;
-            dst[row0 + r] = tile[r * PW + S + A + which];
+        for (int e = lane, r = lane / A, c = lane - (lane / A) * A; e < nrows * A; e += 32) {
+            ao[e] = tile[r * PW + S + c];
+            r += a_dr; c += a_dc;
+            if (c >= A) { c -= A; r++; }
+        }
+        for (int r = lane; r < nrows; r += 32) {
+            const float* t3 = tile + r * PW + S + A;
+            logprobs[row0 + r] = t3[0];
+            advantages[row0 + r] = t3[1];
+            adv_targets[row0 + r] = t3[2];
         }
     }
 }
