@@ -662,14 +662,16 @@ void launch_colsum(float* gb_part, size_t stride, int splits, const float* g, in
 }
 
 void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int splits, const float* g,
-                            const float* x, int m, int n, int l) {
+                            const float* x, int m, int n, int l, bool db_done) {
     if (m <= 0) return;
     int rows = div_up(m, splits);
     rows = div_up(rows, 32) * 32;          // multiple of both tile depths (16 FFMA, 32 TF32)
     if (use_tc(m, n, l, g, x, l, n) && ((stride * 4) % 16) == 0 && ((uintptr_t)gW_part & 15) == 0) {
         tc_linear_backward_weights(gW_part, stride, splits, g, x, m, n, l);
-        dim3 grid2(div_up(l, 32), splits, 1);
-        B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+        if (!db_done) {       // the fused head kernel above this layer may already have written the db slabs (narrow.cu)
+            dim3 grid2(div_up(l, 32), splits, 1);
+            B200_LAUNCH(colsum_kernel, grid2, 256, 0, gb_part, stride, g, m, l, rows);
+        }
         return;
     }
     const bool narrow_in = m >= 1024 && n <= 32 && l >= 64;      // first layer of a low-dimensional env: wide side = l (+ db)

@@ -64,8 +64,9 @@ void linear_forward(float* y, const float* x, const float* W, const float* b, in
 void linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev);
 // partial dW / db slabs: for split s, rows [s*rows_per_split, ...): gW_part[s][l][n] = g^T . x,
 // gb_part[s][l] = column sums of g.  Slab s of layer tensor lives at part + s*stride.  (mat_mul.cu:195-208, K9)
+// db_done: the db slabs are already written (honoured by the tensor-core path only; every other path computes db itself)
 void linear_backward_params(float* gW_part, float* gb_part, size_t stride, int splits, const float* g,
-                            const float* x, int m, int n, int l);
+                            const float* x, int m, int n, int l, bool db_done = false);
 int choose_splits(int m, size_t param_count);
 void activation_inplace(float* x, long long count, int act);
 void activation_grad_inplace(const float* y, float* grad, long long count, int act);

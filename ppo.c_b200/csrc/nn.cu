@@ -323,20 +323,25 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                 lo_ready = db_ready = false;
             }
         }
-    } else
+    } else {
+    bool db_done = false;
     for (int i = L - 1; i >= 0; i--) {
         const int n = nd->sizes[i], l = nd->sizes[i + 1];
         {
             const float* wfwd = (matmul_precision() == 1 && nd->params_tf32) ? nd->params_tf32 : nd->params;
-            if (head_backward_fused(nd, i, m, splits, g, wfwd + nd->w_off[i], nullptr)) { g = nd->gx[i]; continue; }
+            // TF32 mode: a tensor-core layer below would run a column-sum pass for its db; the head kernel emits it instead
+            const bool tc_below = matmul_precision() == 1 && i > 0 && m >= 128 && nd->sizes[i - 1] >= 64 && n >= 64;
+            if (head_backward_fused(nd, i, m, splits, g, wfwd + nd->w_off[i], nullptr, tc_below)) { g = nd->gx[i]; db_done = tc_below; continue; }
         }
         linear_backward_params(nd->partials + nd->w_off[i], nd->partials + nd->b_off[i], nd->slab_stride(), splits, g,
-                               nd->a[i], m, n, l);
+                               nd->a[i], m, n, l, db_done);
+        db_done = false;
         if (i > 0) {  // dX of layer 0 is unused by every caller (the reference computes it anyway)
             const float* wsrc = (matmul_precision() == 1 && nd->params_tf32) ? nd->params_tf32 : nd->params;
             linear_backward_input(nd->gx[i], g, wsrc + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
             g = nd->gx[i];
         }
+    }
     }
     nn->cache_m_backward = m;
 }

@@ -152,7 +152,8 @@ def write_readme(tag, table):
     lines = ["# profiles/ — measured evidence (round %s)" % tag.lstrip("r"), "",
              "All numbers: one B200 box through `gpurun`, CUDA-event timing on the library's stream, inputs larger than L2,",
              "peaks from `MEASURED_PEAKS.json` (HBM 6452.8 GB/s measured copy; TF32 tensor = measured sustained cuBLAS bf16 / 2;",
-             "fp32 = nominal 74.4 TFLOP/s).  `value` = inputs resident in HBM, `e2e` = host-buffer call, `cpu` = oracle port on one host core.",
+             "BF16 = sustained cuBLAS bf16; 3xTF32 = TF32 / 3; fp32 = the FFMA stream measured live by csrc/ubench.cu, 72.5 TFLOP/s).",
+             "`value` = inputs resident in HBM, `e2e` = host-buffer call, `cpu` = the CPU arm of that line (cores and kind are in the JSON).",
              "Files: `%s_bench_<workload>[_gN].json` full bench lines; `%s_launches_<workload>.txt` ncu launch lists;" % (tag, tag),
              "`%s_ncu_<capture>.txt` per-launch metrics of the `ncu --set full` captures; `traffic.json` DRAM bytes per launch;" % tag,
              "`%s_learning_curve_*.json` Pendulum return curves (`scripts/train_pendulum.py`)." % tag, "",
