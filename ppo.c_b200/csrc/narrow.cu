@@ -266,7 +266,7 @@ namespace b200 {
 // One pass over h: a warp takes four rows per iteration (lanes stride k in float4 steps, up to 8 independent 128-bit loads
 // in flight per lane), W sits in shared memory (one LDS.128 per (j, k4) shared by the four rows), butterfly sums at the end.
 constexpr int kNhfRows = 4;
-__global__ void __launch_bounds__(256) narrow_head_forward_kernel(float* __restrict__ y, const float* __restrict__ h, const float* __restrict__ W,
+__global__ void __launch_bounds__(256, 3) narrow_head_forward_kernel(float* __restrict__ y, const float* __restrict__ h, const float* __restrict__ W,
                                                                   const float* __restrict__ b, int m, int n, int l, int act) {
     extern __shared__ __align__(16) float hsm[];          // [l][n]
     for (int e = threadIdx.x; e < l * n; e += 256) hsm[e] = __ldg(W + e);
@@ -322,7 +322,7 @@ bool narrow_head_forward(float* y, const float* h, const float* W, const float* 
         CUDA_CHECK(cudaFuncSetAttribute(narrow_head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int blocks = std::min(div_up(m, 8 * kNhfRows), num_sms() * 4);
+    const int blocks = std::min(div_up(m, 8 * kNhfRows), num_sms() * 3);        // one wave of the 3 CTAs an SM holds
     B200_LAUNCH(narrow_head_forward_kernel, blocks, 256, smem, y, h, W, b, m, n, l, act);
     return true;
 }
@@ -345,10 +345,13 @@ narrow_first_forward_kernel(float* __restrict__ y, float* __restrict__ y_lo, con
         const int j = e / n, k = e - j * n;
         Ws[k][j] = (n0 + j < l) ? __ldg(W + (size_t)(n0 + j) * n + k) : 0.f;
     }
-    const int gj = n0 + 8 * tc;
-    const bool col_ok = gj < l;                    // l is a multiple of 8 (host check)
+    // thread columns: {4tc .. 4tc+3} and {128 + 4tc ..}: the 32 lanes of a store instruction then write 512 contiguous bytes (whole
+    // sectors); two adjacent float4 per lane would leave every sector half-written per instruction
+    const int gj0 = n0 + 4 * tc, gj1 = gj0 + 128;
+    const bool ok0 = gj0 < l, ok1 = gj1 < l;        // l is a multiple of 8 (host check)
     float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-    if (col_ok) { b0 = __ldg(reinterpret_cast<const float4*>(b + gj)); b1 = __ldg(reinterpret_cast<const float4*>(b + gj + 4)); }
+    if (ok0) b0 = __ldg(reinterpret_cast<const float4*>(b + gj0));
+    if (ok1) b1 = __ldg(reinterpret_cast<const float4*>(b + gj1));
     const int n_tiles = (m + kNffRows - 1) / kNffRows;
     constexpr int kPer = (kNffRows * 32 + 255) / 256;          // input floats per thread per tile (n <= 32)
     float xr[kPer];
@@ -381,7 +384,7 @@ narrow_first_forward_kernel(float* __restrict__ y, float* __restrict__ y_lo, con
 #pragma unroll
             for (int c = 0; c < 4; c++) acc[r][c] = make_float2(0.f, 0.f);
         for (int k = 0; k < n; k++) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][8 * tc]), w1 = *reinterpret_cast<const float4*>(&Ws[k][8 * tc + 4]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][4 * tc]), w1 = *reinterpret_cast<const float4*>(&Ws[k][128 + 4 * tc]);
             const float4 x0 = *reinterpret_cast<const float4*>(&Xs0[buf * n + k][8 * tr]), x1 = *reinterpret_cast<const float4*>(&Xs0[buf * n + k][8 * tr + 4]);
             const float2 wp[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
             const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -390,7 +393,8 @@ narrow_first_forward_kernel(float* __restrict__ y, float* __restrict__ y_lo, con
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[r][c] = __ffma2_rn(make_float2(xs[r], xs[r]), wp[c], acc[r][c]);
         }
-        if (col_ok) {
+        if (ok0) {
+            auto lo = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 const int gi = tile * kNffRows + 8 * tr + r;
@@ -400,14 +404,13 @@ narrow_first_forward_kernel(float* __restrict__ y, float* __restrict__ y_lo, con
                 o0.z = act_apply(acc[r][1].x + b0.z, act); o0.w = act_apply(acc[r][1].y + b0.w, act);
                 o1.x = act_apply(acc[r][2].x + b1.x, act); o1.y = act_apply(acc[r][2].y + b1.y, act);
                 o1.z = act_apply(acc[r][3].x + b1.z, act); o1.w = act_apply(acc[r][3].y + b1.w, act);
-                float* dst = y + (size_t)gi * l + gj;
-                *reinterpret_cast<float4*>(dst) = o0;
-                *reinterpret_cast<float4*>(dst + 4) = o1;
+                float* row = y + (size_t)gi * l;
+                *reinterpret_cast<float4*>(row + gj0) = o0;
+                if (ok1) *reinterpret_cast<float4*>(row + gj1) = o1;
                 if (y_lo) {
-                    auto lo = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
-                    float* dl = y_lo + (size_t)gi * l + gj;
-                    *reinterpret_cast<float4*>(dl) = make_float4(lo(o0.x), lo(o0.y), lo(o0.z), lo(o0.w));
-                    *reinterpret_cast<float4*>(dl + 4) = make_float4(lo(o1.x), lo(o1.y), lo(o1.z), lo(o1.w));
+                    float* rl = y_lo + (size_t)gi * l;
+                    *reinterpret_cast<float4*>(rl + gj0) = make_float4(lo(o0.x), lo(o0.y), lo(o0.z), lo(o0.w));
+                    if (ok1) *reinterpret_cast<float4*>(rl + gj1) = make_float4(lo(o1.x), lo(o1.y), lo(o1.z), lo(o1.w));
                 }
             }
         }

@@ -186,7 +186,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     static_assert(!(X3 && BF), "the split mode is a TF32 mode");
     using E = TcElem<BF>;
     constexpr int kTcStages = X3 ? 2 : (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
-    constexpr bool kStaged = EPI != kTcDw && !X3;              // epilogue staging tiles for the TMA-store path
+    constexpr bool kStaged = EPI != kTcDw;                     // epilogue staging tiles for the TMA-store path
+    constexpr int kStgPerWarp = X3 ? kTcStgBytes / 2 : kTcStgBytes;      // the split mode has no bf16 shadow: fp32 staging only
     constexpr int kTcBK = E::kBK, kTcUmmaK = E::kUmmaK;
     constexpr uint32_t A_BYTES = kTcBM * kTcBKBytes;           // 16 KB per stage
     constexpr uint32_t B_BYTES = BN * kTcBKBytes;
@@ -199,7 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stg_base = smem + kTcStages * STAGE_BYTES;                        // staging tiles of the epilogue warps (1024-byte aligned)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (kStaged ? kTcEpiWarps * kTcStgBytes : 0));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + (kStaged ? kTcEpiWarps * kStgPerWarp : 0));
     uint64_t* empty_bar = full_bar + kTcStages;
     uint64_t* tmem_full_bar = empty_bar + kTcStages;      // [2] accumulator buffer b holds a finished tile
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2] the epilogue warps have drained buffer b
@@ -356,8 +357,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool rows_ok = row < p.M;
             constexpr int CPW = BN / (kTcEpiWarps / 4);          // columns per warp
             const bool use_tma = kStaged && p.tma_store;
-            float* stg32 = reinterpret_cast<float*>(stg_base + (warp - 2) * kTcStgBytes);
-            uint4* stg16 = reinterpret_cast<uint4*>(stg_base + (warp - 2) * kTcStgBytes + 4096);
+            float* stg32 = reinterpret_cast<float*>(stg_base + (warp - 2) * kStgPerWarp);
+            uint4* stg16 = reinterpret_cast<uint4*>(stg_base + (warp - 2) * kStgPerWarp + 4096);      // bf16 mode only
 #pragma unroll 1
             for (int c0 = half * CPW; c0 < (half + 1) * CPW; c0 += 32) {
                 const int nb = n0 + c0;
@@ -536,8 +537,9 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF, bool X3>
 static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& talo, const CUtensorMap& tblo, const TcArgs& a_in,
                          dim3 tiles /* (N tiles, M tiles, splits) */) {
     constexpr int kStages = X3 ? 2 : (EPI == kTcDw) ? kTcStagesMax : kTcStagesMax - 1;
-    constexpr bool kStaged = EPI != kTcDw && !X3;
-    const size_t smem = (size_t)kStages * (X3 ? 2 : 1) * (kTcBM + BN) * kTcBKBytes + (kStaged ? kTcEpiWarps * kTcStgBytes : 0) + 1024 /*align*/ + 256 /*barriers*/;
+    constexpr bool kStaged = EPI != kTcDw;
+    const size_t smem = (size_t)kStages * (X3 ? 2 : 1) * (kTcBM + BN) * kTcBKBytes + (kStaged ? kTcEpiWarps * (X3 ? kTcStgBytes / 2 : kTcStgBytes) : 0) +
+                        1024 /*align*/ + 256 /*barriers*/;
     // output tensor maps of the TMA-store epilogue (forward / dX): fp32 boxes {32 columns, 32 rows}, bf16 shadow boxes {64, 32}
     TcArgs a = a_in;
     CUtensorMap tc = ta, tc16 = ta;        // placeholders when the store path is off
