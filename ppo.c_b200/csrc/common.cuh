@@ -44,7 +44,7 @@ int num_sms();
 // Grow-only device scratch, keyed by slot, so hot paths never cudaMalloc (the reference mallocs per
 // minibatch, src/loss.cu:51, src/ppo.cu:150).
 enum ScratchSlot { kScratchGae = 0, kScratchGaeV, kScratchGaeVNext, kScratchLoss, kScratchStage,
-                   kScratchStage2, kScratchStage3, kScratchPartials, kScratchMisc, kScratchSkinny, kScratchSlots };
+                   kScratchStage2, kScratchStage3, kScratchPartials, kScratchMisc, kScratchSkinny, kScratchColsum, kScratchSlots };
 void* scratch(ScratchSlot slot, size_t bytes);
 void* scratch_zeroed_once(ScratchSlot slot, size_t bytes);  // zero-filled when (re)allocated only
 

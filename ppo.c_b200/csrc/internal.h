@@ -87,6 +87,9 @@ bool tc_shape_ok(const void* a, const void* b, int lda_cols, int ldb_cols);
 void tc_linear_forward(float* y, const float* x, const float* W, const float* b, int m, int n, int l, int act);
 void tc_linear_backward_input(float* gx, const float* g, const float* W, const float* xin, int m, int n, int l, int act_prev);
 void tc_linear_backward_weights(float* gW_part, size_t stride, int splits, const float* g, const float* x, int m, int n, int l);
+// the NEXT tensor-core dX launch also writes the column sums of its output (= the db slabs of the layer below) to gb_part
+void tc_request_colsum(float* gb_part, size_t stride, int splits);
+bool tc_colsum_pending();
 void tc_round_copy(const float* src, float* dst, size_t n);   // RNA-rounded TF32 shadow of a weight arena
 int matmul_precision();   // 0 fp32 FFMA (default), 1 TF32 tcgen05 for layers with n, l >= 64, 2 BF16 tcgen05 (widths % 8 == 0),
                           // 3 "3xTF32" split on tcgen05: fp32-accurate (meets the 1e-5 parity of mode 0), layers with n, l >= 64

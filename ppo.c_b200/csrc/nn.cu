@@ -257,6 +257,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         char* w16 = static_cast<char*>(nd->params_bf16);
         const size_t tot16 = bf16_total(nd);
         bool have16 = false;          // gx16[i + 1] holds the shadow of g (the gradient wrt a[i + 1])
+        bool db16_ready = false;      // the db slabs of layer i were written by the dX epilogue of layer i + 1
         for (int i = L - 1; i >= 0; i--) {
             const int n = nd->sizes[i], l = nd->sizes[i + 1];
             if (head_backward_fused(nd, i, m, splits, g, nd->params + nd->w_off[i], nullptr)) { g = nd->gx[i]; have16 = false; continue; }
@@ -266,13 +267,17 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                 float* tmp = static_cast<float*>(scratch(kScratchSkinny, (size_t)splits * l * kPadK * sizeof(float)));
                 tc_linear_backward_weights_bf16_v(tmp, (size_t)l * kPadK, splits, nd->gx16[1], nd->a16[0], m, kPadK, l);
                 tc_unpad_slabs(tmp, nd->partials + nd->w_off[0], nd->slab_stride(), splits, l, n, kPadK);
-                tc_colsum_bf16_v(nd->partials + nd->b_off[0], nd->slab_stride(), splits, nd->gx16[1], m, l);
+                if (!db16_ready) tc_colsum_bf16_v(nd->partials + nd->b_off[0], nd->slab_stride(), splits, nd->gx16[1], m, l);
+                db16_ready = false;
             } else if (w16 && bf16_layer(nd, i, m) && (int)nd->a16.size() > i && nd->a16[i]) {
                 if (!have16) { ensure_shadow(nd->gx16, nd->gx16_cap, i + 1, m, l); tc_to_bf16_v(g, nd->gx16[i + 1], (size_t)m * l); }
                 tc_linear_backward_weights_bf16_v(nd->partials + nd->w_off[i], nd->slab_stride(), splits, nd->gx16[i + 1], nd->a16[i], m, n, l);
-                tc_colsum_bf16_v(nd->partials + nd->b_off[i], nd->slab_stride(), splits, nd->gx16[i + 1], m, l);
+                if (!db16_ready) tc_colsum_bf16_v(nd->partials + nd->b_off[i], nd->slab_stride(), splits, nd->gx16[i + 1], m, l);
+                db16_ready = false;
                 if (i > 0) {
                     const bool next16 = (bf16_layer(nd, i - 1, m) || (i == 1 && bf16_layer0_padk(nd, m))) && (int)nd->a16.size() > i - 1 && nd->a16[i - 1];
+                    // the layer below runs on the tensor path too: its db (fp32 column sums) comes out of this dX epilogue
+                    if (next16) { tc_request_colsum(nd->partials + nd->b_off[i - 1], nd->slab_stride(), splits); db16_ready = true; }
                     if (next16) ensure_shadow(nd->gx16, nd->gx16_cap, i, m, n);
                     tc_linear_backward_input_bf16_v(nd->gx[i], next16 ? nd->gx16[i] : nullptr, nd->gx16[i + 1],
                                                     w16 + 2 * (tot16 + bf16_w_off(nd, i)), nd->a[i], m, n, l, nd->acts[i - 1]);
@@ -286,6 +291,7 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                     g = nd->gx[i];
                 }
                 have16 = false;
+                db16_ready = false;
             }
         }
     } else if (matmul_precision() == 3) {
@@ -311,6 +317,8 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
                 if (!db_ready) launch_colsum(nd->partials + nd->b_off[i], nd->slab_stride(), splits, g, m, l);
                 db_ready = false;
                 if (i > 0) {
+                    // the layer below is a split layer too: its db comes out of this dX epilogue instead of a column-sum pass
+                    if (x3_layer(nd, i - 1, m)) { tc_request_colsum(nd->partials + nd->b_off[i - 1], nd->slab_stride(), splits); db_ready = true; }
                     tc_linear_backward_input_x3(nd->gx[i], g, glo, nd->params + nd->w_off[i], nd->params_lo + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
                     g = nd->gx[i];
                 }
@@ -338,7 +346,13 @@ void net_backward_partials(NeuralNetwork* nn, const float* grad_out, int m) {
         db_done = false;
         if (i > 0) {  // dX of layer 0 is unused by every caller (the reference computes it anyway)
             const float* wsrc = (matmul_precision() == 1 && nd->params_tf32) ? nd->params_tf32 : nd->params;
+            // TF32 mode, tensor-core layer above a tensor-core layer: the db of the layer below comes out of this dX epilogue
+            if (matmul_precision() == 1 && m >= 128 && n >= 64 && l >= 64 && nd->sizes[i - 1] >= 64) {
+                tc_request_colsum(nd->partials + nd->b_off[i - 1], nd->slab_stride(), splits);
+                db_done = true;
+            }
             linear_backward_input(nd->gx[i], g, wsrc + nd->w_off[i], nd->a[i], m, n, l, nd->acts[i - 1]);
+            if (tc_colsum_pending()) { tc_request_colsum(nullptr, 0, 0); db_done = false; }      // this dX did not run on the tensor path
             g = nd->gx[i];
         }
     }

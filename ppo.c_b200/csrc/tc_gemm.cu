@@ -66,6 +66,8 @@ struct TcArgs {
     int splits;             // kTcDw: number of split-K slabs
     size_t c_split_stride;
     int tma_store;          // kTcFwd / kTcDx: the epilogue writes C (and C16) with TMA bulk tensor stores from swizzled staging tiles
+    float* colsum_part;     // kTcDx, optional: [ceil(M / 128) * 4][N] column sums of C per 32-row quadrant of every tile (the bias gradient
+                            // of the layer below, folded in fixed order by colsum_fold_kernel)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -383,8 +385,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_u32(&tmem_empty_bar[buf])) : "memory");
                 }
+                float v[32];
                 if (rows_ok || use_tma) {
-                    float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
                     if (EPI == kTcFwd) {
@@ -416,6 +418,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
                         }
                     }
+                }
+                if (EPI == kTcDx && p.colsum_part != nullptr) {
+                    // Column sums of this 32 x 32 chunk over the warp's 32 rows: recursive halving, 31 shuffles; afterwards lane L
+                    // holds the sum of column L (fixed order -> deterministic).  Rows past M contribute zero.
+                    float w[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) w[j] = rows_ok ? v[j] : 0.f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; i++) {
+                            const float send = upper ? w[i] : w[i + off];
+                            const float keep = upper ? w[i + off] : w[i];
+                            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    if (nb + lane < p.N) p.colsum_part[(size_t)((m0 / kTcBM) * 4 + q) * p.N + nb + lane] = w[0];
+                }
+                if (rows_ok || use_tma) {
                     if (use_tma) {
                         // Stage the 32 x 32 chunk (thread = row) in the 128B-swizzled layout the store tensor map expects (16-byte piece
                         // j of row r sits at piece j ^ (r & 7): conflict-free per quarter-warp), then one lane issues the bulk tensor
@@ -533,6 +555,33 @@ static int tc_cluster() {      // PPO_B200_TC_CLUSTER=1 disables the 2-CTA multi
     return cl;
 }
 
+// ---- bias gradient of the layer below, from the dX epilogue ------------------------------------------------------------
+// db of layer i - 1 = column sums of the array a dX GEMM of layer i writes.  A separate column-sum pass re-reads that whole
+// [minibatch][width] array (268 MB at width 1024: as long as a GEMM); instead the caller announces where the db slabs go
+// (tc_request_colsum) and the NEXT dX launch reduces every 32 x 32 chunk in its epilogue, then colsum_fold_kernel adds the
+// per-quadrant rows in fixed order, `splits` contiguous groups of them into the `splits` slabs.
+static struct { float* gb = nullptr; size_t stride = 0; int splits = 0; } g_colsum_req;
+void tc_request_colsum(float* gb_part, size_t stride, int splits) { g_colsum_req.gb = gb_part; g_colsum_req.stride = stride; g_colsum_req.splits = splits; }
+bool tc_colsum_pending() { return g_colsum_req.gb != nullptr; }      // true when no dX launch has consumed the request
+
+__global__ void __launch_bounds__(256) colsum_fold_kernel(float* __restrict__ gb_part, size_t stride, const float* __restrict__ part, int n_parts, int N,
+                                                          int per) {
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col >= N) return;
+    const int p0 = blockIdx.y * per, p1 = min(n_parts, p0 + per);
+    float t = 0.f;
+    int q = p0;
+    for (; q + 8 <= p1; q += 8) {
+        float u[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) u[i] = __ldcg(part + (size_t)(q + i) * N + col);
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += u[i];
+    }
+    for (; q < p1; q++) t += __ldcg(part + (size_t)q * N + col);
+    gb_part[(size_t)blockIdx.y * stride + col] = t;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL, bool BF, bool X3>
 static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& talo, const CUtensorMap& tblo, const TcArgs& a_in,
                          dim3 tiles /* (N tiles, M tiles, splits) */) {
@@ -544,6 +593,16 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     TcArgs a = a_in;
     CUtensorMap tc = ta, tc16 = ta;        // placeholders when the store path is off
     a.tma_store = 0;
+    a.colsum_part = nullptr;
+    float* cs_gb = nullptr;
+    size_t cs_stride = 0;
+    int cs_splits = 0, cs_parts = 0;
+    if (EPI == kTcDx && g_colsum_req.gb) {
+        cs_gb = g_colsum_req.gb; cs_stride = g_colsum_req.stride; cs_splits = g_colsum_req.splits;
+        cs_parts = div_up(a.M, kTcBM) * 4;
+        a.colsum_part = static_cast<float*>(scratch(kScratchColsum, (size_t)cs_parts * a.N * sizeof(float)));
+    }
+    if (EPI == kTcDx) g_colsum_req.gb = nullptr;
     if (kStaged && tc_tma_store_enabled() && (a.ldc % 4) == 0 && a.ldc == a.N && ((uintptr_t)a.C & 15) == 0 &&
         (!a.C16 || ((a.ldc % 8) == 0 && ((uintptr_t)a.C16 & 15) == 0))) {
         a.tma_store = 1;
@@ -561,6 +620,8 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     const dim3 grid(clusters * CL, 1, 1);
     if (CL == 1) {
         B200_LAUNCH((tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF, X3>), grid, kTcThreads, smem, ta, tb, tc, tc16, talo, tblo, a);
+        if (cs_gb) B200_LAUNCH(colsum_fold_kernel, dim3(div_up(a.N, 256), cs_splits, 1), 256, 0, cs_gb, cs_stride, a.colsum_part, cs_parts, a.N,
+                               div_up(cs_parts, cs_splits));
         return;
     }
     const char* label = BF ? "(tc_gemm_kernel<bf16>)" : X3 ? "(tc_gemm_kernel<3xtf32>)" : "(tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL>)";
@@ -574,6 +635,8 @@ static void launch_tc_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, A_MN, B_MN, EPI, CL, BF, X3>, ta, tb, tc, tc16, talo, tblo, a));
     ++g_launches;
     if (g_profiling) profile_mark(label, false);
+    if (cs_gb) B200_LAUNCH(colsum_fold_kernel, dim3(div_up(a.N, 256), cs_splits, 1), 256, 0, cs_gb, cs_stride, a.colsum_part, cs_parts, a.N,
+                           div_up(cs_parts, cs_splits));
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool BF>

@@ -154,22 +154,23 @@ def test_tc_x3_backward_weights(L, m, n, l, splits):
     assert e < tol_x3(-(-m // splits))
 
 
-@pytest.mark.parametrize("hidden_act", ["tanh", "relu"])
-def test_mlp_x3_matches_fp32_oracle_at_fp32_tolerance(L, hidden_act):
-    """2x256 net (config 3 shape) through the NeuralNetwork API in the 3xTF32 split mode against the fp32 oracle at the
+@pytest.mark.parametrize("hidden_act,sizes", [("tanh", [17, 256, 256, 6]), ("relu", [17, 256, 256, 6]), ("tanh", [17, 256, 320, 256, 1])])
+def test_mlp_x3_matches_fp32_oracle_at_fp32_tolerance(L, hidden_act, sizes):
+    """2x256 net (config 3 shape; and a 3-hidden-layer net, where the bias gradient of a split layer comes out of the dX epilogue
+    of the split layer above it) through the NeuralNetwork API in the 3xTF32 split mode against the fp32 oracle at the
     fp32 path's own tolerance (1e-5 norm-wise on outputs and on every gradient tensor)."""
-    sizes, acts, m = [17, 256, 256, 6], [hidden_act] * 2 + ["none"], 1024
+    acts, m = [hidden_act] * (len(sizes) - 2) + ["none"], 1024
     cabi.srand(4)
     nn = L.create_neural_network(cabi.int_array(sizes), cabi.cstr_array(acts), len(sizes))
     p = b200.nn_get_params(L, nn)
     rng = np.random.default_rng(0)
-    x, g = rng.standard_normal((m, 17)).astype(f32), rng.standard_normal((m, 6)).astype(f32)
+    x, g = rng.standard_normal((m, 17)).astype(f32), rng.standard_normal((m, sizes[-1])).astype(f32)
     dx, dg = b200.dev(x), b200.dev(g)
     launches0 = L.ppo_b200_launch_count()
     L.ppo_b200_set_matmul_precision(3)
     try:
         L.forward_propagation_cuda(nn, dx.fp(), m)
-        y = b200.d2h(L, nn.contents.d_output, (m, 6))
+        y = b200.d2h(L, nn.contents.d_output, (m, sizes[-1]))
         L.backward_propagation_cuda(nn, dg.fp(), m)
         grads = b200.nn_get_device_grads(L, nn)
     finally:
@@ -181,8 +182,8 @@ def test_mlp_x3_matches_fp32_oracle_at_fp32_tolerance(L, hidden_act):
         for cnt in (sizes[i] * sizes[i + 1], sizes[i + 1]):
             per.append(nerr(grads[o:o + cnt], g_o[o:o + cnt]))
             o += cnt
-    print("3xTF32 2x256 %s (m=%d): output err %.2e, per-tensor gradient errors %s, launches %d"
-          % (hidden_act, m, nerr(y, y_o), ["%.1e" % e for e in per], L.ppo_b200_launch_count() - launches0))
+    print("3xTF32 %s %s (m=%d): output err %.2e, per-tensor gradient errors %s, launches %d"
+          % (sizes, hidden_act, m, nerr(y, y_o), ["%.1e" % e for e in per], L.ppo_b200_launch_count() - launches0))
     assert nerr(y, y_o) < 1e-5 and max(per) < 1e-5
     L.free_neural_network(nn)
 
