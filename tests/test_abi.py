@@ -42,6 +42,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert exported - names == set(), sorted(exported - names)
 
 
+def test_packed_row_width_is_whole_sectors():
+    """Host-side layout rule of the row-packed gather mirror (no device needed): a row holds S + A + 3 floats rounded up to
+    whole 32-byte sectors."""
+    lib = b200.lib()
+    for S, A in [(3, 1), (17, 6), (1, 1), (24, 4), (100, 25), (5, 0)]:
+        pw = lib.ppo_b200_packed_row_floats(S, A)
+        assert pw % 8 == 0 and S + A + 3 <= pw < S + A + 3 + 8
+
+
 def test_struct_layouts_match_reference_abi():
     """sizeof/offsetof of the public structs, as compiled from include/ppo_b200.h by gcc, must equal
     the ctypes mirror of the REFERENCE headers (tests/cabi.py)."""
