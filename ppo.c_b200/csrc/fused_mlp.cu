@@ -1,20 +1,23 @@
-// fused_mlp.cu — the small-net fast path (SURVEY.md §8 rows a7+a9..a14 in two launches per minibatch).
+// fused_mlp.cu — the small-net fast path (SURVEY.md §8 rows a6/a7 + a9..a14, (e)).
 //
-// For the reference-width actor/critic nets (every layer width <= 128: 2x64, the reference's default 2x128) one
-// minibatch update is
-//   fused_tile64_kernel   gather rows by permutation index -> forward through ALL layers -> fused loss
-//                         head (MSE, or Gaussian log-prob + PPO-clip surrogate) -> backward through
-//                         all layers -> this CTA's partial gradient slab.  Weights are staged ONCE per
-//                         CTA in shared memory, activations never leave shared memory, nothing but
-//                         the slab is written to HBM.
-//   fused_reduce_adam_kernel  fixed-order sum of the slabs (+ the cross-GPU sum over NVLink peer memory under data
-//                         parallelism) + Adam on the flat parameter vector (+ the log_std vector for the policy) +
-//                         loss accumulation; also refreshes the pre-transposed weight image the next
-//                         fused_tile64_kernel will stage.
-// versus ~14 launches through the layer-wise kernels of gemm.cu/policy.cu/adam.cu (which remain the
-// generic path for wider nets).  The reference does this with ~25 launches, 1-3 blocking D2H reads
-// and 1-2 cudaMallocs per minibatch (src/ppo.cu:495-532).  The two kernels are chained with programmatic
-// dependent launch: the gather prologue of minibatch k+1 overlaps the Adam kernel of minibatch k.
+// For the reference-width actor/critic nets (every layer width <= 128: 2x64, the reference's default 2x128) the update phase
+// runs in PERSISTENT PHASE KERNELS: one cooperative launch executes ALL minibatches of all value epochs (or all policy epochs)
+//   fused_phase_spec64_kernel<ACT>   shape-specialised for S <= 8 -> 64 -> 64 -> 1 (BASELINE.json configs[1]): 128-row tiles, 8 x 8
+//                                    register tiles, compile-time loop bounds
+//   fused_phase_kernel               every other net with widths <= 128 (64-row tile slots, 1 or 2 per CTA)
+// and per minibatch step does  [A] gather rows by permutation index -> forward through ALL layers -> fused loss head (MSE, or
+// Gaussian log-prob + PPO-clip surrogate) -> backward through all layers -> one gradient slab per CTA;  [B] grid barrier;
+// [C] every CTA reduces its slice of the parameter vector over the slabs in fixed order (+ the cross-GPU sum over NVLink peer
+// memory under data parallelism), applies Adam and refreshes its entries of the pre-transposed weight image;  [D] grid barrier;
+// [E] TMA re-stage of the image.  Weights and activations live in shared memory; HBM sees the gathered rows and the slabs.
+//
+// The one-launch-per-minibatch pair the phase kernels grew out of is kept (GAE value forwards, PPO_B200_PERSISTENT=0 A/B runs,
+// data-parallel runs without peer memory):
+//   fused_tile64_kernel       [A] for one minibatch, 64-row tiles
+//   fused_reduce_adam_kernel  [C] for one minibatch, chained with programmatic dependent launch
+// versus ~14 launches through the layer-wise kernels of gemm.cu/policy.cu/adam.cu (which remain the generic path for wider
+// nets).  The reference does this with ~25 launches, 1-3 blocking D2H reads and 1-2 cudaMallocs per minibatch
+// (src/ppo.cu:495-532).
 //
 // Shared-memory layouts (64 rows per CTA, row stride TMP = 68 floats so that TMP % 32 == 4):
 //   activations / gradients  At[feature][TMP]   feature-major: a thread reads 4 consecutive ROWS with
