@@ -1919,7 +1919,10 @@ static int spec64_kind(const FusedPlan& pl, int mb) {
     if (n.sizes[0] > 8 || n.sizes[1] != 64 || n.sizes[2] != 64 || n.sizes[3] != 1) return 0;
     if (n.acts[0] != n.acts[1] || (n.acts[0] != kActTanh && n.acts[0] != kActRelu)) return 0;
     if (n.ldw[0] != kS64LDW || n.ldw[1] != kS64LDW || n.ldw[2] != 8) return 0;
-    if (div_up(mb, kT64TM) <= num_sms()) return 0;
+    // the 128-row tiles pay off when they fill the machine; between one tile and a full wave of 64-row tiles the generic kernel
+    // has more CTAs to spread over.  A minibatch of <= 64 rows (the reference's default, src/main.c:36) is one CTA either way,
+    // and the specialised code is the faster single tile.
+    if (mb > kT64TM && div_up(mb, kT64TM) <= num_sms()) return 0;
     if ((size_t)(n.img_floats + kS64Floats) * sizeof(float) > 220 * 1024) return 0;
     return n.acts[0];
 }
