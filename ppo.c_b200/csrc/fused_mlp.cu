@@ -1847,7 +1847,8 @@ bool fused_minibatch_update(NeuralNetwork* nn, GaussianPolicy* policy, Adam* ada
     a.epsilon = epsilon; a.ent_coeff = ent_coeff;
     a.partials = nd->partials; a.slab = slab;
     const bool image_clean = nd->image && !nd->image_dirty && nd->image_floats == pl.net.img_floats;
-    const bool pdl = pdl_enabled() && pl.kind == 1 && !reduced_out;
+    // no dependent-launch overlap while per-kernel event pairs are being recorded: overlapping pairs would not add up to the step
+    const bool pdl = pdl_enabled() && !g_profiling && pl.kind == 1 && !reduced_out;
     launch_fused(nd, pl, a, pdl && chained && image_clean);
     nd->last_splits = blocks;
 
