@@ -163,10 +163,8 @@ def write_readme(tag, table):
         lines.append("| %s | %d | %.4g | %s | %.3f | %.4g | %s | %s | %s | %s | %s | %s |" % (
             name, n, v, unit, ms, e2e, kern, bound, ("%.4g %s" % (ach, aunit)) if ach else "-", ("%.3f" % frac) if frac else "-",
             ("%.2f" % share) if share else "-", ("%.4g" % cpu) if cpu else "-"))
-    lines.append("")
-    extra = os.path.join(PROF, "NOTES.md")
-    if os.path.exists(extra):
-        lines.append(open(extra).read())
+    lines += ["", "Round-to-round comparison, microbenchmarks, phase timelines and the experiments that were measured and not kept: `NOTES.md`.",
+              "SASS evidence (tcgen05 / TMA mnemonics per kernel): `%s_sass_mnemonics.txt`.  Multi-GPU equivalence logs: `%s_dist_equivalence_*gpu.txt`." % (tag, tag)]
     open(os.path.join(PROF, "README.md"), "w").write("\n".join(lines) + "\n")
 
 
